@@ -1,0 +1,578 @@
+// lpx_bnb.cu — Branch & Bound over simplex relaxations: BranchAndBound.Solve / SolveNode,
+// R/Models/Branch&Bound.cs:30-258.
+//
+// GPU node pool: every LP relaxation (the ~100 % hot spot, Branch&Bound.cs:57,148) is a node
+// descriptor "base problem + unit rows"; all open nodes of all instances of a batch whose
+// relaxations are not known yet are solved in ONE launch of the per-CTA kernels (lpx_cta.cuh),
+// primal and dual nodes mixed.  A relaxation is a pure function of its node, so nodes are
+// evaluated speculatively (both children at once) and then COMMITTED ON THE HOST IN THE
+// REFERENCE'S ORDER (depth-first, ceil child first), which keeps incumbents, pruning decisions
+// and node numbering identical to the recursive C# code.
+//
+// Reference semantics kept on purpose: a child with a '>=' row is routed to Dual
+// Simplex, whose result has no Solution/Tableau, so SolveNode rejects it ("Invalid Simplex
+// result").  It is still solved (it is a _solver.Solve call and its tableaux are part of the
+// iteration log) but never branches.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <vector>
+
+#include "lpx_cta.cuh"
+#include "lpx_runtime.hpp"
+#include "lpx_stream.hpp"
+
+namespace lpx {
+namespace {
+
+const double BB_EPS = 1e-6;  // BranchAndBound.EPS  (Branch&Bound.cs:24)
+const int BB_MAX_DEPTH = 200;  // BranchAndBound.MaxDepth (Branch&Bound.cs:25)
+
+struct Extra {
+    int var, rel;
+    double rhs;
+};
+
+struct Node {
+    int inst = 0;
+    int depth = 0;
+    int parent_rec = -1;
+    bool ceil_child = false;
+    bool is_root_lp = false;
+    std::vector<int> id_path;
+    std::vector<Extra> extras;  // all unit rows from the root down to this node
+    int mode = 0;               // 0 primal, 1 dual
+    // evaluation
+    bool evaluated = false;
+    int lp_status = 0, n_pivots = 0, silent = 0;
+    double z = 0;
+    std::vector<double> x;
+    std::vector<int> pivots;
+    std::vector<double> history;
+    int n_history = 0;
+};
+
+struct Instance {
+    std::vector<std::unique_ptr<Node>> stack;  // back() is solved next
+    int counter = 1;                           // _subProblemCounter
+    double best = -std::numeric_limits<double>::infinity();
+    bool have_best = false;
+    std::vector<double> best_x;
+    int records = 0;
+    long long lp_pivots = 0;
+    int root_status = 0;
+    bool finished = false;
+};
+
+// Math.Round(double): ties to even
+inline double round_even(double v) { return std::nearbyint(v); }
+
+bool is_integral(const std::vector<double>& x) {
+    for (double v : x)
+        if (std::fabs(v - round_even(v)) > BB_EPS) return false;
+    return true;
+}
+
+struct BaseProblem {
+    int m, n;
+    const double* A;
+    const int* rel;
+    const double* b;
+};
+
+// BranchAndBound.IsFeasible (Branch&Bound.cs:276-294): row sums in index order, 1e-6 slack.
+bool is_feasible(const std::vector<double>& x, const BaseProblem& bp, const std::vector<Extra>& extras) {
+    const int n = bp.n;
+    for (int r = 0; r < bp.m; r++) {
+        const double* a = bp.A + (size_t)r * n;
+        double sum = 0;
+        for (int i = 0; i < n; i++) sum += a[i] * x[i];
+        const int rl = bp.rel ? bp.rel[r] : 0;
+        if (rl == 0 && sum > bp.b[r] + BB_EPS) return false;
+        if (rl == 1 && sum < bp.b[r] - BB_EPS) return false;
+        if (rl == 2 && std::fabs(sum - bp.b[r]) > BB_EPS) return false;
+    }
+    for (const Extra& e : extras) {
+        // unit row: the reference still adds 0*x terms; 0*x is +-0 and does not change a finite sum
+        double sum = 0;
+        for (int i = 0; i < n; i++) sum += (i == e.var ? 1.0 : 0.0) * x[i];
+        if (e.rel == 0 && sum > e.rhs + BB_EPS) return false;
+        if (e.rel == 1 && sum < e.rhs - BB_EPS) return false;
+        if (e.rel == 2 && std::fabs(sum - e.rhs) > BB_EPS) return false;
+    }
+    for (double v : x)
+        if (v < -BB_EPS) return false;
+    return true;
+}
+
+int choose_mode(const BaseProblem& bp, const std::vector<Extra>& extras) {
+    for (int r = 0; r < bp.m; r++)
+        if (bp.rel && (bp.rel[r] == 1 || bp.rel[r] == 2)) return 1;
+    for (const Extra& e : extras)
+        if (e.rel == 1 || e.rel == 2) return 1;
+    return 0;
+}
+
+int expanded_rows(int m, const int* rel) {
+    int mm = 0;
+    for (int i = 0; i < m; i++) mm += (rel && rel[i] == 2) ? 2 : 1;
+    return mm;
+}
+
+struct Driver {
+    int count, m, n, sense, mm;
+    const double *A, *rel_unused = nullptr, *b, *c;
+    const int* rel;
+    lpx_options opt;
+    int flags;
+    lpx_bnb_node_fn on_node;
+    void* user;
+    std::vector<Instance> inst;
+    // device copies of the base problems
+    double *dA = nullptr, *db = nullptr, *dc = nullptr;
+    int* drel = nullptr;
+
+    BaseProblem base(int k) const { return BaseProblem{m, n, A + (size_t)k * m * n, rel, b + (size_t)k * m}; }
+
+    // ---- GPU evaluation of a list of nodes ---------------------------------------------------
+    int evaluate(std::vector<Node*>& nodes, bool want_history) {
+        if (nodes.empty()) return LPX_OK;
+        Runtime& r = rt();
+        // split by whether the node tableau fits in shared memory
+        std::vector<Node*> group[2];
+        for (Node* nd : nodes) {
+            const int rows = mm + (int)nd->extras.size() + 1, width = n + rows;
+            group[cta_fits_smem(rows, width) ? 0 : 1].push_back(nd);
+        }
+        for (int g = 0; g < 2; g++) {
+            std::vector<Node*>& G = group[g];
+            if (G.empty()) continue;
+            const bool want_piv = on_node != nullptr;
+            const int pivots_cap = want_piv ? std::min(opt.max_iterations + 100, 4096) : 0;
+            if (!want_history) {
+                int rc = launch_group(G, 0, G.size(), pivots_cap, 0);
+                if (rc != LPX_OK) return rc;
+            } else {
+                // pass 1 sizes the histories, pass 2 re-solves in slices under a memory budget
+                int rc = launch_group(G, 0, G.size(), pivots_cap, 0);
+                if (rc != LPX_OK) return rc;
+                const size_t budget = (size_t)1 << 30;
+                size_t lo = 0;
+                while (lo < G.size()) {
+                    size_t hi = lo, bytes = 0;
+                    int cap = 0, max_rows = 0;
+                    while (hi < G.size()) {
+                        const int rows = mm + (int)G[hi]->extras.size() + 1;
+                        const int need = G[hi]->n_pivots - G[hi]->silent + 1;
+                        const int ncap = std::max(cap, need), nrows = std::max(max_rows, rows);
+                        const size_t nb = (size_t)(hi - lo + 1) * ncap * nrows * (n + nrows) * 8;
+                        if (hi > lo && nb > budget) break;
+                        cap = ncap;
+                        max_rows = nrows;
+                        bytes = nb;
+                        hi++;
+                    }
+                    (void)bytes;
+                    rc = launch_group(G, lo, hi, pivots_cap, cap);
+                    if (rc != LPX_OK) return rc;
+                    lo = hi;
+                }
+            }
+        }
+        (void)r;
+        return LPX_OK;
+    }
+
+    int launch_group(std::vector<Node*>& G, size_t lo, size_t hi, int pivots_cap, int history_cap) {
+        Runtime& r = rt();
+        const int cnt = (int)(hi - lo);
+        int max_extra = 0;
+        size_t total_extra = 0;
+        for (size_t k = lo; k < hi; k++) {
+            max_extra = std::max(max_extra, (int)G[k]->extras.size());
+            total_extra += G[k]->extras.size();
+        }
+        const int max_rows = mm + max_extra + 1, max_width = n + max_rows;
+        const size_t tsize = (size_t)max_rows * max_width;
+
+        // host staging of descriptors
+        int* h_inst = ws_pin_as<int>(WS_NODE_INST, cnt);
+        int* h_off = ws_pin_as<int>(WS_NODE_OFF, cnt);
+        int* h_cnt = ws_pin_as<int>(WS_NODE_CNT, cnt);
+        int* h_mode = ws_pin_as<int>(WS_NODE_MODE, cnt);
+        int* h_var = ws_pin_as<int>(WS_EX_VAR, total_extra + 1);
+        int* h_rel = ws_pin_as<int>(WS_EX_REL, total_extra + 1);
+        double* h_rhs = ws_pin_as<double>(WS_EX_RHS, total_extra + 1);
+        int* d_inst = ws_dev_as<int>(WS_NODE_INST, cnt);
+        int* d_off = ws_dev_as<int>(WS_NODE_OFF, cnt);
+        int* d_cnt = ws_dev_as<int>(WS_NODE_CNT, cnt);
+        int* d_mode = ws_dev_as<int>(WS_NODE_MODE, cnt);
+        int* d_var = ws_dev_as<int>(WS_EX_VAR, total_extra + 1);
+        int* d_rel = ws_dev_as<int>(WS_EX_REL, total_extra + 1);
+        double* d_rhs = ws_dev_as<double>(WS_EX_RHS, total_extra + 1);
+        int* d_stat = ws_dev_as<int>(WS_STATUS, (size_t)cnt * 4);
+        double* d_x = ws_dev_as<double>(WS_X, (size_t)cnt * n);
+        double* d_z = ws_dev_as<double>(WS_Z, cnt);
+        int* d_piv = pivots_cap ? ws_dev_as<int>(WS_PIVOTS, (size_t)cnt * pivots_cap * 2) : nullptr;
+        double* d_hist = history_cap ? ws_dev_as<double>(WS_HISTORY, (size_t)cnt * history_cap * tsize) : nullptr;
+        const bool fits = cta_fits_smem(max_rows, max_width);
+        double* d_scratch = fits ? nullptr : ws_dev_as<double>(WS_SCRATCH, (size_t)cnt * tsize);
+        int* h_stat = ws_pin_as<int>(WS_STATUS, (size_t)cnt * 4);
+        double* h_x = ws_pin_as<double>(WS_X, (size_t)cnt * n);
+        double* h_z = ws_pin_as<double>(WS_Z, cnt);
+        if (!h_inst || !h_off || !h_cnt || !h_mode || !h_var || !h_rel || !h_rhs || !d_inst || !d_off || !d_cnt ||
+            !d_mode || !d_var || !d_rel || !d_rhs || !d_stat || !d_x || !d_z || (pivots_cap && !d_piv) ||
+            (history_cap && !d_hist) || (!fits && !d_scratch) || !h_stat || !h_x || !h_z)
+            return LPX_E_CUDA;
+
+        size_t off = 0;
+        for (int k = 0; k < cnt; k++) {
+            Node* nd = G[lo + k];
+            h_inst[k] = nd->inst;
+            h_off[k] = (int)off;
+            h_cnt[k] = (int)nd->extras.size();
+            h_mode[k] = nd->mode;
+            for (const Extra& e : nd->extras) {
+                h_var[off] = e.var;
+                h_rel[off] = e.rel;
+                h_rhs[off] = e.rhs;
+                off++;
+            }
+        }
+        cudaStream_t s = r.stream;
+        LPX_CUDA(cudaMemcpyAsync(d_inst, h_inst, (size_t)cnt * 4, cudaMemcpyHostToDevice, s));
+        LPX_CUDA(cudaMemcpyAsync(d_off, h_off, (size_t)cnt * 4, cudaMemcpyHostToDevice, s));
+        LPX_CUDA(cudaMemcpyAsync(d_cnt, h_cnt, (size_t)cnt * 4, cudaMemcpyHostToDevice, s));
+        LPX_CUDA(cudaMemcpyAsync(d_mode, h_mode, (size_t)cnt * 4, cudaMemcpyHostToDevice, s));
+        if (total_extra) {
+            LPX_CUDA(cudaMemcpyAsync(d_var, h_var, total_extra * 4, cudaMemcpyHostToDevice, s));
+            LPX_CUDA(cudaMemcpyAsync(d_rel, h_rel, total_extra * 4, cudaMemcpyHostToDevice, s));
+            LPX_CUDA(cudaMemcpyAsync(d_rhs, h_rhs, total_extra * 8, cudaMemcpyHostToDevice, s));
+        }
+
+        CtaBatch B;
+        std::memset(&B, 0, sizeof B);
+        B.A = dA;
+        B.b = db;
+        B.c = dc;
+        B.rel = rel ? drel : nullptr;
+        B.strideA = (long long)m * n;
+        B.strideB = m;
+        B.strideC = n;
+        B.m_in = m;
+        B.n = n;
+        B.sense = sense;
+        B.m_base = mm;
+        B.node_inst = d_inst;
+        B.node_extra_off = d_off;
+        B.node_extra_cnt = d_cnt;
+        B.node_mode = d_mode;
+        B.ex_var = d_var;
+        B.ex_rel = d_rel;
+        B.ex_rhs = d_rhs;
+        B.max_iter = opt.max_iterations;
+        B.max_rows = max_rows;
+        B.max_width = max_width;
+        B.scratch = d_scratch;
+        B.scratch_stride = (long long)tsize;
+        B.status = d_stat;
+        B.n_pivots = d_stat + cnt;
+        B.silent = d_stat + 2 * cnt;
+        B.n_history = d_stat + 3 * cnt;
+        B.pivots = d_piv;
+        B.pivots_cap = pivots_cap;
+        B.x = d_x;
+        B.z = d_z;
+        B.history = d_hist;
+        B.history_stride = (long long)((size_t)history_cap * tsize);
+        B.history_cap = history_cap;
+        int rc = cta_launch(B, cnt, opt.kernel == LPX_KERNEL_CTA_GLOBAL ? LPX_KERNEL_CTA_GLOBAL : LPX_KERNEL_AUTO,
+                            opt.threads, s, nullptr);
+        if (rc != LPX_OK) return rc;
+        LPX_CUDA(cudaMemcpyAsync(h_stat, d_stat, (size_t)cnt * 16, cudaMemcpyDeviceToHost, s));
+        LPX_CUDA(cudaMemcpyAsync(h_x, d_x, (size_t)cnt * n * 8, cudaMemcpyDeviceToHost, s));
+        LPX_CUDA(cudaMemcpyAsync(h_z, d_z, (size_t)cnt * 8, cudaMemcpyDeviceToHost, s));
+        LPX_CUDA(cudaStreamSynchronize(s));
+        for (int k = 0; k < cnt; k++) {
+            Node* nd = G[lo + k];
+            nd->evaluated = true;
+            nd->lp_status = h_stat[k];
+            nd->n_pivots = h_stat[cnt + k];
+            nd->silent = h_stat[2 * cnt + k];
+            nd->z = h_z[k];
+            nd->x.assign(h_x + (size_t)k * n, h_x + (size_t)(k + 1) * n);
+            if (pivots_cap) {
+                const int np = std::min(nd->n_pivots, pivots_cap);
+                nd->pivots.resize((size_t)np * 2);
+                if (np)
+                    LPX_CUDA(cudaMemcpy(nd->pivots.data(), d_piv + (size_t)k * pivots_cap * 2, (size_t)np * 8,
+                                        cudaMemcpyDeviceToHost));
+            }
+            if (history_cap) {
+                const int rows = mm + (int)nd->extras.size() + 1, width = n + rows;
+                const int nh = h_stat[3 * cnt + k];
+                nd->n_history = nh;
+                nd->history.resize((size_t)nh * rows * width);
+                if (nh)
+                    LPX_CUDA(cudaMemcpy(nd->history.data(), d_hist + (size_t)k * history_cap * tsize,
+                                        nd->history.size() * 8, cudaMemcpyDeviceToHost));
+            }
+        }
+        return LPX_OK;
+    }
+
+    // ---- commit logic -------------------------------------------------------------------------
+    void emit(Instance& I, const Node& nd, int outcome, int branch_var, int floor_val, int ceil_val, int rec_index) {
+        if (!on_node) return;
+        lpx_bnb_node rec;
+        std::memset(&rec, 0, sizeof rec);
+        rec.index = rec_index;
+        rec.depth = nd.depth;
+        rec.parent = nd.parent_rec;
+        rec.is_ceil_child = nd.ceil_child ? 1 : 0;
+        rec.id_path_len = (int)nd.id_path.size();
+        rec.id_path = nd.id_path.data();
+        rec.bound_var = nd.extras.empty() || nd.is_root_lp ? -1 : nd.extras.back().var;
+        rec.bound_val = nd.extras.empty() ? 0 : (int)nd.extras.back().rhs;
+        rec.algo = nd.mode;
+        rec.lp_status = nd.lp_status;
+        rec.outcome = outcome;
+        rec.n_pivots = nd.n_pivots;
+        rec.silent_pivots = nd.silent;
+        rec.pivots = nd.pivots.data();
+        rec.rows = mm + (int)nd.extras.size() + 1;
+        rec.cols = n + rec.rows;
+        rec.z = nd.z;
+        rec.x = nd.x.data();
+        rec.branch_var = branch_var;
+        rec.floor_val = floor_val;
+        rec.ceil_val = ceil_val;
+        rec.n_history = nd.n_history;
+        rec.history = nd.history.data();
+        set_bnb_instance(nd.inst);
+        on_node(&rec, user);
+        (void)I;
+    }
+
+    // One SolveNode body (Branch&Bound.cs:128-258) for an evaluated node.
+    void commit_node(Instance& I, std::unique_ptr<Node> ndp) {
+        Node& nd = *ndp;
+        const int rec = I.records++;
+        if (nd.depth > BB_MAX_DEPTH) {
+            emit(I, nd, LPX_BNB_DEPTH, -1, 0, 0, rec);
+            return;
+        }
+        I.lp_pivots += nd.n_pivots;
+        if (nd.lp_status < 0) {  // the solve threw
+            emit(I, nd, LPX_BNB_ERROR, -1, 0, 0, rec);
+            return;
+        }
+        if (nd.mode == 1) {  // Dual Simplex returns no Solution/Tableau/Basis/VarNames
+            emit(I, nd, LPX_BNB_INVALID, -1, 0, 0, rec);
+            return;
+        }
+        const std::vector<double>& x = nd.x;
+        const double z = nd.z;
+        const BaseProblem bp = base(nd.inst);
+        if (!is_feasible(x, bp, nd.extras)) {
+            emit(I, nd, LPX_BNB_INFEASIBLE, -1, 0, 0, rec);
+            return;
+        }
+        if (z <= I.best + BB_EPS) {
+            emit(I, nd, LPX_BNB_PRUNED, -1, 0, 0, rec);
+            return;
+        }
+        if (is_integral(x)) {
+            I.best = z;
+            I.have_best = true;
+            I.best_x.resize(n);
+            for (int i = 0; i < n; i++) I.best_x[i] = round_even(x[i]);
+            emit(I, nd, LPX_BNB_INCUMBENT, -1, 0, 0, rec);
+            return;
+        }
+        int frac_index = -1;
+        double min_dist = std::numeric_limits<double>::max();
+        for (int i = 0; i < n; i++) {
+            const double frac = x[i] - std::floor(x[i]);
+            if (frac > BB_EPS && (1 - frac) > BB_EPS) {
+                const double dist = std::fabs(frac - 0.5);
+                if (dist < min_dist || (dist == min_dist && i < frac_index)) {
+                    min_dist = dist;
+                    frac_index = i;
+                }
+            }
+        }
+        if (frac_index == -1) {
+            emit(I, nd, LPX_BNB_NOFRAC, -1, 0, 0, rec);
+            return;
+        }
+        const int floor_val = (int)std::floor(x[frac_index]);
+        const int ceil_val = (int)std::ceil(x[frac_index]);
+        emit(I, nd, LPX_BNB_BRANCHED, frac_index, floor_val, ceil_val, rec);
+
+        auto child = [&](bool ceil_side, int id) {
+            std::unique_ptr<Node> ch(new Node());
+            ch->inst = nd.inst;
+            ch->depth = nd.depth + 1;
+            ch->parent_rec = rec;
+            ch->ceil_child = ceil_side;
+            ch->id_path = nd.id_path;
+            ch->id_path.push_back(id);
+            ch->extras = nd.extras;
+            ch->extras.push_back(Extra{frac_index, ceil_side ? 1 : 0, (double)(ceil_side ? ceil_val : floor_val)});
+            ch->mode = choose_mode(bp, ch->extras);
+            if (ch->depth > BB_MAX_DEPTH) ch->evaluated = true;  // pruned without an LP
+            return ch;
+        };
+        const int ceil_id = I.counter, floor_id = I.counter + 1;
+        I.counter += 2;
+        // SolveNode(right) then SolveNode(left): the stack pops the ceil child first
+        I.stack.push_back(child(false, floor_id));
+        I.stack.push_back(child(true, ceil_id));
+    }
+
+    // Root LP of BranchAndBound.Solve (Branch&Bound.cs:53-95).
+    void commit_root_lp(Instance& I, std::unique_ptr<Node> ndp) {
+        Node& nd = *ndp;
+        const int rec = I.records++;
+        I.lp_pivots += nd.n_pivots;
+        I.root_status = nd.lp_status;
+        if (nd.lp_status < 0) {
+            emit(I, nd, LPX_BNB_ERROR, -1, 0, 0, rec);
+            I.finished = true;
+            return;
+        }
+        if (nd.mode == 1) {
+            emit(I, nd, LPX_BNB_INVALID, -1, 0, 0, rec);
+            I.finished = true;
+            return;
+        }
+        const BaseProblem bp = base(nd.inst);
+        if (is_integral(nd.x) && is_feasible(nd.x, bp, nd.extras)) {
+            I.best = nd.z;
+            I.have_best = true;
+            I.best_x.resize(n);
+            for (int i = 0; i < n; i++) I.best_x[i] = round_even(nd.x[i]);
+            emit(I, nd, LPX_BNB_INCUMBENT, -1, 0, 0, rec);
+            I.finished = true;
+            return;
+        }
+        emit(I, nd, LPX_BNB_BRANCHED, -1, 0, 0, rec);
+        // SolveNode(problem, "Root Problem", "", ..., 0): the root LP is solved a second time
+        std::unique_ptr<Node> again(new Node());
+        again->inst = nd.inst;
+        again->depth = 0;
+        again->parent_rec = rec;
+        again->mode = nd.mode;
+        I.stack.push_back(std::move(again));
+    }
+
+    int run() {
+        Runtime& r = rt();
+        // base problems to the device once
+        dA = ws_dev_as<double>(WS_A, (size_t)count * m * n);
+        db = ws_dev_as<double>(WS_B, (size_t)count * m);
+        dc = ws_dev_as<double>(WS_C, (size_t)count * n);
+        drel = ws_dev_as<int>(WS_REL, m);
+        if (!dA || !db || !dc || !drel) return LPX_E_CUDA;
+        LPX_CUDA(cudaMemcpyAsync(dA, A, (size_t)count * m * n * 8, cudaMemcpyHostToDevice, r.stream));
+        LPX_CUDA(cudaMemcpyAsync(db, b, (size_t)count * m * 8, cudaMemcpyHostToDevice, r.stream));
+        LPX_CUDA(cudaMemcpyAsync(dc, c, (size_t)count * n * 8, cudaMemcpyHostToDevice, r.stream));
+        if (rel) LPX_CUDA(cudaMemcpyAsync(drel, rel, (size_t)m * 4, cudaMemcpyHostToDevice, r.stream));
+
+        inst.resize(count);
+        for (int k = 0; k < count; k++) {
+            std::unique_ptr<Node> root(new Node());
+            root->inst = k;
+            root->is_root_lp = true;
+            root->mode = choose_mode(base(k), root->extras);
+            inst[k].stack.push_back(std::move(root));
+        }
+        const bool want_history = (flags & LPX_BNB_WANT_HISTORY) && on_node;
+        while (true) {
+            std::vector<Node*> todo;
+            for (Instance& I : inst)
+                if (!I.finished)
+                    for (auto& nd : I.stack)
+                        if (!nd->evaluated) todo.push_back(nd.get());
+            if (todo.empty()) break;
+            int rc = evaluate(todo, want_history);
+            if (rc != LPX_OK) return rc;
+            for (Instance& I : inst) {
+                while (!I.finished && !I.stack.empty() && I.stack.back()->evaluated) {
+                    std::unique_ptr<Node> nd = std::move(I.stack.back());
+                    I.stack.pop_back();
+                    if (nd->is_root_lp) commit_root_lp(I, std::move(nd));
+                    else commit_node(I, std::move(nd));
+                }
+                if (I.stack.empty()) I.finished = true;
+            }
+        }
+        return LPX_OK;
+    }
+};
+
+}  // namespace
+}  // namespace lpx
+
+using namespace lpx;
+
+extern "C" {
+
+int lpx_bnb_simplex_batched(int count, int m, int n, int sense, const double* A, const int* rel, const double* b,
+                            const double* c, const lpx_options* opt, int flags, int* found, double* best_z,
+                            double* best_x, int* n_nodes, long long* n_lp_pivots, int* root_status,
+                            lpx_bnb_node_fn on_node, void* user) {
+    if (count < 1 || m < 1 || n < 1 || !A || !b || !c || (sense != 0 && sense != 1)) {
+        set_error("lpx_bnb_simplex: bad arguments");
+        return LPX_E_BAD_ARGS;
+    }
+    if (rel)
+        for (int i = 0; i < m; i++)
+            if (rel[i] < 0 || rel[i] > 2) {
+                set_error("lpx_bnb_simplex: rel[i] must be 0, 1 or 2");
+                return LPX_E_BAD_ARGS;
+            }
+    int rc = ensure_device();
+    if (rc != LPX_OK) return rc;
+    std::lock_guard<std::recursive_mutex> lk(rt().mu);
+    Driver d;
+    d.count = count;
+    d.m = m;
+    d.n = n;
+    d.sense = sense;
+    d.mm = expanded_rows(m, rel);
+    d.A = A;
+    d.b = b;
+    d.c = c;
+    d.rel = rel;
+    lpx_default_options(&d.opt);
+    if (opt) d.opt = *opt;
+    d.flags = flags;
+    d.on_node = on_node;
+    d.user = user;
+    rc = d.run();
+    if (rc != LPX_OK) return rc;
+    for (int k = 0; k < count; k++) {
+        const Instance& I = d.inst[k];
+        if (found) found[k] = I.have_best ? 1 : 0;
+        if (best_z) best_z[k] = I.best;
+        if (best_x && I.have_best)
+            for (int j = 0; j < n; j++) best_x[(size_t)k * n + j] = I.best_x[j];
+        if (n_nodes) n_nodes[k] = I.records;
+        if (n_lp_pivots) n_lp_pivots[k] = I.lp_pivots;
+        if (root_status) root_status[k] = I.root_status;
+    }
+    return LPX_OK;
+}
+
+int lpx_bnb_simplex(int m, int n, int sense, const double* A, const int* rel, const double* b, const double* c,
+                    const lpx_options* opt, int flags, int* found, double* best_z, double* best_x, int* n_nodes,
+                    long long* n_lp_pivots, int* root_status, lpx_bnb_node_fn on_node, void* user) {
+    return lpx_bnb_simplex_batched(1, m, n, sense, A, rel, b, c, opt, flags, found, best_z, best_x, n_nodes,
+                                   n_lp_pivots, root_status, on_node, user);
+}
+
+}  // extern "C"

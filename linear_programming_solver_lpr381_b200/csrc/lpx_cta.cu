@@ -1,0 +1,374 @@
+// lpx_cta.cu — launcher of the one-CTA-per-tableau kernels and the C-ABI entry points built on
+// them: lpx_primal_solve, lpx_dual_solve, lpx_primal_solve_batched(_dev).
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "lpx_cta.cuh"
+#include "lpx_runtime.hpp"
+#include "lpx_stream.hpp"
+
+namespace lpx {
+
+bool cta_fits_smem(int max_rows, int max_width) {
+    return cta_carve(max_rows, max_width, true).total <= (size_t)max_smem_optin();
+}
+
+template <int THREADS, bool SMEM_T>
+static int launch_variant(const CtaBatch& B, int count, size_t smem, cudaStream_t stream) {
+    auto kfn = cta_simplex_kernel<THREADS, SMEM_T>;
+    LPX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kfn<<<count, THREADS, smem, stream>>>(B);
+    LPX_CUDA(cudaGetLastError());
+    count_launch();
+    return LPX_OK;
+}
+
+int cta_launch(const CtaBatch& B, int count, int kernel_pref, int threads_pref, cudaStream_t stream,
+               bool* used_smem) {
+    if (count <= 0) return LPX_OK;
+    bool smem_T = cta_fits_smem(B.max_rows, B.max_width);
+    if (kernel_pref == LPX_KERNEL_CTA_GLOBAL) smem_T = false;
+    if (kernel_pref == LPX_KERNEL_CTA_SMEM && !smem_T) {
+        set_error("tableau does not fit in shared memory (LPX_KERNEL_CTA_SMEM forced)");
+        return LPX_E_CAPACITY;
+    }
+    if (!smem_T && !B.tableau && !B.scratch) {
+        set_error("internal: global-memory tableau kernel needs scratch");
+        return LPX_E_BAD_ARGS;
+    }
+    const size_t smem = cta_carve(B.max_rows, B.max_width, smem_T).total;
+    if (smem > (size_t)max_smem_optin()) {
+        set_error("problem too wide for the per-CTA kernels (work vectors exceed shared memory)");
+        return LPX_E_CAPACITY;
+    }
+    if (used_smem) *used_smem = smem_T;
+    int threads = threads_pref;
+    if (threads != 128 && threads != 256 && threads != 512) {
+        // narrow tableaux: 256; wide or global-memory ones: 512 for more loads in flight
+        threads = (!smem_T || B.max_width > 256) ? 512 : 256;
+    }
+    if (smem_T) {
+        if (threads == 128) return launch_variant<128, true>(B, count, smem, stream);
+        if (threads == 256) return launch_variant<256, true>(B, count, smem, stream);
+        return launch_variant<512, true>(B, count, smem, stream);
+    }
+    if (threads == 128) return launch_variant<128, false>(B, count, smem, stream);
+    if (threads == 256) return launch_variant<256, false>(B, count, smem, stream);
+    return launch_variant<512, false>(B, count, smem, stream);
+}
+
+static int expanded_rows(int m, const int* rel) {
+    int mm = 0;
+    for (int i = 0; i < m; i++) mm += (rel && rel[i] == 2) ? 2 : 1;
+    return mm;
+}
+
+static int check_problem(int m, int n, int sense, const double* A, const int* rel, const double* b,
+                         const double* c) {
+    if (m < 1 || n < 1 || !A || !b || !c || (sense != 0 && sense != 1)) {
+        set_error("bad arguments: need m >= 1, n >= 1, sense in {0,1}, non-null A, b, c");
+        return LPX_E_BAD_ARGS;
+    }
+    if (rel)
+        for (int i = 0; i < m; i++)
+            if (rel[i] < 0 || rel[i] > 2) {
+                set_error("bad arguments: rel[i] must be 0 (LE), 1 (GE) or 2 (EQ)");
+                return LPX_E_BAD_ARGS;
+            }
+    return LPX_OK;
+}
+
+// One LP through the per-CTA kernels; mode 0 primal / 1 dual.
+static int solve_single_cta(int mode, int m, int n, int sense, const double* A, const int* rel, const double* b,
+                            const double* c, const lpx_options* opt, int* status, int* n_pivots, int* silent,
+                            int* pivots, int pivots_cap, int* basis, double* x, double* z, double* tableau,
+                            double* history, int history_cap) {
+    Runtime& r = rt();
+    const int mm = expanded_rows(m, rel);
+    const int rows = mm + 1, width = n + mm + 1;
+    const size_t tsize = (size_t)rows * width;
+    lpx_options o;
+    lpx_default_options(&o);
+    if (opt) o = *opt;
+    if (pivots_cap < 0) pivots_cap = 0;
+    if (!history) history_cap = 0;
+
+    double* dA = ws_dev_as<double>(WS_A, (size_t)m * n);
+    double* db = ws_dev_as<double>(WS_B, m);
+    double* dc = ws_dev_as<double>(WS_C, n);
+    int* drel = ws_dev_as<int>(WS_REL, m);
+    int* dstat = ws_dev_as<int>(WS_STATUS, 4);
+    int* dpiv = ws_dev_as<int>(WS_PIVOTS, (size_t)std::max(pivots_cap, 1) * 2);
+    int* dbasis = ws_dev_as<int>(WS_BASIS, mm);
+    double* dx = ws_dev_as<double>(WS_X, n);
+    double* dz = ws_dev_as<double>(WS_Z, 1);
+    double* dT = ws_dev_as<double>(WS_TABLEAU, tsize);
+    double* dH = history_cap ? ws_dev_as<double>(WS_HISTORY, tsize * history_cap) : nullptr;
+    if (!dA || !db || !dc || !drel || !dstat || !dpiv || !dbasis || !dx || !dz || !dT || (history_cap && !dH))
+        return LPX_E_CUDA;
+
+    cudaStream_t s = r.stream;
+    LPX_CUDA(cudaMemcpyAsync(dA, A, (size_t)m * n * 8, cudaMemcpyHostToDevice, s));
+    LPX_CUDA(cudaMemcpyAsync(db, b, (size_t)m * 8, cudaMemcpyHostToDevice, s));
+    LPX_CUDA(cudaMemcpyAsync(dc, c, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    if (rel) LPX_CUDA(cudaMemcpyAsync(drel, rel, (size_t)m * 4, cudaMemcpyHostToDevice, s));
+
+    CtaBatch B;
+    std::memset(&B, 0, sizeof B);
+    B.A = dA;
+    B.b = db;
+    B.c = dc;
+    B.rel = rel ? drel : nullptr;
+    B.m_in = m;
+    B.n = n;
+    B.sense = sense;
+    B.m_base = mm;
+    B.mode = mode;
+    B.max_iter = o.max_iterations;
+    B.max_rows = rows;
+    B.max_width = width;
+    B.status = dstat;
+    B.n_pivots = dstat + 1;
+    B.silent = dstat + 2;
+    B.n_history = dstat + 3;
+    B.pivots = pivots_cap ? dpiv : nullptr;
+    B.pivots_cap = pivots_cap;
+    B.basis = dbasis;
+    B.basis_stride = mm;
+    B.x = dx;
+    B.z = dz;
+    B.tableau = dT;
+    B.tableau_stride = (long long)tsize;
+    B.history = dH;
+    B.history_stride = (long long)(tsize * (size_t)history_cap);
+    B.history_cap = history_cap;
+    int rc = cta_launch(B, 1, o.kernel, o.threads, s, nullptr);
+    if (rc != LPX_OK) return rc;
+
+    int hstat[4] = {0, 0, 0, 0};
+    LPX_CUDA(cudaMemcpyAsync(hstat, dstat, sizeof hstat, cudaMemcpyDeviceToHost, s));
+    LPX_CUDA(cudaStreamSynchronize(s));
+    if (status) *status = hstat[0];
+    if (n_pivots) *n_pivots = hstat[1];
+    if (silent) *silent = hstat[2];
+    const bool solved = hstat[0] >= 0 || hstat[0] == LPX_S_ITER_LIMIT;
+    if (pivots && pivots_cap)
+        LPX_CUDA(cudaMemcpyAsync(pivots, dpiv, (size_t)std::min(hstat[1], pivots_cap) * 8, cudaMemcpyDeviceToHost, s));
+    if (solved) {
+        if (basis) LPX_CUDA(cudaMemcpyAsync(basis, dbasis, (size_t)mm * 4, cudaMemcpyDeviceToHost, s));
+        if (x) LPX_CUDA(cudaMemcpyAsync(x, dx, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+        if (z) LPX_CUDA(cudaMemcpyAsync(z, dz, 8, cudaMemcpyDeviceToHost, s));
+        if (tableau) LPX_CUDA(cudaMemcpyAsync(tableau, dT, tsize * 8, cudaMemcpyDeviceToHost, s));
+        if (history && hstat[3] > 0)
+            LPX_CUDA(cudaMemcpyAsync(history, dH, tsize * 8 * (size_t)hstat[3], cudaMemcpyDeviceToHost, s));
+    }
+    LPX_CUDA(cudaStreamSynchronize(s));
+    return LPX_OK;
+}
+
+static void fill_uniform_batch(CtaBatch& B, int m, int n, int sense, int mm, const lpx_options& o) {
+    std::memset(&B, 0, sizeof B);
+    B.m_in = m;
+    B.n = n;
+    B.sense = sense;
+    B.m_base = mm;
+    B.mode = 0;
+    B.max_iter = o.max_iterations;
+    B.max_rows = mm + 1;
+    B.max_width = n + mm + 1;
+    B.strideA = (long long)m * n;
+    B.strideB = m;
+    B.strideC = n;
+    B.basis_stride = mm;
+    B.tableau_stride = (long long)(mm + 1) * (n + mm + 1);
+}
+
+}  // namespace lpx
+
+using namespace lpx;
+
+extern "C" {
+
+int lpx_primal_solve(int m, int n, int sense, const double* A, const int* rel, const double* b, const double* c,
+                     const lpx_options* opt, int* status, int* n_pivots, int* pivots, int pivots_cap, int* basis,
+                     double* x, double* z, double* tableau, double* history, int history_cap) {
+    int rc = check_problem(m, n, sense, A, rel, b, c);
+    if (rc != LPX_OK) return rc;
+    if ((rc = ensure_device()) != LPX_OK) return rc;
+    std::lock_guard<std::recursive_mutex> lk(rt().mu);
+    const int mm = expanded_rows(m, rel);
+    int kernel = opt ? opt->kernel : LPX_KERNEL_AUTO;
+    if (kernel == LPX_KERNEL_AUTO) {
+        // one tableau: the per-CTA kernels win while the tableau is small; past that a single SM
+        // cannot stream it fast enough and the whole-GPU streaming kernels take over.
+        const size_t elems = (size_t)(mm + 1) * (n + mm + 1);
+        kernel = (cta_fits_smem(mm + 1, n + mm + 1) || elems <= (size_t)96 * 1024) ? LPX_KERNEL_CTA_SMEM
+                                                                                    : LPX_KERNEL_STREAM;
+        if (kernel == LPX_KERNEL_CTA_SMEM && !cta_fits_smem(mm + 1, n + mm + 1)) kernel = LPX_KERNEL_CTA_GLOBAL;
+        if (history && history_cap > 0 && kernel == LPX_KERNEL_STREAM) kernel = LPX_KERNEL_CTA_GLOBAL;
+    }
+    if (kernel == LPX_KERNEL_STREAM)
+        return stream_solve_host(m, n, sense, A, rel, b, c, opt, status, n_pivots, pivots, pivots_cap, basis, x, z,
+                                 tableau, history, history_cap);
+    lpx_options o;
+    lpx_default_options(&o);
+    if (opt) o = *opt;
+    o.kernel = kernel;
+    return solve_single_cta(0, m, n, sense, A, rel, b, c, &o, status, n_pivots, nullptr, pivots, pivots_cap, basis, x,
+                            z, tableau, history, history_cap);
+}
+
+int lpx_dual_solve(int m, int n, int sense, const double* A, const int* rel, const double* b, const double* c,
+                   const lpx_options* opt, int* status, int* n_pivots, int* silent_pivots, int* pivots,
+                   int pivots_cap, int* basis, double* x, double* z, double* tableau, double* history,
+                   int history_cap) {
+    int rc = check_problem(m, n, sense, A, rel, b, c);
+    if (rc != LPX_OK) return rc;
+    if ((rc = ensure_device()) != LPX_OK) return rc;
+    std::lock_guard<std::recursive_mutex> lk(rt().mu);
+    lpx_options o;
+    lpx_default_options(&o);
+    if (opt) o = *opt;
+    if (o.kernel == LPX_KERNEL_STREAM) {
+        set_error("lpx_dual_solve runs on the per-CTA kernels only");
+        return LPX_E_BAD_ARGS;
+    }
+    return solve_single_cta(1, m, n, sense, A, rel, b, c, &o, status, n_pivots, silent_pivots, pivots, pivots_cap,
+                            basis, x, z, tableau, history, history_cap);
+}
+
+int lpx_primal_solve_batched_dev(int count, int m, int n, int sense, const double* A, const int* rel,
+                                 const double* b, const double* c, const lpx_options* opt, int* status,
+                                 int* n_pivots, int* basis, double* x, double* z, double* tableau,
+                                 unsigned long long* total_pivots, void* stream) {
+    if (count < 0 || m < 1 || n < 1 || !A || !b || !c || !status || (sense != 0 && sense != 1)) {
+        set_error("lpx_primal_solve_batched_dev: bad arguments");
+        return LPX_E_BAD_ARGS;
+    }
+    int rc = ensure_device();
+    if (rc != LPX_OK) return rc;
+    std::lock_guard<std::recursive_mutex> lk(rt().mu);
+    lpx_options o;
+    lpx_default_options(&o);
+    if (opt) o = *opt;
+    // rel is a device pointer here; the tableau shape needs it on the host
+    int mm = m;
+    if (rel) {
+        std::vector<int> hrel(m);
+        LPX_CUDA(cudaMemcpyAsync(hrel.data(), rel, (size_t)m * 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        LPX_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+        mm = expanded_rows(m, hrel.data());
+    }
+    if (o.kernel == LPX_KERNEL_CTA_REG || (o.kernel == LPX_KERNEL_AUTO && reg_kernel_supports(m, n, mm, rel != nullptr)))
+        return reg_launch_batched(count, m, n, sense, A, b, c, o, status, n_pivots, basis, x, z, tableau, total_pivots,
+                                  (cudaStream_t)stream);
+    CtaBatch B;
+    fill_uniform_batch(B, m, n, sense, mm, o);
+    B.A = A;
+    B.b = b;
+    B.c = c;
+    B.rel = rel;
+    B.status = status;
+    B.n_pivots = n_pivots;
+    B.basis = basis;
+    B.x = x;
+    B.z = z;
+    B.tableau = tableau;
+    B.total_pivots = total_pivots;
+    if (!cta_fits_smem(B.max_rows, B.max_width) || o.kernel == LPX_KERNEL_CTA_GLOBAL) {
+        if (!tableau) {
+            double* sc = ws_dev_as<double>(WS_SCRATCH, (size_t)count * B.tableau_stride);
+            if (!sc) return LPX_E_CUDA;
+            B.scratch = sc;
+            B.scratch_stride = B.tableau_stride;
+        }
+    }
+    return cta_launch(B, count, o.kernel, o.threads, (cudaStream_t)stream, nullptr);
+}
+
+int lpx_primal_solve_batched(int count, int m, int n, int sense, const double* A, const int* rel, const double* b,
+                             const double* c, const lpx_options* opt, int* status, int* n_pivots, int* basis,
+                             double* x, double* z, double* tableau, long long* total_pivots) {
+    if (count < 0 || !status) {
+        set_error("lpx_primal_solve_batched: bad arguments");
+        return LPX_E_BAD_ARGS;
+    }
+    int rc = check_problem(m, n, sense, A, rel, b, c);
+    if (rc != LPX_OK) return rc;
+    if ((rc = ensure_device()) != LPX_OK) return rc;
+    Runtime& r = rt();
+    std::lock_guard<std::recursive_mutex> lk(r.mu);
+    if (total_pivots) *total_pivots = 0;
+    if (count == 0) return LPX_OK;
+    const int mm = expanded_rows(m, rel);
+    const size_t tsize = (size_t)(mm + 1) * (n + mm + 1);
+    const size_t cnt = (size_t)count;
+
+    double* dA = ws_dev_as<double>(WS_A, cnt * m * n);
+    double* db = ws_dev_as<double>(WS_B, cnt * m);
+    double* dc = ws_dev_as<double>(WS_C, cnt * n);
+    int* drel = ws_dev_as<int>(WS_REL, m);
+    int* dstat = ws_dev_as<int>(WS_STATUS, cnt);
+    int* dnp = ws_dev_as<int>(WS_NPIV, cnt);
+    int* dbasis = ws_dev_as<int>(WS_BASIS, cnt * mm);
+    double* dx = ws_dev_as<double>(WS_X, cnt * n);
+    double* dz = ws_dev_as<double>(WS_Z, cnt);
+    double* dT = tableau ? ws_dev_as<double>(WS_TABLEAU, cnt * tsize) : nullptr;
+    unsigned long long* dtot = ws_dev_as<unsigned long long>(WS_TOTAL, 1);
+    if (!dA || !db || !dc || !drel || !dstat || !dnp || !dbasis || !dx || !dz || (tableau && !dT) || !dtot)
+        return LPX_E_CUDA;
+    if (rel) LPX_CUDA(cudaMemcpyAsync(drel, rel, (size_t)m * 4, cudaMemcpyHostToDevice, r.h2d));
+    LPX_CUDA(cudaMemsetAsync(dtot, 0, 8, r.h2d));
+
+    // Three-stage pipeline over chunks of the batch: H2D | solve | D2H on three streams, so that
+    // PCIe traffic in both directions overlaps the kernels.
+    const int chunks = count >= 1024 ? 8 : (count >= 64 ? 4 : 1);
+    std::vector<cudaEvent_t> up(chunks), done(chunks);
+    for (int k = 0; k < chunks; k++) {
+        LPX_CUDA(cudaEventCreateWithFlags(&up[k], cudaEventDisableTiming));
+        LPX_CUDA(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
+    }
+    int result = LPX_OK;
+    for (int k = 0; k < chunks && result == LPX_OK; k++) {
+        const size_t lo = cnt * k / chunks, hi = cnt * (k + 1) / chunks, len = hi - lo;
+        if (len == 0) continue;
+        LPX_CUDA(cudaMemcpyAsync(dA + lo * m * n, A + lo * m * n, len * m * n * 8, cudaMemcpyHostToDevice, r.h2d));
+        LPX_CUDA(cudaMemcpyAsync(db + lo * m, b + lo * m, len * m * 8, cudaMemcpyHostToDevice, r.h2d));
+        LPX_CUDA(cudaMemcpyAsync(dc + lo * n, c + lo * n, len * n * 8, cudaMemcpyHostToDevice, r.h2d));
+        LPX_CUDA(cudaEventRecord(up[k], r.h2d));
+        LPX_CUDA(cudaStreamWaitEvent(r.stream, up[k], 0));
+        result = lpx_primal_solve_batched_dev((int)len, m, n, sense, dA + lo * m * n, rel ? drel : nullptr, db + lo * m,
+                                              dc + lo * n, opt, dstat + lo, dnp + lo, dbasis + lo * mm, dx + lo * n,
+                                              dz + lo, dT ? dT + lo * tsize : nullptr, dtot, r.stream);
+        if (result != LPX_OK) break;
+        LPX_CUDA(cudaEventRecord(done[k], r.stream));
+        LPX_CUDA(cudaStreamWaitEvent(r.d2h, done[k], 0));
+        LPX_CUDA(cudaMemcpyAsync(status + lo, dstat + lo, len * 4, cudaMemcpyDeviceToHost, r.d2h));
+        if (n_pivots) LPX_CUDA(cudaMemcpyAsync(n_pivots + lo, dnp + lo, len * 4, cudaMemcpyDeviceToHost, r.d2h));
+        if (basis)
+            LPX_CUDA(cudaMemcpyAsync(basis + lo * mm, dbasis + lo * mm, len * mm * 4, cudaMemcpyDeviceToHost, r.d2h));
+        if (x) LPX_CUDA(cudaMemcpyAsync(x + lo * n, dx + lo * n, len * n * 8, cudaMemcpyDeviceToHost, r.d2h));
+        if (z) LPX_CUDA(cudaMemcpyAsync(z + lo, dz + lo, len * 8, cudaMemcpyDeviceToHost, r.d2h));
+        if (tableau)
+            LPX_CUDA(cudaMemcpyAsync(tableau + lo * tsize, dT + lo * tsize, len * tsize * 8, cudaMemcpyDeviceToHost,
+                                     r.d2h));
+    }
+    unsigned long long htot = 0;
+    if (result == LPX_OK) {
+        cudaError_t e = cudaStreamSynchronize(r.stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&htot, dtot, 8, cudaMemcpyDeviceToHost, r.d2h);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(r.d2h);
+        if (e != cudaSuccess) result = cuda_fail(e, "batched pipeline sync", __FILE__, __LINE__);
+    } else {
+        cudaDeviceSynchronize();
+    }
+    for (int k = 0; k < chunks; k++) {
+        cudaEventDestroy(up[k]);
+        cudaEventDestroy(done[k]);
+    }
+    if (total_pivots) *total_pivots = (long long)htot;
+    return result;
+}
+
+}  // extern "C"

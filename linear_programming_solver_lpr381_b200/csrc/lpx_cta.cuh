@@ -1,0 +1,417 @@
+// lpx_cta.cuh — one CTA per tableau: the whole simplex solve (build, all pivots, extraction)
+// runs inside one thread block, with the tableau resident in shared memory (SMEM_T) or in
+// global memory (L2/HBM) for shapes that do not fit.
+//
+// Replaces, per tableau, the reference loop R/Models/PrimalSimplex.cs:57-127 (primal) and
+// R/Models/DualSimplex.cs:15-114 (dual), including
+//   ExpandEqualitiesToInequalities  PrimalSimplex.cs:161-177   (row map built in-kernel)
+//   BuildTableau                    PrimalSimplex.cs:179-203
+//   PrepareForTableau               DualSimplex.cs:117-158
+//   ForceDualFeasibility            DualSimplex.cs:195-228
+// Branch & Bound nodes (R/Models/Branch&Bound.cs:233-248) are expressed as "base problem +
+// extra unit rows" so that a batch of nodes of different depths runs in one launch.
+#pragma once
+#include "lpx_common.cuh"
+
+namespace lpx {
+
+struct CtaBatch {
+    // base problems: instance k at A + k*strideA etc.; rel (nullable = all LE) is shared
+    const double* A;
+    const double* b;
+    const double* c;
+    const int* rel;
+    long long strideA, strideB, strideC;
+    int m_in, n, sense;
+    int m_base;  // rows of the base problem after EQ expansion
+    // optional per-problem node descriptors (nullable: problem p == instance p, no extra rows)
+    const int* node_inst;
+    const int* node_extra_off;
+    const int* node_extra_cnt;
+    const int* node_mode;
+    const int* ex_var;
+    const int* ex_rel;
+    const double* ex_rhs;
+    int mode;      // 0 primal, 1 dual (used when node_mode == nullptr)
+    int max_iter;
+    int max_rows, max_width;  // upper bounds over the batch (shared-memory carve, output strides)
+    double* scratch;          // global tableaux when !SMEM_T and tableau == nullptr
+    long long scratch_stride;
+    // outputs, indexed by problem p = blockIdx.x
+    int* status;
+    int* n_pivots;
+    int* silent;
+    int* pivots;  // pivots_cap pairs per problem
+    int pivots_cap;
+    int* basis;  // basis_stride per problem
+    int basis_stride;
+    double* x;  // n per problem
+    double* z;
+    double* tableau;  // compact rows x width per problem (nullable)
+    long long tableau_stride;
+    double* history;  // history_cap compact tableaux per problem (nullable)
+    long long history_stride;
+    int history_cap;
+    int* n_history;
+    unsigned long long* total_pivots;
+};
+
+// Shared-memory carve shared by host (sizing) and device.
+struct CtaCarve {
+    size_t prow, fcol, red, rsrc, rsgn, basis, ctl, T, total;
+};
+__host__ __device__ inline CtaCarve cta_carve(int max_rows, int max_width, bool smem_T) {
+    CtaCarve c;
+    size_t off = 0;
+    c.prow = off;
+    off += (size_t)max_width * 8;
+    c.fcol = off;
+    off += (size_t)max_rows * 8;
+    c.red = off;
+    off += 34 * 16;
+    c.rsrc = off;
+    off += (size_t)max_rows * 4;
+    c.rsgn = off;
+    off += (size_t)max_rows * 4;
+    c.basis = off;
+    off += (size_t)max_rows * 4;
+    c.ctl = off;
+    off += 16 * 4;
+    off = (off + 15) & ~(size_t)15;
+    c.T = off;
+    if (smem_T) off += (size_t)max_rows * max_width * 8;
+    c.total = off;
+    return c;
+}
+
+__device__ __forceinline__ double dneg(double v) {
+    return __longlong_as_double(__double_as_longlong(v) ^ (long long)0x8000000000000000ULL);
+}
+
+// Gauss-Jordan pivot on (l, e): PrimalSimplex.Pivot (PrimalSimplex.cs:245-257).
+// The factor column and the normalised pivot row are staged in shared memory first, so every
+// element sees factor = T[i,e] as it was BEFORE row i changed and the ROUNDED quotient T[l,j]/piv.
+// Rows with factor 0 are updated too (sign-of-zero parity).
+template <int THREADS>
+__device__ __forceinline__ void cta_pivot(double* T, int ld, int rows, int width, int l, int e, double* prow,
+                                          double* fcol) {
+    const int tid = threadIdx.x;
+    const double piv = T[(size_t)l * ld + e];
+    for (int j = tid; j < width; j += THREADS) prow[j] = __ddiv_rn(T[(size_t)l * ld + j], piv);
+    for (int i = tid; i < rows; i += THREADS) fcol[i] = T[(size_t)i * ld + e];
+    __syncthreads();
+    const int cw = (width + 31) & ~31;
+    if (cw >= THREADS) {
+        for (int j = tid; j < width; j += THREADS) {
+            const double pj = prow[j];
+            double* t = T + j;
+#pragma unroll 4
+            for (int i = 0; i < rows; i++, t += ld) {
+                const double cur = *t;
+                *t = (i == l) ? pj : __dsub_rn(cur, __dmul_rn(fcol[i], pj));
+            }
+        }
+    } else {
+        const int G = THREADS / cw;
+        const int g = tid / cw, j = tid - g * cw;
+        if (g < G && j < width) {
+            const double pj = prow[j];
+            double* t = T + (size_t)g * ld + j;
+            const size_t step = (size_t)G * ld;
+#pragma unroll 4
+            for (int i = g; i < rows; i += G, t += step) {
+                const double cur = *t;
+                *t = (i == l) ? pj : __dsub_rn(cur, __dmul_rn(fcol[i], pj));
+            }
+        }
+    }
+    __syncthreads();
+}
+
+template <int THREADS>
+__device__ __forceinline__ void cta_copy_out(double* dst, const double* T, int ld, int rows, int width) {
+    if (ld == width) {
+        const int total = rows * width;
+        for (int k = threadIdx.x; k < total; k += THREADS) dst[k] = T[k];
+    } else {
+        for (int i = 0; i < rows; i++)
+            for (int j = threadIdx.x; j < width; j += THREADS) dst[(size_t)i * width + j] = T[(size_t)i * ld + j];
+    }
+}
+
+template <int THREADS, bool SMEM_T>
+__global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = THREADS / 32;
+    const int p = blockIdx.x;
+
+    const int inst = B.node_inst ? B.node_inst[p] : p;
+    const int nex = B.node_extra_cnt ? B.node_extra_cnt[p] : 0;
+    const int exo = B.node_extra_off ? B.node_extra_off[p] : 0;
+    const int mode = B.node_mode ? B.node_mode[p] : B.mode;
+    const int n = B.n;
+    const int m = B.m_base + nex;
+    const int rows = m + 1, width = n + m + 1, ld = width;
+    const int rhs = width - 1;
+
+    const CtaCarve cv = cta_carve(B.max_rows, B.max_width, SMEM_T);
+    double* prow = reinterpret_cast<double*>(smem_raw + cv.prow);
+    double* fcol = reinterpret_cast<double*>(smem_raw + cv.fcol);
+    ArgMin* red = reinterpret_cast<ArgMin*>(smem_raw + cv.red);
+    int* rsrc = reinterpret_cast<int*>(smem_raw + cv.rsrc);
+    int* rsgn = reinterpret_cast<int*>(smem_raw + cv.rsgn);
+    int* sbasis = reinterpret_cast<int*>(smem_raw + cv.basis);
+    int* ctl = reinterpret_cast<int*>(smem_raw + cv.ctl);
+    double* T;
+    if (SMEM_T) T = reinterpret_cast<double*>(smem_raw + cv.T);
+    else T = B.tableau ? B.tableau + (size_t)p * B.tableau_stride : B.scratch + (size_t)p * B.scratch_stride;
+
+    const double* Ai = B.A + (size_t)inst * B.strideA;
+    const double* bi = B.b + (size_t)inst * B.strideB;
+    const double* ci = B.c + (size_t)inst * B.strideC;
+
+    // ---- row map + the reference's up-front checks (PrimalSimplex.cs:66-77) -------------------
+    if (tid == 0) {
+        int st = LPX_RUNNING, k = 0;
+        for (int r = 0; r < B.m_in + nex; r++) {
+            int rl, src;
+            double bv;
+            if (r < B.m_in) {
+                rl = B.rel ? B.rel[r] : 0;
+                bv = bi[r];
+                src = r;
+            } else {
+                rl = B.ex_rel[exo + r - B.m_in];
+                bv = B.ex_rhs[exo + r - B.m_in];
+                src = -1 - (r - B.m_in);
+            }
+            if (mode == 0) {
+                if (st == LPX_RUNNING) {
+                    if (rl == 1) st = LPX_S_GE_ROW;
+                    else if (bv < -1e-9) st = LPX_S_NEG_RHS;
+                }
+                rsrc[k] = src;
+                rsgn[k] = 0;
+                k++;
+                if (rl == 2) {
+                    rsrc[k] = src;
+                    rsgn[k] = 1;
+                    k++;
+                }
+            } else {
+                if (rl == 2) {
+                    rsrc[k] = src;
+                    rsgn[k] = 0;
+                    k++;
+                    rsrc[k] = src;
+                    rsgn[k] = 1;
+                    k++;
+                } else {
+                    int flip = 0;
+                    if (rl == 1) {
+                        flip ^= 1;
+                        bv = __dmul_rn(bv, -1.0);
+                    }
+                    if (bv < -LPX_EPS) flip ^= 1;
+                    rsrc[k] = src;
+                    rsgn[k] = flip;
+                    k++;
+                }
+            }
+        }
+        ctl[0] = st;
+        ctl[1] = k;  // == m
+    }
+    __syncthreads();
+    int status = ctl[0];
+
+    int n_piv = 0, n_silent = 0, n_hist = 0;
+    int* plog = B.pivots ? B.pivots + (size_t)p * B.pivots_cap * 2 : nullptr;
+    double* hist = B.history ? B.history + (size_t)p * B.history_stride : nullptr;
+    const size_t tsize = (size_t)rows * width;
+
+    if (status == LPX_RUNNING) {
+        // ---- BuildTableau -------------------------------------------------------------------
+        for (int i = warp; i < rows; i += NW) {
+            double* Ti = T + (size_t)i * ld;
+            if (i < m) {
+                const int src = rsrc[i];
+                const bool flip = rsgn[i] != 0;
+                const int xv = src < 0 ? B.ex_var[exo + (-1 - src)] : -1;
+                const double* Ar = src >= 0 ? Ai + (size_t)src * n : nullptr;
+                for (int j = lane; j < width; j += 32) {
+                    double v;
+                    if (j < n) {
+                        v = Ar ? Ar[j] : (j == xv ? 1.0 : 0.0);
+                        v = neg_if(v, flip);
+                    } else if (j == rhs) {
+                        v = src >= 0 ? bi[src] : B.ex_rhs[exo + (-1 - src)];
+                        v = neg_if(v, flip);
+                    } else {
+                        v = (j == n + i) ? 1.0 : 0.0;
+                    }
+                    Ti[j] = v;
+                }
+            } else {
+                for (int j = lane; j < width; j += 32) {
+                    double v = 0.0;
+                    if (j < n) {
+                        double cj = ci[j];
+                        if (B.sense == 1) cj = dneg(cj);  // Min -> Max (PrimalSimplex.cs:62-63)
+                        v = dneg(cj);                     // T[m,j] = -C[j]
+                    }
+                    Ti[j] = v;
+                }
+            }
+        }
+        for (int i = tid; i < m; i += THREADS) sbasis[i] = n + i;
+        __syncthreads();
+
+        const double* zrow = T + (size_t)m * ld;
+
+        if (mode == 1) {
+            // ---- ForceDualFeasibility: <= 100 silent primal pivots, ratio margin 1e-12 -------
+            for (int guard = 0; guard < 100; guard++) {
+                const int e = block_argmin_below<THREADS>(zrow, width - 1, -LPX_EPS, red);
+                if (e < 0) break;
+                if (warp == 0) {
+                    const int l = warp_margin_scan(m, LPX_MARGIN_DUAL, [&](int i, double& r) {
+                        const double a = T[(size_t)i * ld + e];
+                        if (a > LPX_EPS) {
+                            r = __ddiv_rn(T[(size_t)i * ld + rhs], a);
+                            return true;
+                        }
+                        return false;
+                    });
+                    if (lane == 0) ctl[2] = l;
+                }
+                __syncthreads();
+                const int l = ctl[2];
+                if (l < 0) break;
+                cta_pivot<THREADS>(T, ld, rows, width, l, e, prow, fcol);
+                if (tid == 0) {
+                    sbasis[l] = e;
+                    if (plog && n_piv < B.pivots_cap) {
+                        plog[2 * n_piv] = e;
+                        plog[2 * n_piv + 1] = l;
+                    }
+                }
+                n_piv++;
+                n_silent++;
+            }
+        }
+
+        if (hist && n_hist < B.history_cap) {
+            cta_copy_out<THREADS>(hist + (size_t)n_hist * tsize, T, ld, rows, width);
+            n_hist++;
+        }
+
+        int iter = 1;
+        while (true) {
+            if (iter > B.max_iter) {
+                status = LPX_S_ITER_LIMIT;
+                break;
+            }
+            int e, l;
+            if (mode == 0) {
+                // ChooseEntering: most negative z-row entry below -1e-9, lowest index on ties
+                e = block_argmin_below<THREADS>(zrow, width - 1, -LPX_EPS, red);
+                if (e < 0) {
+                    status = LPX_OPTIMAL;
+                    break;
+                }
+                // ChooseLeaving: sequential margin scan over rows with T[i,e] > 1e-9
+                if (warp == 0) {
+                    const int lv = warp_margin_scan(m, LPX_MARGIN_PRIMAL, [&](int i, double& r) {
+                        const double a = T[(size_t)i * ld + e];
+                        if (a > LPX_EPS) {
+                            r = __ddiv_rn(T[(size_t)i * ld + rhs], a);
+                            return true;
+                        }
+                        return false;
+                    });
+                    if (lane == 0) ctl[2] = lv;
+                }
+                __syncthreads();
+                l = ctl[2];
+                if (l < 0) {
+                    status = LPX_UNBOUNDED;
+                    break;
+                }
+            } else {
+                // dual: leaving row = most negative RHS below -1e-9 (DualSimplex.cs:45-55)
+                l = block_argmin_below_strided<THREADS>(T + rhs, (size_t)ld, m, -LPX_EPS, red);
+                if (l < 0) {
+                    status = LPX_OPTIMAL;
+                    break;
+                }
+                // entering column: min z_j / (-a) over a < -1e-9, margin 1e-12 (DualSimplex.cs:76-91)
+                if (warp == 0) {
+                    const double* lrow = T + (size_t)l * ld;
+                    const int ev = warp_margin_scan(width - 1, LPX_MARGIN_DUAL, [&](int j, double& r) {
+                        const double a = lrow[j];
+                        if (a < -LPX_EPS) {
+                            r = __ddiv_rn(zrow[j], dneg(a));
+                            return true;
+                        }
+                        return false;
+                    });
+                    if (lane == 0) ctl[2] = ev;
+                }
+                __syncthreads();
+                e = ctl[2];
+                if (e < 0) {
+                    status = LPX_INFEASIBLE;
+                    break;
+                }
+            }
+            cta_pivot<THREADS>(T, ld, rows, width, l, e, prow, fcol);
+            if (tid == 0) {
+                sbasis[l] = e;
+                if (plog && n_piv < B.pivots_cap) {
+                    plog[2 * n_piv] = e;
+                    plog[2 * n_piv + 1] = l;
+                }
+            }
+            n_piv++;
+            if (hist && n_hist < B.history_cap) {
+                cta_copy_out<THREADS>(hist + (size_t)n_hist * tsize, T, ld, rows, width);
+                n_hist++;
+            }
+            iter++;
+        }
+        __syncthreads();
+
+        // ---- FinalizeReport's numeric part (PrimalSimplex.cs:132-138) -------------------------
+        if (B.basis)
+            for (int i = tid; i < m; i += THREADS) B.basis[(size_t)p * B.basis_stride + i] = sbasis[i];
+        if (B.x) {
+            double* xo = B.x + (size_t)p * n;
+            for (int j = tid; j < n; j += THREADS) xo[j] = 0.0;
+            __syncthreads();
+            if (tid == 0)
+                for (int i = 0; i < m; i++)
+                    if (sbasis[i] < n) xo[sbasis[i]] = T[(size_t)i * ld + rhs];
+        }
+        if (B.z && tid == 0) B.z[p] = T[(size_t)m * ld + rhs];
+        if (B.tableau && (SMEM_T || T != B.tableau + (size_t)p * B.tableau_stride))
+            cta_copy_out<THREADS>(B.tableau + (size_t)p * B.tableau_stride, T, ld, rows, width);
+    }
+
+    if (tid == 0) {
+        B.status[p] = status;
+        if (B.n_pivots) B.n_pivots[p] = n_piv;
+        if (B.silent) B.silent[p] = n_silent;
+        if (B.n_history) B.n_history[p] = n_hist;
+        if (B.total_pivots && n_piv) atomicAdd(B.total_pivots, (unsigned long long)n_piv);
+    }
+}
+
+// Host-side launcher (lpx_cta.cu): picks SMEM_T from the carve size, sets the shared-memory
+// attribute, launches `count` CTAs on `stream`.  scratch must be provided when the tableau does
+// not fit in shared memory and B.tableau is null.
+int cta_launch(const CtaBatch& B, int count, int kernel_pref, int threads_pref, cudaStream_t stream, bool* used_smem);
+bool cta_fits_smem(int max_rows, int max_width);
+
+}  // namespace lpx

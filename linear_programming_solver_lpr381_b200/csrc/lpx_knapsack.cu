@@ -1,0 +1,795 @@
+// lpx_knapsack.cu — best-first Branch & Bound for the 0/1 knapsack:
+// BranchAndBoundKnapsack.Solve, R/Models/BranchAndBoundKnapsack.cs:58-407.
+//
+// The hot function is ComputeRelaxation (:431-491): a greedy fractional bound whose floating
+// point result depends on the ORDER of its additions (fixed-to-1 items in original index order,
+// then undecided items in ratio-rank order).  One warp evaluates one node: the lanes copy the
+// parent's assignment vector into the child's pool slot (coalesced) and stage it in shared
+// memory; lane 0 then performs the two sums in exactly the reference's order.
+//
+// GPU node pool: assignment vectors live in a device pool (n bytes per node).  Each round the
+// host speculates on the top-K heap nodes and asks the device for their subtrees down to depth D
+// (level by level; a level reads its parents' results on the device, no host round trip).
+// Relaxations are pure functions of the node, so the host then COMMITS in the reference's order:
+// its own max-heap with the reference's sift rules (:494-547), left child before right child,
+// incumbent updates exactly where the C# code makes them.  Speculative results that were not
+// consumed stay cached under their heap node.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <queue>
+#include <vector>
+
+#include "lpx_common.cuh"
+#include "lpx_runtime.hpp"
+#include "lpx_stream.hpp"
+
+namespace lpx {
+
+#define KN_EPS 1e-9  // BranchAndBoundKnapsack.EPS (:56)
+
+enum { KF_INFEASIBLE = 1, KF_ALLINT = 2, KF_SKIPPED = 4, KF_EARLY = 8 };
+static const int KN_MAX_CHUNKS = 64;
+static const int KN_CHUNK_SLOTS = 1 << 15;
+
+struct KnIn {
+    int inst;
+    int parent_slot;     // pool slot of the parent's assignment (-1: take it from parent_pending)
+    int parent_pending;  // index in this round's arrays of a parent evaluated in an earlier level
+    int var;             // original index to fix (-1: none = root; -2: from the parent's fractional item)
+    int side;            // value to fix it to
+    int out_slot;
+};
+
+struct KnOut {
+    double bound, weight, frac;
+    int frac_rank, break_rank;
+    int flags, var;
+};
+
+struct KnParams {
+    const double* w_s;   // [inst][n] weight by ratio rank
+    const double* p_s;   // [inst][n] profit by ratio rank
+    const int* orig_s;   // [inst][n] original index by ratio rank
+    const double* w_o;   // [inst][n] weight by original index
+    const double* p_o;   // [inst][n]
+    const double* cap;   // [inst]
+    const double* best;  // [inst] incumbent when the round was planned
+    int n;
+    signed char* chunks[KN_MAX_CHUNKS];
+    const KnIn* in;
+    KnOut* out;
+    int first, count;    // evaluations [first, first+count) form this level
+};
+
+__device__ __forceinline__ signed char* kn_slot(const KnParams& P, int slot) {
+    return P.chunks[slot / KN_CHUNK_SLOTS] + (size_t)(slot % KN_CHUNK_SLOTS) * P.n;
+}
+
+// 8 warps per CTA; dynamic shared memory = 8 * n bytes.
+__global__ void __launch_bounds__(256) knap_eval_kernel(const KnParams P) {
+    extern __shared__ signed char sm_assign[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int idx = blockIdx.x * 8 + warp;
+    if (idx >= P.count) return;
+    const int e = P.first + idx;
+    const KnIn in = P.in[e];
+    const int n = P.n;
+    signed char* sa = sm_assign + (size_t)warp * n;
+    KnOut o;
+    o.bound = o.weight = o.frac = 0.0;
+    o.frac_rank = -1;
+    o.break_rank = n;
+    o.flags = 0;
+    o.var = in.var;
+
+    int parent_slot = in.parent_slot, var = in.var;
+    const double best = P.best[in.inst];
+    if (in.parent_pending >= 0) {
+        const KnOut po = P.out[in.parent_pending];
+        // children are only wanted below a node the reference could push: feasible, fractional,
+        // bound above the incumbent (the incumbent only grows, so a skip stays valid)
+        const bool expandable = !(po.flags & (KF_INFEASIBLE | KF_ALLINT | KF_SKIPPED)) && po.frac_rank >= 0 &&
+                                po.bound > best + KN_EPS;
+        if (!expandable) {
+            o.flags = KF_SKIPPED;
+            if (lane == 0) P.out[e] = o;
+            return;
+        }
+        parent_slot = P.in[in.parent_pending].out_slot;
+        var = P.orig_s[(size_t)in.inst * n + po.frac_rank];
+        o.var = var;
+    }
+    const signed char* src = kn_slot(P, parent_slot);
+    signed char* dst = kn_slot(P, in.out_slot);
+    for (int i = lane; i < n; i += 32) {
+        signed char a = src[i];
+        if (i == var) a = (signed char)in.side;
+        sa[i] = a;
+        dst[i] = a;
+    }
+    __syncwarp();
+    if (lane != 0) return;
+
+    const double* w_o = P.w_o + (size_t)in.inst * n;
+    const double* p_o = P.p_o + (size_t)in.inst * n;
+    const double* w_s = P.w_s + (size_t)in.inst * n;
+    const double* p_s = P.p_s + (size_t)in.inst * n;
+    const int* orig_s = P.orig_s + (size_t)in.inst * n;
+    const double capacity = P.cap[in.inst];
+    const double limit = __dadd_rn(capacity, KN_EPS);
+
+    // 1) items fixed to 1, in original index order (:442-452)
+    double weight = 0.0, profit = 0.0;
+    for (int i = 0; i < n; i++) {
+        if (sa[i] == 1) {
+            weight = __dadd_rn(weight, w_o[i]);
+            profit = __dadd_rn(profit, p_o[i]);
+        }
+    }
+    if (weight > limit) {  // :455-456
+        o.bound = profit;
+        o.weight = weight;
+        o.flags = KF_INFEASIBLE | KF_EARLY;
+        P.out[e] = o;
+        return;
+    }
+    // 2) undecided items greedily in ratio order (:459-488)
+    int s = 0;
+    for (; s < n; s++) {
+        if (sa[orig_s[s]] >= 0) continue;  // fixed to 1 (counted) or to 0
+        const double wi = w_s[s];
+        const double t = __dadd_rn(weight, wi);
+        if (t <= limit) {
+            weight = t;
+            profit = __dadd_rn(profit, p_s[s]);
+        } else {
+            const double remain = __dsub_rn(capacity, weight);
+            if (remain > KN_EPS && wi > KN_EPS) {
+                const double frac = __ddiv_rn(remain, wi);
+                profit = __dadd_rn(profit, __dmul_rn(p_s[s], frac));
+                weight = __dadd_rn(weight, __dmul_rn(wi, frac));
+                o.frac_rank = s;
+                o.frac = frac;
+            }
+            break;
+        }
+    }
+    o.break_rank = s;
+    o.bound = profit;
+    o.weight = weight;
+    bool allint = true;  // relaxed.All(v => |v - Round(v)| < EPS): only the fractional item can fail
+    if (o.frac_rank >= 0) allint = fabs(__dsub_rn(o.frac, rint(o.frac))) < KN_EPS;
+    if (allint) o.flags |= KF_ALLINT;
+    if (weight > limit) o.flags |= KF_INFEASIBLE;
+    P.out[e] = o;
+}
+
+namespace {
+
+struct EvalRec {
+    KnOut r{};
+    int slot = -1;
+    int child[2] = {-1, -1};
+    bool pending = false;
+    bool alive = false;
+};
+
+struct HeapNode {
+    double bound;
+    int eval;
+    std::vector<int> label;
+};
+
+int cmp_double(double a, double b) {  // double.CompareTo
+    if (a < b) return -1;
+    if (a > b) return 1;
+    if (a == b) return 0;
+    if (std::isnan(a)) return std::isnan(b) ? 0 : -1;
+    return 1;
+}
+
+// SimpleMaxHeap<Node> (:494-547), same swaps, same tie behaviour.
+struct MaxHeap {
+    std::vector<HeapNode> data;
+    static int cmp(const HeapNode& a, const HeapNode& b) { return cmp_double(a.bound, b.bound); }
+    void push(HeapNode item) {
+        data.push_back(std::move(item));
+        int ci = (int)data.size() - 1;
+        while (ci > 0) {
+            const int pi = (ci - 1) / 2;
+            if (cmp(data[ci], data[pi]) <= 0) break;
+            std::swap(data[ci], data[pi]);
+            ci = pi;
+        }
+    }
+    HeapNode pop() {
+        int li = (int)data.size() - 1;
+        std::swap(data[0], data[li]);
+        HeapNode ret = std::move(data[li]);
+        data.pop_back();
+        li = (int)data.size() - 1;
+        int i = 0;
+        while (true) {
+            const int l = 2 * i + 1, r = 2 * i + 2;
+            int largest = i;
+            if (l <= li && cmp(data[l], data[largest]) > 0) largest = l;
+            if (r <= li && cmp(data[r], data[largest]) > 0) largest = r;
+            if (largest == i) break;
+            std::swap(data[i], data[largest]);
+            i = largest;
+        }
+        return ret;
+    }
+};
+
+struct KInstance {
+    MaxHeap heap;
+    double best = -std::numeric_limits<double>::infinity();
+    std::vector<int> best_x;
+    long long evals = 0, pops = 0;
+    int pop_index = 0;
+    bool done = false;
+    int root_eval = -1;
+    std::vector<int> orig_by_rank;
+};
+
+struct KnDriver {
+    int count, n;
+    const double *profit, *weight, *capacity;
+    lpx_options opt;
+    lpx_knap_pop_fn on_pop;
+    void* user;
+    int spec_nodes = 8, spec_depth = 3;
+
+    std::vector<KInstance> inst;
+    std::vector<EvalRec> recs;
+    std::vector<int> free_recs;
+    std::vector<int> free_slots;
+    int n_chunks = 0, next_slot = 0;
+    signed char* chunks[KN_MAX_CHUNKS] = {};
+    KnParams P{};
+    double *d_ws, *d_ps, *d_wo, *d_po, *d_cap, *d_best;
+    int* d_orig;
+
+    ~KnDriver() {
+        for (int k = 0; k < n_chunks; k++) cudaFree(chunks[k]);
+    }
+
+    int alloc_slot() {
+        if (!free_slots.empty()) {
+            int s = free_slots.back();
+            free_slots.pop_back();
+            return s;
+        }
+        if (next_slot >= n_chunks * KN_CHUNK_SLOTS) {
+            if (n_chunks >= KN_MAX_CHUNKS) return -1;
+            void* p = nullptr;
+            if (cudaMalloc(&p, (size_t)KN_CHUNK_SLOTS * n) != cudaSuccess) {
+                cudaGetLastError();
+                return -1;
+            }
+            chunks[n_chunks++] = (signed char*)p;
+        }
+        return next_slot++;
+    }
+    int alloc_rec() {
+        int id;
+        if (!free_recs.empty()) {
+            id = free_recs.back();
+            free_recs.pop_back();
+        } else {
+            id = (int)recs.size();
+            recs.emplace_back();
+        }
+        recs[id] = EvalRec();
+        recs[id].alive = true;
+        return id;
+    }
+    // release an evaluation, everything cached below it, and their pool slots
+    void free_tree(int id) {
+        if (id < 0) return;
+        std::vector<int> st{id};
+        while (!st.empty()) {
+            const int k = st.back();
+            st.pop_back();
+            EvalRec& r = recs[k];
+            if (!r.alive) continue;
+            for (int s = 0; s < 2; s++)
+                if (r.child[s] >= 0) st.push_back(r.child[s]);
+            if (r.slot >= 0) free_slots.push_back(r.slot);
+            r.alive = false;
+            free_recs.push_back(k);
+        }
+    }
+    void free_self(int id) {  // the node was expanded: its children live on
+        EvalRec& r = recs[id];
+        if (r.slot >= 0) free_slots.push_back(r.slot);
+        r.alive = false;
+        free_recs.push_back(id);
+    }
+
+    signed char* slot_ptr(int slot) { return chunks[slot / KN_CHUNK_SLOTS] + (size_t)(slot % KN_CHUNK_SLOTS) * n; }
+
+    int fetch_assigned(int slot, std::vector<signed char>& out) {
+        out.resize(n);
+        LPX_CUDA(cudaMemcpy(out.data(), slot_ptr(slot), n, cudaMemcpyDeviceToHost));
+        return LPX_OK;
+    }
+
+    // relaxed[i] of ComputeRelaxation, rebuilt from the assignment and where the greedy pass stopped
+    void relaxed_from(const KInstance& I, const std::vector<signed char>& a, const KnOut& r, std::vector<double>& relaxed) {
+        relaxed.assign(n, 0.0);
+        for (int i = 0; i < n; i++)
+            if (a[i] == 1) relaxed[i] = 1.0;
+        if (r.flags & KF_EARLY) return;  // fixed items alone exceed the capacity (:455-456)
+        for (int s = 0; s < r.break_rank && s < n; s++) {
+            const int o = I.orig_by_rank[s];
+            if (a[o] < 0) relaxed[o] = 1.0;
+        }
+        if (r.frac_rank >= 0) relaxed[I.orig_by_rank[r.frac_rank]] = r.frac;
+    }
+
+    struct Plan {
+        std::vector<int> roots;  // heap-node evaluations planned under (for pruning skipped results)
+        std::vector<KnIn> in;
+        std::vector<int> rec;    // EvalRec id per planned evaluation
+        std::vector<int> level;
+    };
+
+    // plan the subtree of evaluation `id` (complete) down to `depth` levels
+    void plan_below(Plan& pl, int k, int id, int depth) {
+        struct Item { int rec; int pending; int depth; int level; };
+        std::vector<Item> q{{id, -1, depth, 0}};
+        const KInstance& I = inst[k];
+        while (!q.empty()) {
+            Item it = q.back();
+            q.pop_back();
+            if (it.depth <= 0) continue;
+            EvalRec& r = recs[it.rec];
+            if (!r.pending) {
+                const bool expandable = !(r.r.flags & (KF_INFEASIBLE | KF_ALLINT)) && r.r.frac_rank >= 0 &&
+                                        r.r.bound > I.best + KN_EPS;
+                // the popped node itself is expanded whenever it has a fractional item (:147,180)
+                const bool is_heap_node = it.rec == id;
+                if (!(expandable || (is_heap_node && r.r.frac_rank >= 0))) continue;
+            }
+            for (int side = 0; side < 2; side++) {
+                int ch = recs[it.rec].child[side];
+                int ch_pending = -1, ch_level = it.level;
+                if (ch < 0) {
+                    const int slot = alloc_slot();
+                    if (slot < 0) return;  // pool exhausted: plan what we have
+                    ch = alloc_rec();
+                    EvalRec& c = recs[ch];
+                    c.slot = slot;
+                    c.pending = true;
+                    recs[it.rec].child[side] = ch;
+                    KnIn in;
+                    in.inst = k;
+                    in.side = side;
+                    in.out_slot = slot;
+                    if (recs[it.rec].pending) {
+                        in.parent_slot = -1;
+                        in.parent_pending = it.pending;
+                        in.var = -2;
+                    } else {
+                        in.parent_slot = recs[it.rec].slot;
+                        in.parent_pending = -1;
+                        in.var = I.orig_by_rank[recs[it.rec].r.frac_rank];
+                    }
+                    ch_pending = (int)pl.in.size();
+                    pl.in.push_back(in);
+                    pl.rec.push_back(ch);
+                    pl.level.push_back(it.level);
+                    ch_level = it.level + 1;
+                }
+                q.push_back({ch, ch_pending, it.depth - 1, ch_level});
+            }
+        }
+    }
+
+    int run_plan(Plan& pl) {
+        Runtime& r = rt();
+        const int total = (int)pl.in.size();
+        if (total == 0) return LPX_OK;
+        // order by level (stable), remapping parent_pending
+        std::vector<int> order(total), pos(total);
+        for (int i = 0; i < total; i++) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return pl.level[a] < pl.level[b]; });
+        for (int i = 0; i < total; i++) pos[order[i]] = i;
+        KnIn* h_in = ws_pin_as<KnIn>(WS_KN_AUX, total);
+        KnOut* h_out = ws_pin_as<KnOut>(WS_KN_OUT, total);
+        KnIn* d_in = ws_dev_as<KnIn>(WS_KN_AUX, total);
+        KnOut* d_out = ws_dev_as<KnOut>(WS_KN_OUT, total);
+        double* h_best = ws_pin_as<double>(WS_MISC0, count);
+        if (!h_in || !h_out || !d_in || !d_out || !h_best) return LPX_E_CUDA;
+        std::vector<int> rec_sorted(total);
+        std::vector<int> level_first, level_count;
+        for (int i = 0; i < total; i++) {
+            KnIn in = pl.in[order[i]];
+            if (in.parent_pending >= 0) in.parent_pending = pos[in.parent_pending];
+            h_in[i] = in;
+            rec_sorted[i] = pl.rec[order[i]];
+            const int lv = pl.level[order[i]];
+            if ((int)level_first.size() <= lv) {
+                level_first.resize(lv + 1, i);
+                level_count.resize(lv + 1, 0);
+            }
+            level_count[lv]++;
+        }
+        for (int k = 0; k < count; k++) h_best[k] = inst[k].best;
+        cudaStream_t s = r.stream;
+        LPX_CUDA(cudaMemcpyAsync(d_in, h_in, (size_t)total * sizeof(KnIn), cudaMemcpyHostToDevice, s));
+        LPX_CUDA(cudaMemcpyAsync(d_best, h_best, (size_t)count * 8, cudaMemcpyHostToDevice, s));
+        for (int k = 0; k < n_chunks; k++) P.chunks[k] = chunks[k];
+        P.in = d_in;
+        P.out = d_out;
+        const size_t smem = (size_t)8 * n;
+        for (size_t lv = 0; lv < level_first.size(); lv++) {
+            if (level_count[lv] == 0) continue;
+            P.first = level_first[lv];
+            P.count = level_count[lv];
+            knap_eval_kernel<<<(P.count + 7) / 8, 256, smem, s>>>(P);
+            count_launch();
+        }
+        LPX_CUDA(cudaGetLastError());
+        LPX_CUDA(cudaMemcpyAsync(h_out, d_out, (size_t)total * sizeof(KnOut), cudaMemcpyDeviceToHost, s));
+        LPX_CUDA(cudaStreamSynchronize(s));
+        for (int i = 0; i < total; i++) {
+            EvalRec& rec = recs[rec_sorted[i]];
+            rec.r = h_out[i];
+            rec.pending = false;
+        }
+        return LPX_OK;
+    }
+
+    // remove skipped children below `id` so that a later plan re-evaluates them if needed
+    void prune_skipped(int id) {
+        std::vector<int> st{id};
+        while (!st.empty()) {
+            const int k = st.back();
+            st.pop_back();
+            for (int s = 0; s < 2; s++) {
+                const int ch = recs[k].child[s];
+                if (ch < 0) continue;
+                if (recs[ch].r.flags & KF_SKIPPED) {
+                    free_tree(ch);
+                    recs[k].child[s] = -1;
+                } else {
+                    st.push_back(ch);
+                }
+            }
+        }
+    }
+
+    void fill_eval(lpx_knap_eval& ev, const EvalRec& r, int pop_index, int child, int decision,
+                   const signed char* assigned) {
+        ev.pop_index = pop_index;
+        ev.child = child;
+        ev.var = r.r.var;
+        ev.bound = r.r.bound;
+        ev.weight = r.r.weight;
+        ev.frac_rank = r.r.frac_rank;
+        ev.frac = r.r.frac;
+        ev.break_rank = r.r.break_rank;
+        ev.decision = decision;
+        ev.assigned = assigned;
+    }
+
+    // Commit as many pops of instance k as the cached evaluations allow.
+    int commit(int k) {
+        KInstance& I = inst[k];
+        std::vector<signed char> a_node, a_child[2];
+        std::vector<double> relaxed;
+        while (!I.heap.data.empty()) {
+            const HeapNode& top = I.heap.data[0];
+            const bool skip = top.bound <= I.best + KN_EPS;
+            const EvalRec& tr = recs[top.eval];
+            if (!skip && tr.r.frac_rank >= 0 && (tr.child[0] < 0 || tr.child[1] < 0 || recs[tr.child[0]].pending ||
+                                                 recs[tr.child[1]].pending))
+                return LPX_OK;  // children not evaluated yet: next round
+            HeapNode node = I.heap.pop();
+            I.pops++;
+            if (skip) {  // :124
+                free_tree(node.eval);
+                continue;
+            }
+            const int this_pop = I.pop_index++;
+            EvalRec cur = recs[node.eval];
+            lpx_knap_pop pop;
+            std::memset(&pop, 0, sizeof pop);
+            pop.pop_index = this_pop;
+            pop.label_len = (int)node.label.size();
+            pop.label = node.label.data();
+            const bool want_cb = on_pop != nullptr;
+            if (want_cb) {
+                int rc = fetch_assigned(cur.slot, a_node);
+                if (rc != LPX_OK) return rc;
+            }
+            if (cur.r.frac_rank < 0) {  // :147-177
+                int closed = 3;
+                if (cur.r.weight <= capacity[k] + KN_EPS) {
+                    if (cur.r.bound > I.best + KN_EPS) {
+                        I.best = cur.r.bound;
+                        if (!want_cb) {
+                            int rc = fetch_assigned(cur.slot, a_node);
+                            if (rc != LPX_OK) return rc;
+                        }
+                        relaxed_from(I, a_node, cur.r, relaxed);
+                        for (int i = 0; i < n; i++) I.best_x[i] = relaxed[i] >= 0.5 ? 1 : 0;
+                        closed = 1;
+                    } else {
+                        closed = 2;
+                    }
+                }
+                if (want_cb) {
+                    fill_eval(pop.relax, cur, this_pop, -1, LPX_KN_ROOT, a_node.data());
+                    pop.closed = closed;
+                    on_pop(&pop, nullptr, nullptr, user);
+                }
+                free_tree(node.eval);
+                continue;
+            }
+            lpx_knap_eval evs[2];
+            for (int side = 0; side < 2; side++) {
+                const int ce = cur.child[side];
+                const EvalRec cr = recs[ce];
+                I.evals++;
+                int decision;
+                if (want_cb) {
+                    int rc = fetch_assigned(cr.slot, a_child[side]);
+                    if (rc != LPX_OK) return rc;
+                }
+                if (cr.r.weight > capacity[k] + KN_EPS) {
+                    decision = LPX_KN_INFEASIBLE;
+                    free_tree(ce);
+                } else if (cr.r.bound > I.best + KN_EPS) {
+                    if (cr.r.flags & KF_ALLINT) {
+                        decision = LPX_KN_CANDIDATE_INT;
+                        if (cr.r.bound > I.best + KN_EPS) {
+                            I.best = cr.r.bound;
+                            if (!want_cb) {
+                                int rc = fetch_assigned(cr.slot, a_child[side]);
+                                if (rc != LPX_OK) return rc;
+                            }
+                            relaxed_from(I, a_child[side], cr.r, relaxed);
+                            for (int i = 0; i < n; i++) I.best_x[i] = (int)std::nearbyint(relaxed[i]);
+                        }
+                        free_tree(ce);
+                    } else {
+                        decision = LPX_KN_PUSHED;
+                        HeapNode hn;
+                        hn.bound = cr.r.bound;
+                        hn.eval = ce;
+                        if (want_cb) {
+                            if (node.label.size() == 1 && node.label[0] == 0) hn.label = {side + 1};
+                            else {
+                                hn.label = node.label;
+                                hn.label.push_back(side + 1);
+                            }
+                        }
+                        I.heap.push(std::move(hn));
+                    }
+                } else {
+                    decision = LPX_KN_DROPPED;
+                    free_tree(ce);
+                }
+                if (want_cb) fill_eval(evs[side], cr, this_pop, side, decision, a_child[side].data());
+            }
+            if (want_cb) {
+                fill_eval(pop.relax, cur, this_pop, -1, LPX_KN_ROOT, a_node.data());
+                pop.closed = 0;
+                on_pop(&pop, &evs[0], &evs[1], user);
+            }
+            free_self(node.eval);
+        }
+        I.done = true;
+        return LPX_OK;
+    }
+
+    int run() {
+        Runtime& r = rt();
+        inst.resize(count);
+        // ratio ordering on the host (:75-79): stable OrderByDescending(Ratio).ThenByDescending(Profit)
+        std::vector<double> h_ws((size_t)count * n), h_ps((size_t)count * n);
+        std::vector<int> h_orig((size_t)count * n);
+        for (int k = 0; k < count; k++) {
+            const double* p = profit + (size_t)k * n;
+            const double* w = weight + (size_t)k * n;
+            std::vector<int> idx(n);
+            for (int i = 0; i < n; i++) idx[i] = i;
+            auto ratio = [&](int i) { return w[i] > 0 ? p[i] / w[i] : std::numeric_limits<double>::infinity(); };
+            std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
+                const int c = cmp_double(ratio(a), ratio(b));
+                if (c != 0) return c > 0;
+                return cmp_double(p[a], p[b]) > 0;
+            });
+            inst[k].orig_by_rank = idx;
+            inst[k].best_x.assign(n, 0);
+            for (int s = 0; s < n; s++) {
+                h_ws[(size_t)k * n + s] = w[idx[s]];
+                h_ps[(size_t)k * n + s] = p[idx[s]];
+                h_orig[(size_t)k * n + s] = idx[s];
+            }
+        }
+        const size_t cn = (size_t)count * n;
+        d_ws = ws_dev_as<double>(WS_KN_ITEMS, cn * 4);
+        d_orig = ws_dev_as<int>(WS_KN_ASSIGN, cn);
+        d_cap = ws_dev_as<double>(WS_MISC1, count);
+        d_best = ws_dev_as<double>(WS_MISC2, count);
+        if (!d_ws || !d_orig || !d_cap || !d_best) return LPX_E_CUDA;
+        d_ps = d_ws + cn;
+        d_wo = d_ws + 2 * cn;
+        d_po = d_ws + 3 * cn;
+        cudaStream_t s = r.stream;
+        LPX_CUDA(cudaMemcpyAsync(d_ws, h_ws.data(), cn * 8, cudaMemcpyHostToDevice, s));
+        LPX_CUDA(cudaMemcpyAsync(d_ps, h_ps.data(), cn * 8, cudaMemcpyHostToDevice, s));
+        LPX_CUDA(cudaMemcpyAsync(d_wo, weight, cn * 8, cudaMemcpyHostToDevice, s));
+        LPX_CUDA(cudaMemcpyAsync(d_po, profit, cn * 8, cudaMemcpyHostToDevice, s));
+        LPX_CUDA(cudaMemcpyAsync(d_orig, h_orig.data(), cn * 4, cudaMemcpyHostToDevice, s));
+        LPX_CUDA(cudaMemcpyAsync(d_cap, capacity, (size_t)count * 8, cudaMemcpyHostToDevice, s));
+        LPX_CUDA(cudaStreamSynchronize(s));
+        P.w_s = d_ws;
+        P.p_s = d_ps;
+        P.orig_s = d_orig;
+        P.w_o = d_wo;
+        P.p_o = d_po;
+        P.cap = d_cap;
+        P.best = d_best;
+        P.n = n;
+        LPX_CUDA(cudaFuncSetAttribute(knap_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * n)));
+
+        // roots: all undecided (:101-113)
+        {
+            Plan pl;
+            const int seed_slot = alloc_slot();
+            if (seed_slot < 0) {
+                set_error("knapsack: cannot allocate the node pool");
+                return LPX_E_CUDA;
+            }
+            LPX_CUDA(cudaMemset(slot_ptr(seed_slot), 0xFF, n));
+            for (int k = 0; k < count; k++) {
+                const int slot = alloc_slot();
+                const int id = alloc_rec();
+                recs[id].slot = slot;
+                recs[id].pending = true;
+                inst[k].root_eval = id;
+                KnIn in;
+                in.inst = k;
+                in.parent_slot = seed_slot;
+                in.parent_pending = -1;
+                in.var = -1;
+                in.side = 0;
+                in.out_slot = slot;
+                pl.in.push_back(in);
+                pl.rec.push_back(id);
+                pl.level.push_back(0);
+            }
+            int rc = run_plan(pl);
+            if (rc != LPX_OK) return rc;
+            for (int k = 0; k < count; k++) {
+                HeapNode hn;
+                hn.bound = recs[inst[k].root_eval].r.bound;
+                hn.eval = inst[k].root_eval;
+                hn.label = {0};
+                inst[k].heap.push(std::move(hn));
+                inst[k].evals++;
+            }
+        }
+
+        while (true) {
+            Plan pl;
+            bool any = false;
+            for (int k = 0; k < count; k++) {
+                KInstance& I = inst[k];
+                if (I.done) continue;
+                any = true;
+                // best-first peek at the top-K heap entries without disturbing the heap
+                auto cmpq = [&](int a, int b) { return cmp_double(I.heap.data[a].bound, I.heap.data[b].bound) < 0; };
+                std::priority_queue<int, std::vector<int>, decltype(cmpq)> pq(cmpq);
+                if (!I.heap.data.empty()) pq.push(0);
+                int taken = 0;
+                while (!pq.empty() && taken < spec_nodes) {
+                    const int i = pq.top();
+                    pq.pop();
+                    const int l = 2 * i + 1, rr = 2 * i + 2;
+                    if (l < (int)I.heap.data.size()) pq.push(l);
+                    if (rr < (int)I.heap.data.size()) pq.push(rr);
+                    const HeapNode& hn = I.heap.data[i];
+                    if (hn.bound <= I.best + KN_EPS) continue;
+                    // the front runner gets the deep look-ahead, the others one level
+                    plan_below(pl, k, hn.eval, taken == 0 ? spec_depth : 1);
+                    pl.roots.push_back(hn.eval);
+                    taken++;
+                }
+            }
+            if (!any) break;
+            int rc = run_plan(pl);
+            if (rc != LPX_OK) return rc;
+            bool progressed = false;
+            // unlink evaluations the device skipped, so they can be planned again later
+            for (int id : pl.roots) prune_skipped(id);
+            for (int k = 0; k < count; k++) {
+                KInstance& I = inst[k];
+                if (I.done) continue;
+                const long long before = I.pops;
+                rc = commit(k);
+                if (rc != LPX_OK) return rc;
+                if (I.pops != before || I.done) progressed = true;
+            }
+            if (!progressed && pl.in.empty()) {
+                set_error("knapsack: node pool exhausted (no progress possible)");
+                return LPX_E_CAPACITY;
+            }
+        }
+        return LPX_OK;
+    }
+};
+
+}  // namespace
+}  // namespace lpx
+
+using namespace lpx;
+
+static int knapsack_entry(int count, int n, const double* profit, const double* weight, const double* capacity,
+                          const lpx_options* opt, int* found, double* best_value, int* best_x, long long* n_evals,
+                          long long* n_pops, int* rank_order, lpx_knap_pop_fn on_pop, void* user) {
+    if (count < 1 || n < 1 || !profit || !weight || !capacity) {
+        set_error("lpx_bnb_knapsack: bad arguments");
+        return LPX_E_BAD_ARGS;
+    }
+    if ((size_t)8 * n > (size_t)200 * 1024) {
+        set_error("lpx_bnb_knapsack: more than 25600 items per instance is not supported");
+        return LPX_E_CAPACITY;
+    }
+    int rc = ensure_device();
+    if (rc != LPX_OK) return rc;
+    std::lock_guard<std::recursive_mutex> lk(rt().mu);
+    KnDriver d;
+    d.count = count;
+    d.n = n;
+    d.profit = profit;
+    d.weight = weight;
+    d.capacity = capacity;
+    lpx_default_options(&d.opt);
+    if (opt) d.opt = *opt;
+    if (d.opt.reserved[0] > 0) d.spec_nodes = d.opt.reserved[0];
+    if (d.opt.reserved[1] > 0) d.spec_depth = d.opt.reserved[1];
+    d.on_pop = on_pop;
+    d.user = user;
+    rc = d.run();
+    if (rc != LPX_OK) return rc;
+    for (int k = 0; k < count; k++) {
+        const KInstance& I = d.inst[k];
+        const bool none = std::isinf(I.best) && I.best < 0;
+        if (found) found[k] = none ? 0 : 1;
+        if (best_value) best_value[k] = I.best;
+        if (best_x)
+            for (int i = 0; i < n; i++) best_x[(size_t)k * n + i] = I.best_x[i];
+        if (n_evals) n_evals[k] = I.evals;
+        if (n_pops) n_pops[k] = I.pops;
+        if (rank_order && k == 0)
+            for (int s = 0; s < n; s++) rank_order[s] = I.orig_by_rank[s];
+    }
+    return LPX_OK;
+}
+
+extern "C" {
+
+int lpx_bnb_knapsack(int n, const double* profit, const double* weight, double capacity, const lpx_options* opt,
+                     int* found, double* best_value, int* best_x, long long* n_evals, long long* n_pops,
+                     int* rank_order, lpx_knap_pop_fn on_pop, void* user) {
+    return knapsack_entry(1, n, profit, weight, &capacity, opt, found, best_value, best_x, n_evals, n_pops,
+                          rank_order, on_pop, user);
+}
+
+int lpx_bnb_knapsack_batched(int count, int n, const double* profit, const double* weight, const double* capacity,
+                             const lpx_options* opt, int* found, double* best_value, int* best_x,
+                             long long* n_evals, long long* n_pops) {
+    return knapsack_entry(count, n, profit, weight, capacity, opt, found, best_value, best_x, n_evals, n_pops, nullptr,
+                          nullptr, nullptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,590 @@
+// lpx_stream.cu — ONE large dense tableau spread over the whole GPU (BASELINE config 3:
+// 4096 x 8192 -> 4097 x 12289 doubles = 403 MB, far beyond L2).  Each pivot is
+//
+//   select  (1 CTA)   exact ChooseLeaving on two compact 4097-vectors, normalise the pivot row,
+//                     update the z-row in registers and pick the NEXT entering column
+//   update  (grid)    one HBM pass: T[i,j] -= f[i] * p[j], 128-bit loads/stores, the pivot row
+//                     held in registers per column strip; the pass also captures the next
+//                     entering column and the RHS into compact vectors for the next select
+//
+// so the tableau is read and written exactly once per pivot: 2 * 8 * rows * cols algorithmic
+// bytes.  Replaces R/Models/PrimalSimplex.cs:92-124 (loop), :205-257 (rules).
+//
+// HBM layout: row-major, leading dimension padded to a multiple of 16 doubles (128 B) so every
+// row starts on a 128-byte line and double2 accesses are aligned; pad columns hold zeros.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "lpx_common.cuh"
+#include "lpx_runtime.hpp"
+#include "lpx_stream.hpp"
+
+namespace lpx {
+
+struct StreamCtl {
+    int status;   // LPX_RUNNING until decided
+    int pivots;   // pivots performed
+    int enter;    // entering column of the next pivot (-1: optimal)
+    int leave;    // leaving row of the pivot being applied
+    int active;   // 1: the update kernel has a pivot to apply
+    int capture;  // entering column of the pivot after this one (-1: none)
+    int k;        // index of the pivot being applied
+    int pad;
+};
+
+struct StreamParams {
+    double* T;
+    int ld, rows, width, m, n;
+    double* colbuf;  // 2 x colstride: entering column of pivot k lives in buffer k & 1
+    int colstride;
+    double* rhsbuf;  // rows
+    double* prow;    // ld
+    double* ratio;   // m
+    int* basis;
+    int* pivlog;
+    int pivlog_cap;
+    StreamCtl* ctl;
+    int max_iter;
+};
+
+__device__ __forceinline__ double dneg_s(double v) {
+    return __longlong_as_double(__double_as_longlong(v) ^ (long long)0x8000000000000000ULL);
+}
+
+template <int THREADS>
+__device__ __forceinline__ int block_min_int(int v, int* sred) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = __reduce_min_sync(0xffffffffu, v);
+    if (lane == 0) sred[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < THREADS / 32 ? sred[lane] : INT_MAX;
+        w = __reduce_min_sync(0xffffffffu, w);
+        if (lane == 0) sred[32] = w;
+    }
+    __syncthreads();
+    const int r = sred[32];
+    __syncthreads();
+    return r;
+}
+
+// ---- setup kernels --------------------------------------------------------------------------
+
+// First offending constraint in the reference's order (PrimalSimplex.cs:66-77).
+__global__ void __launch_bounds__(1024) stream_validate_kernel(StreamCtl* ctl, const double* b, int m_in,
+                                                               int first_ge) {
+    __shared__ int sred[34];
+    int cand = INT_MAX;
+    for (int r = threadIdx.x; r < m_in; r += 1024)
+        if (b[r] < -1e-9) {
+            cand = r;
+            break;
+        }
+    cand = block_min_int<1024>(cand, sred);
+    if (threadIdx.x == 0) {
+        int st = LPX_RUNNING;
+        if (first_ge != INT_MAX || cand != INT_MAX) st = (first_ge <= cand) ? LPX_S_GE_ROW : LPX_S_NEG_RHS;
+        ctl->status = st;
+        ctl->pivots = 0;
+        ctl->enter = -1;
+        ctl->leave = -1;
+        ctl->active = 0;
+        ctl->capture = -1;
+        ctl->k = 0;
+    }
+}
+
+// BuildTableau (PrimalSimplex.cs:179-203) with the EQ expansion folded in through a row map.
+__global__ void __launch_bounds__(256) stream_build_kernel(StreamParams P, const double* A, const double* b,
+                                                           const double* c, const int* rsrc, const int* rsgn,
+                                                           int sense) {
+    const int n = P.n, m = P.m, rhs = P.width - 1;
+    for (int i = blockIdx.x; i < P.rows; i += gridDim.x) {
+        double* Ti = P.T + (size_t)i * P.ld;
+        if (i < m) {
+            const int src = rsrc[i];
+            const bool flip = rsgn[i] != 0;
+            const double* Ar = A + (size_t)src * n;
+            for (int j = threadIdx.x; j < P.ld; j += 256) {
+                double v = 0.0;
+                if (j < n) v = neg_if(Ar[j], flip);
+                else if (j == rhs) v = neg_if(b[src], flip);
+                else if (j == n + i) v = 1.0;
+                Ti[j] = v;
+            }
+            if (threadIdx.x == 0) P.basis[i] = n + i;
+        } else {
+            for (int j = threadIdx.x; j < P.ld; j += 256) {
+                double v = 0.0;
+                if (j < n) {
+                    double cj = c[j];
+                    if (sense == 1) cj = dneg_s(cj);
+                    v = dneg_s(cj);
+                }
+                Ti[j] = v;
+            }
+        }
+    }
+}
+
+// ChooseEntering on the initial z-row.
+__global__ void __launch_bounds__(1024) stream_first_kernel(StreamParams P) {
+    __shared__ ArgMin red[34];
+    if (P.ctl->status != LPX_RUNNING) return;
+    const int e = block_argmin_below<1024>(P.T + (size_t)P.m * P.ld, P.width - 1, -LPX_EPS, red);
+    if (threadIdx.x == 0) P.ctl->enter = e;
+}
+
+// Compact copies of the entering column and of the RHS (only needed before the first pivot; from
+// then on the update pass captures them on the fly).
+__global__ void __launch_bounds__(256) stream_gather_kernel(StreamParams P) {
+    if (P.ctl->status != LPX_RUNNING) return;
+    const int e = P.ctl->enter;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= P.rows) return;
+    const double* Ti = P.T + (size_t)i * P.ld;
+    if (e >= 0) P.colbuf[i] = Ti[e];
+    P.rhsbuf[i] = Ti[P.width - 1];
+}
+
+// ---- per-pivot kernels ------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(1024) stream_select_kernel(StreamParams P, int probe_only) {
+    __shared__ ArgMin red[34];
+    __shared__ int ired[34];
+    StreamCtl* ctl = P.ctl;
+    const int tid = threadIdx.x;
+    if (tid == 0) ctl->active = 0;
+    if (ctl->status != LPX_RUNNING) return;
+    const int k = ctl->pivots;
+    if (k >= P.max_iter) {  // "if (iter > MaxIterations) throw" comes before the optimality test
+        if (tid == 0) ctl->status = LPX_S_ITER_LIMIT;
+        return;
+    }
+    const int e = ctl->enter;
+    if (e < 0) {
+        if (tid == 0) ctl->status = LPX_OPTIMAL;
+        return;
+    }
+    const int m = P.m;
+    const double* col = P.colbuf + (size_t)(k & 1) * P.colstride;
+
+    // ChooseLeaving.  Ratios first (NaN marks "not eligible": NaN < x is false) ...
+    for (int i = tid; i < m; i += 1024) {
+        const double a = col[i];
+        double r = __longlong_as_double(0x7ff8000000000000LL);
+        if (a > LPX_EPS) r = __ddiv_rn(P.rhsbuf[i], a);
+        P.ratio[i] = r;
+    }
+    __syncthreads();
+    // ... then the reference's sequential rule "take i if ratio < best - 1e-9", reproduced exactly:
+    // repeatedly find the FIRST row after the last accepted one that beats the running best.
+    // The number of rounds is the number of accepted updates (about ln m on random data).
+    const int R = (m + 1023) / 1024;
+    const int lo = tid * R, hi = min(m, lo + R);
+    double best = __longlong_as_double(0x7ff0000000000000LL);
+    int row = -1, start = 0;
+    while (true) {
+        const double thr = __dsub_rn(best, LPX_MARGIN_PRIMAL);
+        int cand = INT_MAX;
+        for (int i = max(lo, start); i < hi; i++)
+            if (P.ratio[i] < thr) {
+                cand = i;
+                break;
+            }
+        cand = block_min_int<1024>(cand, ired);
+        if (cand == INT_MAX) break;
+        best = P.ratio[cand];
+        row = cand;
+        start = cand + 1;
+    }
+    if (row < 0) {
+        if (tid == 0) ctl->status = LPX_UNBOUNDED;
+        return;
+    }
+    if (probe_only) return;
+
+    // Normalise the pivot row (true division), write it back, and on the way compute the updated
+    // z-row entries z_j - f_z * p_j to choose the NEXT entering column (ChooseEntering).
+    const int l = row;
+    const double piv = col[l], fz = col[m];
+    double* Tl = P.T + (size_t)l * P.ld;
+    const double* Tz = P.T + (size_t)m * P.ld;
+    ArgMin a;
+    a.v = -LPX_EPS;
+    a.i = INT_MAX;
+    const int ncand = P.width - 1;
+    for (int j = tid; j < P.ld; j += 1024) {
+        const double pj = __ddiv_rn(Tl[j], piv);
+        P.prow[j] = pj;
+        Tl[j] = pj;
+        if (j < ncand) {
+            const double zn = __dsub_rn(Tz[j], __dmul_rn(fz, pj));
+            if (zn < a.v) {
+                a.v = zn;
+                a.i = j;
+            }
+        }
+    }
+    a = warp_argmin(a);
+    const int lane = tid & 31, warp = tid >> 5;
+    if (lane == 0) red[warp] = a;
+    __syncthreads();
+    if (warp == 0) {
+        ArgMin b2 = red[lane];
+        b2 = warp_argmin(b2);
+        if (lane == 0) {
+            const int en = b2.i == INT_MAX ? -1 : b2.i;
+            double* out = P.colbuf + (size_t)((k + 1) & 1) * P.colstride;
+            if (en >= 0) out[l] = P.prow[en];
+            P.rhsbuf[l] = P.prow[P.width - 1];
+            P.basis[l] = e;
+            if (k < P.pivlog_cap) {
+                P.pivlog[2 * k] = e;
+                P.pivlog[2 * k + 1] = l;
+            }
+            ctl->leave = l;
+            ctl->capture = en;
+            ctl->k = k;
+            ctl->pivots = k + 1;
+            ctl->enter = en;
+            ctl->active = 1;
+        }
+    }
+}
+
+// The HBM pass.  grid = (column strips of 512, row chunks); each thread owns two adjacent
+// columns for its CTA's rows, so p[j] stays in registers and f[i] is a broadcast load.
+// The sweep direction alternates with the pivot parity: the rows written last by pivot k are
+// read first by pivot k+1, while they are still in the 126 MB L2.
+template <int UNROLL>
+__global__ void __launch_bounds__(256, 4) stream_update_kernel(StreamParams P) {
+    const StreamCtl* ctl = P.ctl;
+    if (ctl->active == 0) return;
+    const int l = ctl->leave, k = ctl->k, cap = ctl->capture;
+    const int j0 = (blockIdx.x * 256 + threadIdx.x) * 2;
+    if (j0 >= P.ld) return;
+    const double* __restrict__ f = P.colbuf + (size_t)(k & 1) * P.colstride;
+    double* __restrict__ out = P.colbuf + (size_t)((k + 1) & 1) * P.colstride;
+    const int rpc = (P.rows + gridDim.y - 1) / gridDim.y;
+    const int r0 = blockIdx.y * rpc;
+    const int r1 = min(P.rows, r0 + rpc);
+    const int cnt = r1 - r0;
+    if (cnt <= 0) return;
+    const double2 p = *reinterpret_cast<const double2*>(P.prow + j0);
+    const int rhs = P.width - 1;
+    const int cx = (cap == j0) ? 0 : ((cap == j0 + 1) ? 1 : -1);
+    const int rx = (rhs == j0) ? 0 : ((rhs == j0 + 1) ? 1 : -1);
+    const bool rev = (k & 1) != 0;
+    double* __restrict__ Tc = P.T + j0;
+    const size_t ld = (size_t)P.ld;
+
+    for (int q = 0; q < cnt; q += UNROLL) {
+        double2 t[UNROLL];
+        double fi[UNROLL];
+        int ri[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            const int qq = q + u;
+            ri[u] = qq < cnt ? (rev ? r1 - 1 - qq : r0 + qq) : -1;
+            if (ri[u] >= 0) {
+                t[u] = *reinterpret_cast<const double2*>(Tc + (size_t)ri[u] * ld);
+                fi[u] = f[ri[u]];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            if (ri[u] >= 0 && ri[u] != l) {
+                double2 v;
+                v.x = __dsub_rn(t[u].x, __dmul_rn(fi[u], p.x));
+                v.y = __dsub_rn(t[u].y, __dmul_rn(fi[u], p.y));
+                *reinterpret_cast<double2*>(Tc + (size_t)ri[u] * ld) = v;
+                if (cx >= 0) out[ri[u]] = cx == 0 ? v.x : v.y;
+                if (rx >= 0) P.rhsbuf[ri[u]] = rx == 0 ? v.x : v.y;
+            }
+        }
+    }
+}
+
+}  // namespace lpx
+
+// ---- session object -----------------------------------------------------------------------------
+
+using namespace lpx;
+
+struct lpx_session {
+    StreamParams P{};
+    int m_in = 0, n = 0, sense = 0;
+    lpx_options opt{};
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    void* buffers[12] = {};
+    int nbuf = 0;
+    dim3 grid_update;
+    int device = 0;
+};
+
+namespace lpx {
+
+static void* sess_alloc(lpx_session* s, size_t bytes) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+    if (e != cudaSuccess) {
+        cuda_fail(e, "cudaMalloc(session)", __FILE__, __LINE__);
+        return nullptr;
+    }
+    s->buffers[s->nbuf++] = p;
+    return p;
+}
+
+static void sess_free(lpx_session* s) {
+    if (!s) return;
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (int i = 0; i < s->nbuf; i++) cudaFree(s->buffers[i]);
+    if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+static int launch_pair(lpx_session* s, int probe_only) {
+    stream_select_kernel<<<1, 1024, 0, s->stream>>>(s->P, probe_only);
+    count_launch();
+    if (!probe_only) {
+        stream_update_kernel<4><<<s->grid_update, 256, 0, s->stream>>>(s->P);
+        count_launch();
+    }
+    LPX_CUDA(cudaGetLastError());
+    return LPX_OK;
+}
+
+// A, b, c: device pointers valid until this call returns (setup runs synchronously).
+static lpx_session* session_create(int m, int n, int sense, const double* dA, const int* rel, const double* db,
+                                   const double* dc, const lpx_options* opt) {
+    if (ensure_device() != LPX_OK) return nullptr;
+    std::lock_guard<std::recursive_mutex> lk(rt().mu);
+    lpx_session* s = new lpx_session();
+    lpx_default_options(&s->opt);
+    if (opt) s->opt = *opt;
+    s->m_in = m;
+    s->n = n;
+    s->sense = sense;
+    s->device = rt().device;
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("cudaStreamCreate failed");
+        delete s;
+        return nullptr;
+    }
+    s->own_stream = true;
+
+    // row map of the EQ expansion, and the first '>=' row, both known from rel on the host
+    std::vector<int> rsrc, rsgn;
+    int first_ge = INT_MAX;
+    for (int r = 0; r < m; r++) {
+        const int rl = rel ? rel[r] : 0;
+        if (rl == 1 && first_ge == INT_MAX) first_ge = r;
+        rsrc.push_back(r);
+        rsgn.push_back(0);
+        if (rl == 2) {
+            rsrc.push_back(r);
+            rsgn.push_back(1);
+        }
+    }
+    const int mm = (int)rsrc.size();
+    StreamParams& P = s->P;
+    P.m = mm;
+    P.n = n;
+    P.rows = mm + 1;
+    P.width = n + mm + 1;
+    P.ld = (P.width + 15) & ~15;
+    P.colstride = (P.rows + 15) & ~15;
+    P.max_iter = s->opt.max_iterations;
+    P.pivlog_cap = std::max(1, std::min(P.max_iter, 1 << 20));
+    const size_t tbytes = (size_t)P.rows * P.ld * 8;
+    P.T = (double*)sess_alloc(s, tbytes);
+    P.colbuf = (double*)sess_alloc(s, (size_t)2 * P.colstride * 8);
+    P.rhsbuf = (double*)sess_alloc(s, (size_t)P.colstride * 8);
+    P.prow = (double*)sess_alloc(s, (size_t)P.ld * 8);
+    P.ratio = (double*)sess_alloc(s, (size_t)P.colstride * 8);
+    P.basis = (int*)sess_alloc(s, (size_t)mm * 4);
+    P.pivlog = (int*)sess_alloc(s, (size_t)P.pivlog_cap * 8);
+    P.ctl = (StreamCtl*)sess_alloc(s, sizeof(StreamCtl));
+    int* drsrc = (int*)sess_alloc(s, (size_t)mm * 4);
+    int* drsgn = (int*)sess_alloc(s, (size_t)mm * 4);
+    if (!P.T || !P.colbuf || !P.rhsbuf || !P.prow || !P.ratio || !P.basis || !P.pivlog || !P.ctl || !drsrc || !drsgn) {
+        sess_free(s);
+        return nullptr;
+    }
+    cudaStream_t st = s->stream;
+    bool ok = true;
+    ok = ok && cudaMemcpyAsync(drsrc, rsrc.data(), (size_t)mm * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(drsgn, rsgn.data(), (size_t)mm * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    ok = ok && cudaMemsetAsync(P.colbuf, 0, (size_t)2 * P.colstride * 8, st) == cudaSuccess;
+    ok = ok && cudaMemsetAsync(P.rhsbuf, 0, (size_t)P.colstride * 8, st) == cudaSuccess;
+    if (ok) {
+        stream_validate_kernel<<<1, 1024, 0, st>>>(P.ctl, db, m, first_ge);
+        const int bgrid = std::min(P.rows, sm_count() * 8);
+        stream_build_kernel<<<bgrid, 256, 0, st>>>(P, dA, db, dc, drsrc, drsgn, sense);
+        stream_first_kernel<<<1, 1024, 0, st>>>(P);
+        stream_gather_kernel<<<(P.rows + 255) / 256, 256, 0, st>>>(P);
+        count_launch(4);
+        ok = cudaGetLastError() == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess;
+    }
+    if (!ok) {
+        cuda_fail(cudaGetLastError(), "session setup", __FILE__, __LINE__);
+        sess_free(s);
+        return nullptr;
+    }
+    // update grid: column strips x row chunks sized to one resident wave
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stream_update_kernel<4>, 256, 0);
+    if (occ < 1) occ = 1;
+    const int strips = (P.ld / 2 + 255) / 256;
+    int chunks = (sm_count() * occ) / strips;
+    chunks = std::max(1, std::min(chunks, P.rows));
+    s->grid_update = dim3(strips, chunks, 1);
+    return s;
+}
+
+int stream_solve_host(int m, int n, int sense, const double* A, const int* rel, const double* b, const double* c,
+                      const lpx_options* opt, int* status, int* n_pivots, int* pivots, int pivots_cap, int* basis,
+                      double* x, double* z, double* tableau, double* history, int history_cap) {
+    if (history && history_cap > 0) {
+        set_error("per-iteration history is not available on the streaming kernel; use LPX_KERNEL_CTA_GLOBAL");
+        return LPX_E_CAPACITY;
+    }
+    lpx_session* s = lpx_session_open(m, n, sense, A, rel, b, c, opt);
+    if (!s) return LPX_E_CUDA;
+    int st = LPX_RUNNING, np = 0, rc = LPX_OK;
+    while (st == LPX_RUNNING && rc == LPX_OK) rc = lpx_session_step(s, 512, &st, &np);
+    if (rc == LPX_OK) {
+        if (status) *status = st;
+        if (n_pivots) *n_pivots = np;
+        if (pivots && pivots_cap > 0) rc = lpx_session_read_pivots(s, pivots, pivots_cap);
+        const bool solved = st >= 0 || st == LPX_S_ITER_LIMIT;
+        if (rc == LPX_OK && solved && (basis || x || z)) rc = lpx_session_read_solution(s, basis, x, z);
+        if (rc == LPX_OK && solved && tableau) rc = lpx_session_read_tableau(s, tableau);
+    }
+    lpx_session_close(s);
+    return rc;
+}
+
+}  // namespace lpx
+
+extern "C" {
+
+lpx_session* lpx_session_open_dev(int m, int n, int sense, const double* A, const int* rel, const double* b,
+                                  const double* c, const lpx_options* opt) {
+    if (m < 1 || n < 1 || !A || !b || !c || (sense != 0 && sense != 1)) {
+        set_error("lpx_session_open_dev: bad arguments");
+        return nullptr;
+    }
+    return session_create(m, n, sense, A, rel, b, c, opt);
+}
+
+lpx_session* lpx_session_open(int m, int n, int sense, const double* A, const int* rel, const double* b,
+                              const double* c, const lpx_options* opt) {
+    if (m < 1 || n < 1 || !A || !b || !c || (sense != 0 && sense != 1)) {
+        set_error("lpx_session_open: bad arguments");
+        return nullptr;
+    }
+    if (ensure_device() != LPX_OK) return nullptr;
+    std::lock_guard<std::recursive_mutex> lk(rt().mu);
+    double *dA = nullptr, *db = nullptr, *dc = nullptr;
+    lpx_session* s = nullptr;
+    if (cudaMalloc(&dA, (size_t)m * n * 8) == cudaSuccess && cudaMalloc(&db, (size_t)m * 8) == cudaSuccess &&
+        cudaMalloc(&dc, (size_t)n * 8) == cudaSuccess &&
+        cudaMemcpy(dA, A, (size_t)m * n * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+        cudaMemcpy(db, b, (size_t)m * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+        cudaMemcpy(dc, c, (size_t)n * 8, cudaMemcpyHostToDevice) == cudaSuccess) {
+        s = session_create(m, n, sense, dA, rel, db, dc, opt);
+    } else {
+        cuda_fail(cudaGetLastError(), "lpx_session_open: staging inputs", __FILE__, __LINE__);
+    }
+    cudaFree(dA);
+    cudaFree(db);
+    cudaFree(dc);
+    return s;
+}
+
+int lpx_session_step_async(lpx_session* s, int max_pivots) {
+    if (!s || max_pivots < 0) {
+        set_error("lpx_session_step_async: bad arguments");
+        return LPX_E_BAD_ARGS;
+    }
+    for (int k = 0; k < max_pivots; k++) {
+        int rc = launch_pair(s, 0);
+        if (rc != LPX_OK) return rc;
+    }
+    return LPX_OK;
+}
+
+int lpx_session_sync(lpx_session* s, int* status, int* pivots_total) {
+    if (!s) {
+        set_error("lpx_session_sync: null session");
+        return LPX_E_BAD_ARGS;
+    }
+    // probe: resolves OPTIMAL / UNBOUNDED / ITER_LIMIT for the tableau as it stands, no pivot
+    int rc = launch_pair(s, 1);
+    if (rc != LPX_OK) return rc;
+    StreamCtl h;
+    LPX_CUDA(cudaMemcpyAsync(&h, s->P.ctl, sizeof h, cudaMemcpyDeviceToHost, s->stream));
+    LPX_CUDA(cudaStreamSynchronize(s->stream));
+    if (status) *status = h.status;
+    if (pivots_total) *pivots_total = h.pivots;
+    return LPX_OK;
+}
+
+int lpx_session_step(lpx_session* s, int max_pivots, int* status, int* pivots_total) {
+    int rc = lpx_session_step_async(s, max_pivots);
+    if (rc != LPX_OK) return rc;
+    return lpx_session_sync(s, status, pivots_total);
+}
+
+void* lpx_session_stream(lpx_session* s) { return s ? (void*)s->stream : nullptr; }
+
+int lpx_session_dims(const lpx_session* s, int* rows, int* cols) {
+    if (!s) return LPX_E_BAD_ARGS;
+    if (rows) *rows = s->P.rows;
+    if (cols) *cols = s->P.width;
+    return LPX_OK;
+}
+
+int lpx_session_read_tableau(lpx_session* s, double* tableau) {
+    if (!s || !tableau) return LPX_E_BAD_ARGS;
+    LPX_CUDA(cudaMemcpy2DAsync(tableau, (size_t)s->P.width * 8, s->P.T, (size_t)s->P.ld * 8, (size_t)s->P.width * 8,
+                               s->P.rows, cudaMemcpyDeviceToHost, s->stream));
+    LPX_CUDA(cudaStreamSynchronize(s->stream));
+    return LPX_OK;
+}
+
+int lpx_session_read_solution(lpx_session* s, int* basis, double* x, double* z) {
+    if (!s) return LPX_E_BAD_ARGS;
+    const int m = s->P.m, n = s->P.n;
+    std::vector<int> hb(m);
+    std::vector<double> hr(s->P.rows);
+    LPX_CUDA(cudaMemcpyAsync(hb.data(), s->P.basis, (size_t)m * 4, cudaMemcpyDeviceToHost, s->stream));
+    LPX_CUDA(cudaMemcpyAsync(hr.data(), s->P.rhsbuf, (size_t)s->P.rows * 8, cudaMemcpyDeviceToHost, s->stream));
+    LPX_CUDA(cudaStreamSynchronize(s->stream));
+    if (basis) std::memcpy(basis, hb.data(), (size_t)m * 4);
+    if (x) {
+        for (int j = 0; j < n; j++) x[j] = 0.0;
+        for (int i = 0; i < m; i++)
+            if (hb[i] < n) x[hb[i]] = hr[i];
+    }
+    if (z) *z = hr[m];
+    return LPX_OK;
+}
+
+int lpx_session_read_pivots(lpx_session* s, int* pivots, int pivots_cap) {
+    if (!s || !pivots || pivots_cap < 0) return LPX_E_BAD_ARGS;
+    StreamCtl h;
+    LPX_CUDA(cudaMemcpyAsync(&h, s->P.ctl, sizeof h, cudaMemcpyDeviceToHost, s->stream));
+    LPX_CUDA(cudaStreamSynchronize(s->stream));
+    const int k = std::min(std::min(h.pivots, pivots_cap), s->P.pivlog_cap);
+    if (k > 0) LPX_CUDA(cudaMemcpy(pivots, s->P.pivlog, (size_t)k * 8, cudaMemcpyDeviceToHost));
+    return LPX_OK;
+}
+
+void lpx_session_close(lpx_session* s) { sess_free(s); }
+
+}  // extern "C"

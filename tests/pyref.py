@@ -1,0 +1,389 @@
+"""Second, independent restatement of the reference's algorithms in plain Python loops (IEEE
+doubles, no FMA), written straight from the C# sources.  Small cases only.  It exists to pin the
+C++ oracle: tests/golden/*.json is produced by this file (tests/golden/make_golden.py) and the
+oracle, the CUDA path and this file must all agree bit for bit.
+
+  primal()    R/Models/PrimalSimplex.cs:57-127, 161-257
+  dual()      R/Models/DualSimplex.cs:15-114, 117-158, 195-246
+  bnb()       R/Models/Branch&Bound.cs:30-258
+  knapsack()  R/Models/BranchAndBoundKnapsack.cs:58-328, 431-547
+"""
+import math
+
+EPS = 1e-9
+LE, GE, EQ = 0, 1, 2
+
+
+class SolveError(Exception):
+    def __init__(self, code, msg):
+        super().__init__(msg)
+        self.code = code
+
+
+def _build(rows_a, rows_b, c):
+    m, n = len(rows_a), len(c)
+    w = n + m + 1
+    T = [[0.0] * w for _ in range(m + 1)]
+    for i in range(m):
+        for j in range(n):
+            T[i][j] = rows_a[i][j]
+        T[i][n + i] = 1.0
+        T[i][n + m] = rows_b[i]
+    for j in range(n):
+        T[m][j] = -c[j]
+    return T, list(range(n, n + m))
+
+
+def _entering(T):
+    m = len(T) - 1
+    best, mv = -1, -EPS
+    for j in range(len(T[0]) - 1):
+        if T[m][j] < mv:
+            mv, best = T[m][j], j
+    return best
+
+
+def _leaving(T, e, margin):
+    m = len(T) - 1
+    best, row = math.inf, -1
+    for i in range(m):
+        a = T[i][e]
+        if a > EPS:
+            r = T[i][-1] / a
+            if r < best - margin:
+                best, row = r, i
+    return row
+
+
+def _pivot(T, r, c):
+    piv = T[r][c]
+    T[r] = [v / piv for v in T[r]]
+    for i in range(len(T)):
+        if i == r:
+            continue
+        f = T[i][c]
+        T[i] = [T[i][j] - f * T[r][j] for j in range(len(T[i]))]
+
+
+def primal(A, b, c, rel=None, sense=0, max_iterations=10000, history=False):
+    m = len(A)
+    rel = rel if rel is not None else [LE] * m
+    c = [-v for v in c] if sense == 1 else list(c)
+    for i in range(m):
+        if rel[i] == GE:
+            raise SolveError(-1, "ge")
+        if b[i] < -1e-9:
+            raise SolveError(-2, "negrhs")
+    ra, rb = [], []
+    for i in range(m):
+        ra.append(list(A[i]))
+        rb.append(b[i])
+        if rel[i] == EQ:
+            ra.append([v * -1 for v in A[i]])
+            rb.append(b[i] * -1)
+    T, basis = _build(ra, rb, c)
+    pivots, hist = [], [[row[:] for row in T]] if history else None
+    it = 1
+    status = 0
+    while True:
+        if it > max_iterations:
+            raise SolveError(-3, "iter")
+        e = _entering(T)
+        if e == -1:
+            break
+        l = _leaving(T, e, 1e-9)
+        if l == -1:
+            status = 1
+            break
+        _pivot(T, l, e)
+        basis[l] = e
+        pivots.append((e, l))
+        if history:
+            hist.append([row[:] for row in T])
+        it += 1
+    n = len(c)
+    x = [0.0] * n
+    for i in range(len(T) - 1):
+        if basis[i] < n:
+            x[basis[i]] = T[i][-1]
+    return dict(status=status, pivots=pivots, basis=basis, x=x, z=T[-1][-1], tableau=T, history=hist)
+
+
+def dual(A, b, c, rel=None, sense=0):
+    m = len(A)
+    rel = rel if rel is not None else [LE] * m
+    c = [-v for v in c] if sense == 1 else list(c)
+    ra, rb = [], []
+    for i in range(m):
+        if rel[i] == EQ:
+            ra.append(list(A[i]))
+            rb.append(b[i])
+            ra.append([v * -1 for v in A[i]])
+            rb.append(-b[i])
+        else:
+            a, bb = list(A[i]), b[i]
+            if rel[i] == GE:
+                a = [v * -1 for v in a]
+                bb = bb * -1
+            if bb < -EPS:
+                a = [v * -1 for v in a]
+                bb = bb * -1
+            ra.append(a)
+            rb.append(bb)
+    T, basis = _build(ra, rb, c)
+    pivots = []
+    silent = 0
+    for _ in range(100):
+        e = _entering(T)
+        if e == -1:
+            break
+        l = _leaving(T, e, 1e-12)
+        if l == -1:
+            break
+        _pivot(T, l, e)
+        basis[l] = e
+        pivots.append((e, l))
+        silent += 1
+    mm = len(T) - 1
+    ns = len(T[0]) - 1
+    it = 1
+    while True:
+        if it > 10000:
+            raise SolveError(-3, "iter")
+        leave, mn = -1, -EPS
+        for i in range(mm):
+            if T[i][ns] < mn:
+                mn, leave = T[i][ns], i
+        if leave == -1:
+            status = 0
+            break
+        enter, best = -1, math.inf
+        for j in range(ns):
+            a = T[leave][j]
+            if a < -EPS:
+                r = T[mm][j] / (-a)
+                if r < best - 1e-12:
+                    best, enter = r, j
+        if enter == -1:
+            status = 2
+            break
+        _pivot(T, leave, enter)
+        basis[leave] = enter
+        pivots.append((enter, leave))
+        it += 1
+    n = len(c)
+    x = [0.0] * n
+    for i in range(mm):
+        if basis[i] < n:
+            x[basis[i]] = T[i][-1]
+    return dict(status=status, pivots=pivots, silent=silent, basis=basis, x=x, z=T[-1][-1], tableau=T)
+
+
+def _round_even(v):
+    return float(round(v))  # Python round() is ties-to-even like Math.Round
+
+
+def bnb(A, b, c, rel=None, sense=0):
+    """Returns (found, best_z, best_x, node outcomes in solve order)."""
+    BB = 1e-6
+    n = len(c)
+    m0 = len(A)
+    rel0 = list(rel) if rel is not None else [LE] * m0
+    state = dict(best=-math.inf, best_x=None, counter=1, nodes=[])
+
+    def algo(rl):
+        return 1 if any(r in (GE, EQ) for r in rl) else 0
+
+    def feasible(x, Ar, rl, br):
+        for a, r, bb in zip(Ar, rl, br):
+            s = 0.0
+            for i in range(n):
+                s += a[i] * x[i]
+            if r == LE and s > bb + BB:
+                return False
+            if r == GE and s < bb - BB:
+                return False
+            if r == EQ and abs(s - bb) > BB:
+                return False
+        return all(v >= -BB for v in x)
+
+    def integral(x):
+        return all(abs(v - _round_even(v)) <= BB for v in x)
+
+    def solve_lp(Ar, rl, br):
+        if algo(rl) == 1:
+            try:
+                dual(Ar, br, c, rl, sense)
+            except SolveError:
+                return "error", None, None
+            return "invalid", None, None
+        try:
+            r = primal(Ar, br, c, rl, sense)
+        except SolveError:
+            return "error", None, None
+        return "ok", r["x"], r["z"]
+
+    def node(Ar, rl, br, depth):
+        if depth > 200:
+            state["nodes"].append(7)
+            return
+        st, x, z = solve_lp(Ar, rl, br)
+        if st == "error":
+            state["nodes"].append(0)
+            return
+        if st == "invalid":
+            state["nodes"].append(1)
+            return
+        if not feasible(x, Ar, rl, br):
+            state["nodes"].append(2)
+            return
+        if z <= state["best"] + BB:
+            state["nodes"].append(3)
+            return
+        if integral(x):
+            state["best"] = z
+            state["best_x"] = [_round_even(v) for v in x]
+            state["nodes"].append(4)
+            return
+        fi, md = -1, float("inf")
+        for i in range(n):
+            fp = x[i] - math.floor(x[i])
+            if fp > BB and (1 - fp) > BB:
+                d = abs(fp - 0.5)
+                if d < md or (d == md and i < fi):
+                    md, fi = d, i
+        if fi == -1:
+            state["nodes"].append(6)
+            return
+        fl, ce = int(math.floor(x[fi])), int(math.ceil(x[fi]))
+        state["nodes"].append(5)
+        unit = [0.0] * n
+        unit[fi] = 1.0
+        node(Ar + [unit], rl + [GE], br + [float(ce)], depth + 1)
+        node(Ar + [unit], rl + [LE], br + [float(fl)], depth + 1)
+
+    Ar = [list(r) for r in A]
+    st, x, z = solve_lp(Ar, rel0, list(b))
+    if st != "ok":
+        state["nodes"].append(0 if st == "error" else 1)
+        return False, -math.inf, None, state["nodes"]
+    if integral(x) and feasible(x, Ar, rel0, list(b)):
+        state["nodes"].append(4)
+        return True, z, [_round_even(v) for v in x], state["nodes"]
+    state["nodes"].append(5)
+    node(Ar, rel0, list(b), 0)
+    return state["best_x"] is not None, state["best"], state["best_x"], state["nodes"]
+
+
+def knapsack(p, w, cap):
+    """Returns (found, best, best_x, evals) with evals = [(bound, weight, frac_rank, decision), ...]."""
+    n = len(p)
+    KE = 1e-9
+
+    def ratio(i):
+        return p[i] / w[i] if w[i] > 0 else math.inf
+
+    order = sorted(range(n), key=lambda i: (-ratio(i), -p[i]))  # stable
+    # python's sort with a tuple key is stable and matches OrderByDescending.ThenByDescending
+    rank_of = {o: s for s, o in enumerate(order)}
+
+    def relax(assigned):
+        relaxed = [0.0] * n
+        weight = profit = 0.0
+        frac = -1
+        for i in range(n):
+            if assigned[i] == 1:
+                relaxed[i] = 1.0
+                weight += w[i]
+                profit += p[i]
+        if weight > cap + KE:
+            return relaxed, profit, -1, weight
+        for s in range(n):
+            o = order[s]
+            if assigned[o] == 1:
+                continue
+            if assigned[o] == 0:
+                continue
+            if weight + w[o] <= cap + KE:
+                relaxed[o] = 1.0
+                weight += w[o]
+                profit += p[o]
+            else:
+                remain = cap - weight
+                if remain > KE and w[o] > KE:
+                    f = remain / w[o]
+                    relaxed[o] = f
+                    profit += p[o] * f
+                    weight += w[o] * f
+                    frac = s
+                break
+        return relaxed, profit, frac, weight
+
+    heap = []
+
+    def push(item):
+        heap.append(item)
+        ci = len(heap) - 1
+        while ci > 0:
+            pi = (ci - 1) // 2
+            if not heap[ci][0] > heap[pi][0]:
+                break
+            heap[ci], heap[pi] = heap[pi], heap[ci]
+            ci = pi
+
+    def pop():
+        li = len(heap) - 1
+        heap[0], heap[li] = heap[li], heap[0]
+        ret = heap.pop()
+        li = len(heap) - 1
+        i = 0
+        while True:
+            l, r, big = 2 * i + 1, 2 * i + 2, i
+            if l <= li and heap[l][0] > heap[big][0]:
+                big = l
+            if r <= li and heap[r][0] > heap[big][0]:
+                big = r
+            if big == i:
+                break
+            heap[i], heap[big] = heap[big], heap[i]
+            i = big
+        return ret
+
+    best, best_x = -math.inf, [0] * n
+    evals = []
+    root = [-1] * n
+    rr = relax(root)
+    evals.append((rr[1], rr[3], rr[2], 0))
+    push((rr[1], root))
+    pops = 0
+    while heap:
+        bound, assigned = pop()
+        pops += 1
+        if bound <= best + KE:
+            continue
+        relaxed, prof, frac, wt = relax(assigned)
+        if frac == -1:
+            if wt <= cap + KE and prof > best + KE:
+                best = prof
+                best_x = [1 if v >= 0.5 else 0 for v in relaxed]
+            continue
+        o = order[frac]
+        for side in (0, 1):
+            ch = assigned[:]
+            ch[o] = side
+            rl, pr, fr, cw = relax(ch)
+            if cw > cap + KE:
+                dec = 1
+            elif pr > best + KE:
+                if all(abs(v - _round_even(v)) < KE for v in rl):
+                    dec = 2
+                    if pr > best + KE:
+                        best = pr
+                        best_x = [int(_round_even(v)) for v in rl]
+                else:
+                    dec = 3
+                    push((pr, ch))
+            else:
+                dec = 4
+            evals.append((pr, cw, fr, dec))
+    return best > -math.inf, best, best_x, evals, pops, order
