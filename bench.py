@@ -1,0 +1,441 @@
+#!/usr/bin/env python
+"""bench.py — simplex pivots/sec and B&B nodes/sec on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload batched|large]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A step is one pass of the hot path over one batch of synthetic input:
+  batched (default, BASELINE config 2): 4096 dense LPs of 64 x 128 per GPU, one launch of the
+      per-tableau kernel; `value` = pivots/sec with inputs resident in HBM, `e2e` = the same through
+      lpx_primal_solve_batched with pinned HOST buffers (H2D + D2H inside the timed call).
+  large (BASELINE config 3): a window of pivots of one 4096 x 8192 LP, HBM-streamed.
+The line also carries `large_tableau`, `bnb_simplex` and `bnb_knapsack` sections (configs 3-5).
+Multi-GPU: independent problems per rank (weak scaling, no data-path collective); torch.distributed
+only provides the barrier and the max-over-ranks of the timings.
+
+--impl reference: the reference's own CPU implementation of the path.  The C# binary cannot run
+here (no .NET); the timed code is the C++ restatement in oracle/ on all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C2 = dict(count=4096, m=64, n=128)
+C3 = dict(m=4096, n=8192)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the oracle (C++ restatement of the C# loops) on all host threads
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc_ffi
+    from linear_programming_solver_lpr381_b200 import workloads
+    cores = os.cpu_count() or 1
+    if args.workload == "large":
+        A, b, c = workloads.large_c3(**C3)
+        m, n = A.shape
+        T = np.zeros((m + 1, n + m + 1))
+        T[:m, :n] = A
+        T[:m, n:n + m] = np.eye(m)
+        T[:m, -1] = b
+        T[m, :n] = -c
+        basis = np.arange(n, n + m, dtype=np.int32)
+        per_step = 4
+        times = []
+        for s in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            orc_ffi.primal_core(T, basis, per_step)
+            dt = time.perf_counter() - t0
+            if s >= args.warmup:
+                times.append(dt)
+        total = per_step * len(times)
+        value = total / sum(times)
+        used, sample = 1, f"{per_step} pivots per step of the 4096x8192 tableau (single tableau: one thread, as upstream)"
+        cfg = {"workload": "C3 single large dense LP 4096x8192, window of pivots", **C3}
+    else:
+        A, b, c = workloads.batch_c2(**C2, seed=1)
+        times, piv = [], 0
+        for s in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            r = orc_ffi.primal_batch(A, b, c, threads=cores, with_format=False, want_tableau=True)
+            dt = time.perf_counter() - t0
+            if s >= args.warmup:
+                times.append(dt)
+                piv += int(r["total_pivots"])
+        value = piv / sum(times)
+        used, sample = cores, "full 4096-LP batch per step, arithmetic loop only (no per-iteration text formatting)"
+        cfg = {"workload": "C2 batched dense LPs: 4096 x (64 constraints x 128 vars)", **C2}
+    line = {
+        "impl": "reference", "metric": "simplex pivots/sec", "value": value, "unit": "pivots/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": cfg,
+        "cpu_baseline": {"value": value, "unit": "pivots/s", "cores": used, "kind": "port", "sample": sample,
+                         "note": "C++ restatement of the reference's C# loops (oracle/); the C# binary cannot be "
+                                 "built here (no .NET toolchain)"},
+        "e2e": {"value": value, "unit": "pivots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from linear_programming_solver_lpr381_b200 import _ffi as F
+    from linear_programming_solver_lpr381_b200 import api, workloads
+
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    F.check(F.lib().lpx_init(local_rank))
+    hbm_peak, peak_kind = load_peaks()
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    extras = {}
+    sampler = ClockSampler(local_rank)
+
+    # ---------------- config 3: large tableau (value when --workload large, else a section) ------
+    def bench_large(steps, warmup, per_step):
+        A, b, c = workloads.large_c3(**C3, seed=7 + rank)
+        dA, db, dc = (torch.from_numpy(v).to(dev) for v in (A, b, c))
+        torch.cuda.synchronize()
+        s = api.Session(dA.data_ptr(), db.data_ptr(), dc.data_ptr(), device_ptrs=True, m=C3["m"], n=C3["n"],
+                        max_iterations=1 << 30)
+        del dA
+        rows, cols = s.rows, s.cols
+        sstream = torch.cuda.ExternalStream(s.stream)
+        for _ in range(warmup):
+            s.step_async(per_step)
+        s.sync()
+        barrier()
+        l0 = F.lib().lpx_kernel_launches()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for k in range(steps):
+            ev[k][0].record(sstream)
+            s.step_async(per_step)
+            ev[k][1].record(sstream)
+        st, tot = s.sync()
+        barrier()
+        launches = F.lib().lpx_kernel_launches() - l0 - 1
+        ms = [a.elapsed_time(bb) for a, bb in ev]
+        total_ms = max_over_ranks(sum(ms))
+        done = per_step * steps
+        if st != F.RUNNING:
+            raise SystemExit(f"large LP finished early (status {st}) inside the timed window")
+        bytes_per_pivot = 2 * 8 * rows * cols
+        pivots_s = world * done / (total_ms * 1e-3)
+        ach = bytes_per_pivot * done / (sum(ms) * 1e-3) / 1e9
+        s.close()
+        return dict(value=pivots_s, ms_per_step=total_ms / steps, launches=launches, rows=rows, cols=cols,
+                    pivots_per_step=per_step,
+                    roofline={"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                              "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_kind,
+                              "algorithmic_bytes_per_pivot": bytes_per_pivot,
+                              "note": "select + update kernels of one pivot timed together; bytes = one read + one "
+                                      "write of the (m+1)x(n+m+1) tableau"})
+
+    # ---------------- config 2: batched --------------------------------------------------------
+    def bench_batched(steps, warmup):
+        A, b, c = workloads.batch_c2(**C2, seed=1 + rank)
+        count, m, n = A.shape
+        rows, cols = m + 1, n + m + 1
+        dA, db, dc = (torch.from_numpy(v).to(dev) for v in (A, b, c))
+        st = torch.zeros(count, dtype=torch.int32, device=dev)
+        npv = torch.zeros(count, dtype=torch.int32, device=dev)
+        basis = torch.zeros((count, m), dtype=torch.int32, device=dev)
+        x = torch.zeros((count, n), dtype=torch.float64, device=dev)
+        z = torch.zeros(count, dtype=torch.float64, device=dev)
+        T = torch.zeros((count, rows, cols), dtype=torch.float64, device=dev)
+        tot = torch.zeros(1, dtype=torch.int64, device=dev)
+
+        def launch():
+            api.primal_solve_batched_dev(count, m, n, 0, dA.data_ptr(), None, db.data_ptr(), dc.data_ptr(),
+                                         st.data_ptr(), npv.data_ptr(), basis.data_ptr(), x.data_ptr(), z.data_ptr(),
+                                         T.data_ptr(), tot.data_ptr(), stream.cuda_stream)
+
+        for _ in range(warmup):
+            launch()
+        barrier()
+        tot.zero_()
+        l0 = F.lib().lpx_kernel_launches()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        sampler.start()
+        barrier()
+        for k in range(steps):
+            ev[k][0].record(stream)
+            launch()
+            ev[k][1].record(stream)
+        barrier()
+        clocks = sampler.stop()
+        launches = F.lib().lpx_kernel_launches() - l0
+        ms = [a.elapsed_time(bb) for a, bb in ev]
+        total_ms = max_over_ranks(sum(ms))
+        pivots = int(tot.item())
+        all_pivots = sum_over_ranks(pivots)
+        value = all_pivots / (total_ms * 1e-3)
+        assert int((st != 0).sum().item()) == 0, "a batched LP did not reach OPTIMAL"
+
+        # e2e: the reference-facing call, pinned host buffers in and out
+        hA, hb, hc = F.PinnedArray(A.shape), F.PinnedArray(b.shape), F.PinnedArray(c.shape)
+        hA.array[...] = A
+        hb.array[...] = b
+        hc.array[...] = c
+        out = dict(status=F.PinnedArray((count,), np.int32).array, n_pivots=F.PinnedArray((count,), np.int32).array,
+                   basis=F.PinnedArray((count, m), np.int32).array, x=F.PinnedArray((count, n)).array,
+                   z=F.PinnedArray((count,)).array, tableau=F.PinnedArray((count, rows, cols)).array)
+        h2d = A.nbytes + b.nbytes + c.nbytes
+        d2h = sum(v.nbytes for v in out.values())
+        for _ in range(max(1, warmup)):
+            api.primal_solve_batched(hA.array, hb.array, hc.array, out=out)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_piv = 0
+        for _ in range(steps):
+            r = api.primal_solve_batched(hA.array, hb.array, hc.array, out=out)
+            e2e_piv += r["total_pivots"]
+        torch.cuda.synchronize()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        e2e_value = sum_over_ranks(e2e_piv) / e2e_s
+
+        # roofline of the per-tableau kernel: on-chip, bounded by the unfused FP64 rate
+        rate = F.C.c_double()
+        F.check(F.lib().lpx_measure_fp64_rate(F.C.byref(rate)))
+        flops_per_pivot = 2 * m * cols + cols
+        ach_tf = flops_per_pivot * pivots / (sum(ms) * 1e-3) / 1e12
+        hbm_bytes = (A.nbytes + b.nbytes + c.nbytes) + T.numel() * 8 + x.numel() * 8 + basis.numel() * 4
+        roof = {"bound": "fp64", "achieved": ach_tf, "peak": rate.value, "unit": "TFLOP/s",
+                "frac": ach_tf / rate.value if rate.value else None, "traffic": None,
+                "peak_source": "measured in this run: unfused DMUL+DADD issue rate (lpx_measure_fp64_rate); FMA is "
+                               "excluded by the bit-exactness contract",
+                "flops_per_pivot": flops_per_pivot,
+                "hbm": {"bound": "hbm", "achieved": hbm_bytes * steps / (sum(ms) * 1e-3) / 1e9, "peak": hbm_peak,
+                        "unit": "GB/s", "algorithmic_bytes_per_launch": hbm_bytes, "peak_source": peak_kind,
+                        "note": "inputs read once + final tableaux/x/basis written once; the tableau lives on-chip "
+                                "across all pivots, so this kernel is not HBM-bound"}}
+        return dict(value=value, ms_per_step=total_ms / steps, launches=launches, clocks=clocks, pivots_per_step=pivots,
+                    e2e={"value": e2e_value, "unit": "pivots/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                         "ms_per_step": 1e3 * e2e_s / steps}, roofline=roof, host=(A, b, c))
+
+    # ---------------- configs 4 and 5 (sections) ------------------------------------------------
+    def bench_bnb(count):
+        As, bs, cs = zip(*[workloads.ip_c4(seed=1000 * rank + 11 + k) for k in range(count)])
+        A, b, c = np.stack(As), np.stack(bs), np.stack(cs)
+        api.bnb_simplex_batched(A[:1], b[:1], c[:1])
+        barrier()
+        l0 = F.lib().lpx_kernel_launches()
+        t0 = time.perf_counter()
+        r = api.bnb_simplex_batched(A, b, c)
+        dt = max_over_ranks(time.perf_counter() - t0)
+        nodes = sum_over_ranks(int(r["n_nodes"].sum()))
+        return {"metric": "B&B simplex nodes/sec (LP relaxations solved per second)", "value": nodes / dt,
+                "unit": "nodes/s", "instances_per_gpu": count, "nodes": nodes, "lp_pivots": sum_over_ranks(int(r["lp_pivots"].sum())),
+                "seconds": dt, "gpu_launches": F.lib().lpx_kernel_launches() - l0,
+                "mode": "reference-exact tree (SURVEY F5), independent instances per GPU, host commit in DFS order",
+                "timing": "end to end through lpx_bnb_simplex_batched (host buffers)"}
+
+    def bench_knap(count):
+        ps, ws, caps = zip(*[workloads.knapsack_c5(seed=1000 * rank + 13 + k) for k in range(count)])
+        p, w, cap = np.stack(ps), np.stack(ws), np.array(caps)
+        api.bnb_knapsack_batched(p[:1], w[:1], cap[:1])
+        barrier()
+        l0 = F.lib().lpx_kernel_launches()
+        t0 = time.perf_counter()
+        r = api.bnb_knapsack_batched(p, w, cap)
+        dt = max_over_ranks(time.perf_counter() - t0)
+        nodes = sum_over_ranks(int(r["n_evals"].sum()))
+        return {"metric": "B&B knapsack nodes/sec (ComputeRelaxation evaluations committed per second)",
+                "value": nodes / dt, "unit": "nodes/s", "instances_per_gpu": count, "nodes": nodes, "seconds": dt,
+                "gpu_launches": F.lib().lpx_kernel_launches() - l0,
+                "timing": "end to end through lpx_bnb_knapsack_batched (host buffers)"}
+
+    # ---------------- CPU baseline on rank 0, N = 1 ---------------------------------------------
+    def cpu_baseline(host):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import orc_ffi
+        A, b, c = host
+        t0 = time.perf_counter()
+        piv = 0
+        reps = 0
+        while time.perf_counter() - t0 < 8.0:
+            piv += int(orc_ffi.primal_batch(A, b, c, threads=1)["total_pivots"])
+            reps += 1
+        dt = time.perf_counter() - t0
+        sub = slice(0, 64)
+        t1 = time.perf_counter()
+        pf = int(orc_ffi.primal_batch(A[sub], b[sub], c[sub], threads=1, with_format=True)["total_pivots"])
+        dtf = time.perf_counter() - t1
+        return {"value": piv / dt, "unit": "pivots/s", "cores": 1, "kind": "port",
+                "sample": f"the full 4096-LP C2 batch x {reps} passes, single thread, arithmetic loop only",
+                "with_reference_text_formatting": {"value": pf / dtf, "unit": "pivots/s",
+                                                   "sample": "first 64 LPs of the batch, one thread, including the "
+                                                             "reference's unconditional per-iteration AppendTableau"},
+                "host_cores_available": os.cpu_count(),
+                "note": "C++ restatement (oracle/) of the C# loops, not the C# binary (no .NET toolchain here)"}
+
+    if args.workload == "large":
+        per_step = 20
+        L = bench_large(args.steps, args.warmup, per_step)
+        line = {"metric": "simplex pivots/sec", "value": L["value"], "unit": "pivots/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": L["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "C3 single large dense LP 4096x8192 (tableau 4097x12289), window of "
+                                       f"{per_step} pivots per step", **C3, "inputs_larger_than_L2": True},
+                "roofline": L["roofline"], "gpu_launches": L["launches"], "cpu_baseline": None,
+                "e2e": {"value": L["value"], "unit": "pivots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                        "note": "the tableau is resident in HBM for the whole session; only 16 bytes of status "
+                                "cross PCIe per step"}}
+    else:
+        Bm = bench_batched(args.steps, args.warmup)
+        host = Bm.pop("host")
+        if not args.no_extras:
+            try:
+                Lg = bench_large(3, 3, 20)
+                extras["large_tableau"] = {"metric": "simplex pivots/sec, one 4096x8192 LP (tableau 4097x12289)",
+                                           "value": Lg["value"], "unit": "pivots/s", "ms_per_pivot":
+                                           Lg["ms_per_step"] / Lg["pivots_per_step"], "roofline": Lg["roofline"],
+                                           "gpu_launches": Lg["launches"]}
+            except Exception as e:  # a section must not take the headline down
+                extras["large_tableau"] = {"error": str(e)}
+            try:
+                extras["bnb_simplex"] = bench_bnb(16)
+            except Exception as e:
+                extras["bnb_simplex"] = {"error": str(e)}
+            try:
+                extras["bnb_knapsack"] = bench_knap(16)
+            except Exception as e:
+                extras["bnb_knapsack"] = {"error": str(e)}
+        line = {"metric": "simplex pivots/sec", "value": Bm["value"], "unit": "pivots/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": Bm["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "C2 batched dense LPs: 4096 x (64 constraints x 128 vars) per GPU, one CTA "
+                                       "per tableau", **C2, "pivots_per_step_per_gpu": Bm["pivots_per_step"],
+                           "inputs_larger_than_L2": True, "l2_note": "275 MB of inputs and 411 MB of result "
+                           "tableaux per step exceed the 126 MB L2; no flush needed"},
+                "roofline": Bm["roofline"], "e2e": Bm["e2e"], "gpu_launches": Bm["launches"], "clocks": Bm["clocks"],
+                "cpu_baseline": cpu_baseline(host) if (rank == 0 and world == 1) else None}
+        line.update(extras)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="batched", choices=["batched", "large"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs 3-5 sections")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -232,6 +232,11 @@ void lpx_comm_destroy(void);
 int lpx_comm_world(void);
 int lpx_comm_rank(void);
 
+/* ---- measurement helpers (bench.py) --------------------------------------------------------- */
+/* Unfused FP64 rate (separate DMUL and DADD, the only arithmetic the bit-exactness contract
+ * allows) in TFLOP/s: the roofline denominator of the on-chip batched kernels. */
+int lpx_measure_fp64_rate(double* tflops);
+
 /* ---- counters (for benchmarks: "how many of my kernels launched") --------------------------- */
 long long lpx_kernel_launches(void);   /* since lpx_init / last reset */
 void lpx_reset_counters(void);

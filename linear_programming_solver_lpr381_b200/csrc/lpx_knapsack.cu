@@ -679,6 +679,7 @@ struct KnDriver {
             }
         }
 
+        int stalled = 0;
         while (true) {
             Plan pl;
             bool any = false;
@@ -719,8 +720,9 @@ struct KnDriver {
                 if (rc != LPX_OK) return rc;
                 if (I.pops != before || I.done) progressed = true;
             }
-            if (!progressed && pl.in.empty()) {
-                set_error("knapsack: node pool exhausted (no progress possible)");
+            stalled = progressed ? 0 : stalled + 1;
+            if (stalled > 2 || (!progressed && pl.in.empty())) {
+                set_error("knapsack: no progress possible (node pool exhausted?)");
                 return LPX_E_CAPACITY;
             }
         }

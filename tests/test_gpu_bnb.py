@@ -1,0 +1,168 @@
+"""GPU parity: Branch & Bound (simplex) and Branch & Bound Knapsack through the C ABI."""
+import numpy as np
+import pytest
+
+from conftest import assert_bits_equal, case_arrays, unhex
+
+from linear_programming_solver_lpr381_b200 import workloads
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["ip_floor_path", "ip_integral_root", "ip_with_ge_root", "ip_three_vars"])
+def test_bnb_kat(lpx, kat, name):
+    case = kat["ip"][name]
+    A, b, c, rel = case_arrays(case)
+    r = lpx.bnb_simplex(A, b, c, rel, case["sense"], trace=True)
+    assert r["found"] == case["found"]
+    assert [nd["outcome"] for nd in r["nodes"]] == case["node_outcomes"]
+    if case["found"]:
+        assert_bits_equal([r["best_z"]], [unhex(case["best_z"])], "best_z")
+        assert_bits_equal(r["best_x"], unhex(case["best_x"]), "best_x")
+
+
+def compare_bnb(got, want, what):
+    assert got["found"] == want["found"], what
+    assert got["n_nodes"] == want["n_nodes"], what
+    assert [nd["outcome"] for nd in got["nodes"]] == want["outcome"].tolist(), what
+    assert [nd["algo"] for nd in got["nodes"]] == want["algo"].tolist(), what
+    assert [nd["n_pivots"] for nd in got["nodes"]] == want["pivots"].tolist(), what
+    assert [nd["depth"] for nd in got["nodes"]] == want["depth"].tolist(), what
+    assert got["lp_pivots"] == want["total_pivots"], what
+    zs = [nd["z"] if nd["algo"] == 0 and nd["lp_status"] >= 0 else 0.0 for nd in got["nodes"]]
+    assert_bits_equal(zs, want["z"], what + " node z")
+    assert [nd["branch_var"] for nd in got["nodes"]] == want["branch_var"].tolist(), what
+    if want["found"]:
+        assert_bits_equal([got["best_z"]], [want["best_z"]], what + " best_z")
+        assert_bits_equal(got["best_x"], want["best_x"], what + " best_x")
+
+
+def test_bnb_random_small(lpx, orc):
+    rng = np.random.default_rng(31)
+    for t in range(25):
+        m, n = int(rng.integers(2, 7)), int(rng.integers(2, 9))
+        A = rng.integers(1, 12, size=(m, n)).astype(float)
+        b = rng.integers(10, 80, size=m).astype(float)
+        c = rng.integers(1, 15, size=n).astype(float)
+        want = orc.bnb_simplex(A, b, c)
+        got = lpx.bnb_simplex(A, b, c, trace=True)
+        compare_bnb(got, want, f"case {t}")
+
+
+def test_bnb_c4_instance(lpx, orc):
+    """BASELINE config 4: 60 x 120 general IP, every node of the reference's tree."""
+    A, b, c = workloads.ip_c4(seed=11)
+    want = orc.bnb_simplex(A, b, c)
+    got = lpx.bnb_simplex(A, b, c, trace=True)
+    compare_bnb(got, want, "C4 seed 11")
+    # node tableaux outgrow shared memory on the way down: both kernel variants were exercised
+    assert max(nd["rows"] * nd["cols"] for nd in got["nodes"]) * 8 > 227 * 1024
+
+
+def test_bnb_batched_instances(lpx, orc):
+    count = 6
+    As, bs, cs = zip(*[workloads.ip_c4(m=20, n=30, seed=40 + k) for k in range(count)])
+    got = lpx.bnb_simplex_batched(np.stack(As), np.stack(bs), np.stack(cs))
+    for k in range(count):
+        want = orc.bnb_simplex(As[k], bs[k], cs[k])
+        assert bool(got["found"][k]) == want["found"]
+        assert got["n_nodes"][k] == want["n_nodes"]
+        assert got["lp_pivots"][k] == want["total_pivots"]
+        if want["found"]:
+            assert_bits_equal([got["best_z"][k]], [want["best_z"]], f"best_z {k}")
+            assert_bits_equal(got["best_x"][k], want["best_x"], f"best_x {k}")
+
+
+def test_bnb_node_history(lpx, orc, kat):
+    case = kat["ip"]["ip_floor_path"]
+    A, b, c, rel = case_arrays(case)
+    r = lpx.bnb_simplex(A, b, c, rel, case["sense"], want_history=True)
+    root = r["nodes"][0]
+    want = orc.primal_solve(A, b, c, rel, case["sense"], history=True)
+    assert_bits_equal(root["history"], want["history"], "root history")
+    # the ceil child runs Dual Simplex on "x2 >= 2" (flipped twice into "x2 <= 2", DualSimplex.cs:141-153)
+    ceil = r["nodes"][2]
+    assert ceil["algo"] == 1 and ceil["outcome"] == 1
+    A2 = np.vstack([A, [0.0, 1.0]])
+    w2 = orc.dual_solve(A2, np.append(b, 2.0), c, np.append(rel, 1).astype(np.int32), case["sense"], history=True)
+    assert ceil["n_pivots"] == w2["n_pivots"] and ceil["silent"] == w2["silent"]
+    assert_bits_equal(ceil["history"], w2["history"], "dual child history")
+
+
+# ---- knapsack -----------------------------------------------------------------------------------
+
+def knap_events(got):
+    ev = []
+    for p in got["pops"]:
+        if p["left"] is not None:
+            for side in ("left", "right"):
+                e = p[side]
+                ev.append((e["bound"], e["weight"], e["frac_rank"], e["decision"], p["pop_index"], e["child"], e["var"]))
+    return ev
+
+
+def compare_knap(got, want, what):
+    assert got["found"] == want["found"], what
+    assert got["n_pops"] == want["n_pops"], what
+    assert got["n_evals"] == want["n_evals"], what
+    assert got["best_x"].tolist() == want["best_x"].tolist(), what
+    if want["found"]:
+        assert_bits_equal([got["best"]], [want["best"]], what + " best")
+    if "pops" in got:
+        ev = knap_events(got)
+        assert len(ev) == want["n_evals"] - 1, what
+        assert_bits_equal([e[0] for e in ev], want["bound"][1:], what + " bounds")
+        assert_bits_equal([e[1] for e in ev], want["weight"][1:], what + " weights")
+        assert [e[2] for e in ev] == want["frac"][1:].tolist(), what
+        assert [e[3] for e in ev] == want["decision"][1:].tolist(), what
+        assert [e[4] for e in ev] == want["parent"][1:].tolist(), what
+        assert [e[6] for e in ev] == want["var"][1:].tolist(), what
+
+
+@pytest.mark.parametrize("name", ["knap_classic", "knap_ties", "knap_all_fit", "knap_zero_weight",
+                                  "knap_fractional_data", "knap_nothing_fits"])
+def test_knapsack_kat(lpx, orc, kat, name):
+    case = kat["knap"][name]
+    p, w, cap = unhex(case["p"]), unhex(case["w"]), unhex(case["cap"])
+    got = lpx.bnb_knapsack(p, w, cap, trace=True)
+    assert got["rank_order"].tolist() == case["rank_order"]
+    compare_knap(got, orc.knapsack(p, w, cap, eval_cap=4096), name)
+
+
+@pytest.mark.parametrize("spec", [(1, 1), (4, 2), (8, 3), (16, 5)])
+def test_knapsack_random_any_speculation(lpx, orc, spec):
+    rng = np.random.default_rng(55)
+    for t in range(10):
+        n = int(rng.integers(3, 40))
+        w = np.round(rng.random(n) * 20 + 0.5, 2)
+        p = np.round(rng.random(n) * 30 + 0.5, 2)
+        cap = float(np.round(w.sum() * 0.45, 2))
+        want = orc.knapsack(p, w, cap, eval_cap=1 << 18)
+        got = lpx.bnb_knapsack(p, w, cap, trace=True, spec_nodes=spec[0], spec_depth=spec[1])
+        compare_knap(got, want, f"case {t} spec={spec}")
+
+
+@pytest.mark.parametrize("kind", ["uncorrelated", "weak", "fractional"])
+def test_knapsack_c5(lpx, orc, kind):
+    """BASELINE config 5: 2000 items."""
+    p, w, cap = workloads.knapsack_c5(kind=kind)
+    want = orc.knapsack(p, w, cap)
+    got = lpx.bnb_knapsack(p, w, cap)
+    compare_knap(got, want, kind)
+
+
+def test_knapsack_c5_trace(lpx, orc):
+    p, w, cap = workloads.knapsack_c5(n=300, seed=4, kind="fractional")
+    want = orc.knapsack(p, w, cap)
+    got = lpx.bnb_knapsack(p, w, cap, trace=True)
+    compare_knap(got, want, "n=300 fractional trace")
+
+
+def test_knapsack_batched(lpx, orc):
+    ps, ws, caps = zip(*[workloads.knapsack_c5(n=400, seed=100 + k) for k in range(5)])
+    got = lpx.bnb_knapsack_batched(np.stack(ps), np.stack(ws), np.array(caps))
+    for k in range(5):
+        want = orc.knapsack(ps[k], ws[k], caps[k])
+        assert got["n_evals"][k] == want["n_evals"] and got["n_pops"][k] == want["n_pops"]
+        assert_bits_equal([got["best"][k]], [want["best"]], f"best {k}")
+        assert got["best_x"][k].tolist() == want["best_x"].tolist()

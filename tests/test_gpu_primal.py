@@ -1,0 +1,203 @@
+"""GPU parity: Primal / Dual Simplex through the C ABI against the oracle and the golden cases.
+Bit-exact: status, pivot sequence, basis, every double of x, z and the tableau (incl. -0.0)."""
+import numpy as np
+import pytest
+
+from conftest import assert_bits_equal, case_arrays, unhex
+
+from linear_programming_solver_lpr381_b200 import _ffi as F
+from linear_programming_solver_lpr381_b200 import workloads
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = [F.KERNEL_AUTO, F.KERNEL_CTA_SMEM, F.KERNEL_CTA_GLOBAL, F.KERNEL_STREAM]
+LP_NAMES = ["wyndor", "unbounded", "degenerate_tie", "near_tie_margin", "near_tie_margin_rev", "eq_expansion",
+            "min_trivial", "min_negative_costs", "ge_row", "neg_rhs", "neg_rhs_tolerated", "iter_limit_hit",
+            "iter_limit_ok", "zero_cost_negzero", "klee_minty3"]
+
+
+def compare_primal(got, want, what):
+    assert got["status"] == want["status"], what
+    if want["status"] < 0 and want["status"] != F.S_ITER_LIMIT:
+        return
+    assert got["n_pivots"] == want["n_pivots"], what
+    assert got["pivots"].tolist() == want["pivots"].tolist(), what
+    if want["status"] == F.S_ITER_LIMIT:
+        return
+    assert got["basis"].tolist() == want["basis"].tolist(), what
+    assert_bits_equal(got["x"], want["x"], what + " x")
+    assert_bits_equal([got["z"]], [want["z"]], what + " z")
+    assert_bits_equal(got["tableau"], want["tableau"], what + " tableau")
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("name", LP_NAMES)
+def test_primal_kat(lpx, kat, name, kernel):
+    case = kat["lp"][name]
+    A, b, c, rel = case_arrays(case)
+    r = lpx.primal_solve(A, b, c, rel, case["sense"], max_iterations=case["max_iterations"], kernel=kernel)
+    assert r["status"] == case["status"]
+    if case["status"] < 0:
+        return
+    assert r["pivots"].tolist() == case["pivots"]
+    assert r["basis"].tolist() == case["basis"]
+    assert_bits_equal(r["x"], unhex(case["x"]), "x")
+    assert_bits_equal([r["z"]], [unhex(case["z"])], "z")
+    assert_bits_equal(r["tableau"], unhex(case["tableau"]), "tableau")
+
+
+@pytest.mark.parametrize("kernel", [F.KERNEL_CTA_SMEM, F.KERNEL_CTA_GLOBAL])
+def test_history_matches_oracle(lpx, orc, kernel):
+    p = orc.parse_text(workloads.WYNDOR_TEXT)
+    want = orc.primal_solve(p["A"], p["b"], p["c"], p["rel"], p["sense"], history=True)
+    got = lpx.primal_solve(p["A"], p["b"], p["c"], p["rel"], p["sense"], history=8, kernel=kernel)
+    assert_bits_equal(got["history"], want["history"], "history")
+    A, b, c = workloads.lp_integer(12, 20, 4)
+    want = orc.primal_solve(A, b, c, history=True)
+    got = lpx.primal_solve(A, b, c, history=want["n_pivots"] + 1, kernel=kernel)
+    assert_bits_equal(got["history"], want["history"], "history 12x20")
+
+
+@pytest.mark.parametrize("name", ["dual_ge", "dual_mixed", "dual_eq", "dual_infeasible", "dual_ge_child_becomes_le"])
+@pytest.mark.parametrize("kernel", [F.KERNEL_CTA_SMEM, F.KERNEL_CTA_GLOBAL])
+def test_dual_kat(lpx, kat, name, kernel):
+    case = kat["dual"][name]
+    A, b, c, rel = case_arrays(case)
+    r = lpx.dual_solve(A, b, c, rel, case["sense"], kernel=kernel)
+    assert r["status"] == case["status"] and r["silent"] == case["silent"]
+    assert r["pivots"].tolist() == case["pivots"]
+    assert r["basis"].tolist() == case["basis"]
+    assert_bits_equal(r["x"], unhex(case["x"]), "x")
+    assert_bits_equal(r["tableau"], unhex(case["tableau"]), "tableau")
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_random_small_vs_oracle(lpx, orc, kernel):
+    rng = np.random.default_rng(101)
+    for t in range(60):
+        m, n = int(rng.integers(1, 24)), int(rng.integers(1, 40))
+        A = rng.integers(-3, 10, size=(m, n)).astype(float)
+        b = rng.integers(0, 40, size=m).astype(float)
+        c = rng.integers(-4, 10, size=n).astype(float)
+        rel = rng.choice([0, 0, 0, 0, 2], size=m).astype(np.int32)
+        sense = int(rng.integers(0, 2))
+        want = orc.primal_solve(A, b, c, rel, sense, max_iterations=300)
+        got = lpx.primal_solve(A, b, c, rel, sense, max_iterations=300, kernel=kernel)
+        compare_primal(got, want, f"case {t} m={m} n={n} kernel={kernel}")
+
+
+def test_random_dual_vs_oracle(lpx, orc):
+    rng = np.random.default_rng(77)
+    for t in range(60):
+        m, n = int(rng.integers(1, 16)), int(rng.integers(1, 24))
+        A = rng.integers(0, 9, size=(m, n)).astype(float)
+        b = rng.integers(1, 25, size=m).astype(float)
+        c = rng.integers(1, 9, size=n).astype(float)
+        rel = rng.choice([0, 1, 2], size=m).astype(np.int32)
+        sense = int(rng.integers(0, 2))
+        want = orc.dual_solve(A, b, c, rel, sense)
+        got = lpx.dual_solve(A, b, c, rel, sense)
+        assert got["status"] == want["status"] and got["silent"] == want["silent"], t
+        assert got["pivots"].tolist() == want["pivots"].tolist(), t
+        assert_bits_equal(got["tableau"], want["tableau"], f"dual tableau {t}")
+        assert_bits_equal(got["x"], want["x"], f"dual x {t}")
+
+
+def test_tie_free_decimal_mid_size(lpx, orc):
+    for kernel in (F.KERNEL_CTA_SMEM, F.KERNEL_CTA_GLOBAL, F.KERNEL_STREAM):
+        A, b, c = workloads.lp_decimal(40, 70, 12)
+        want = orc.primal_solve(A, b, c)
+        got = lpx.primal_solve(A, b, c, kernel=kernel)
+        compare_primal(got, want, f"decimal 40x70 kernel={kernel}")
+
+
+@pytest.mark.parametrize("kind", ["integer", "decimal"])
+@pytest.mark.parametrize("kernel", [F.KERNEL_AUTO, F.KERNEL_CTA_SMEM, F.KERNEL_CTA_GLOBAL])
+def test_batched_c2_shape(lpx, orc, kind, kernel):
+    A, b, c = workloads.batch_c2(count=192, seed=5, kind=kind)
+    want = orc.primal_batch(A, b, c, threads=8, want_tableau=True)
+    got = lpx.primal_solve_batched(A, b, c, kernel=kernel)
+    assert np.array_equal(got["status"], want["status"])
+    assert np.array_equal(got["n_pivots"], want["n_pivots"])
+    assert got["total_pivots"] == want["total_pivots"]
+    assert np.array_equal(got["basis"], want["basis"])
+    assert_bits_equal(got["x"], want["x"], "x")
+    assert_bits_equal(got["z"], want["z"], "z")
+    assert_bits_equal(got["tableau"], want["tableau"], "tableau")
+
+
+def test_batched_full_c2_against_oracle(lpx, orc):
+    """BASELINE config 2 at full size: 4096 LPs of 64 x 128, every output bit compared."""
+    A, b, c = workloads.batch_c2(count=4096, seed=1)
+    want = orc.primal_batch(A, b, c, threads=8, want_tableau=True)
+    got = lpx.primal_solve_batched(A, b, c)
+    assert np.array_equal(got["status"], want["status"])
+    assert np.array_equal(got["n_pivots"], want["n_pivots"])
+    assert np.array_equal(got["basis"], want["basis"])
+    assert_bits_equal(got["z"], want["z"], "z")
+    assert_bits_equal(got["x"], want["x"], "x")
+    assert_bits_equal(got["tableau"], want["tableau"], "tableau")
+    # size-independent properties: basic columns are exact unit vectors, z = c_B . x_B on integers
+    T = got["tableau"]
+    k = 17
+    for i, col in enumerate(got["basis"][k]):
+        unit = np.zeros(65)
+        unit[i] = 1.0
+        assert np.array_equal(np.abs(T[k][:, col]), unit)
+
+
+def test_batched_edge_cases(lpx, orc):
+    # empty batch
+    r = lpx.primal_solve_batched(np.zeros((0, 3, 4)), np.zeros((0, 3)), np.zeros((0, 4)))
+    assert r["total_pivots"] == 0 and r["status"].shape == (0,)
+    # batch of one, 1 x 1
+    r = lpx.primal_solve_batched(np.array([[[2.0]]]), np.array([[6.0]]), np.array([[1.0]]))
+    assert r["status"][0] == 0 and r["x"][0, 0] == 3.0 and r["z"][0] == 3.0
+    # a batch that mixes optimal, unbounded and negative-RHS instances, with an EQ row pattern
+    rng = np.random.default_rng(3)
+    A = rng.integers(-2, 8, size=(40, 6, 9)).astype(float)
+    b = rng.integers(-1, 30, size=(40, 6)).astype(float)
+    c = rng.integers(-3, 9, size=(40, 9)).astype(float)
+    rel = np.array([0, 2, 0, 0, 2, 0], dtype=np.int32)
+    got = lpx.primal_solve_batched(A, b, c, rel=rel, max_iterations=50)
+    for k in range(40):
+        want = orc.primal_solve(A[k], b[k], c[k], rel, 0, max_iterations=50)
+        assert got["status"][k] == want["status"], k
+        if want["status"] >= 0:
+            assert got["n_pivots"][k] == want["n_pivots"]
+            assert_bits_equal(got["tableau"][k], want["tableau"], f"tableau {k}")
+            assert_bits_equal(got["x"][k], want["x"], f"x {k}")
+
+
+def test_batched_device_pointers(lpx, orc):
+    torch = pytest.importorskip("torch")
+    A, b, c = workloads.batch_c2(count=128, seed=9)
+    dev = torch.device("cuda:0")
+    dA, db, dc = (torch.from_numpy(v).to(dev) for v in (A, b, c))
+    count, m, n = A.shape
+    st = torch.zeros(count, dtype=torch.int32, device=dev)
+    npv = torch.zeros(count, dtype=torch.int32, device=dev)
+    basis = torch.zeros((count, m), dtype=torch.int32, device=dev)
+    x = torch.zeros((count, n), dtype=torch.float64, device=dev)
+    z = torch.zeros(count, dtype=torch.float64, device=dev)
+    T = torch.zeros((count, m + 1, n + m + 1), dtype=torch.float64, device=dev)
+    tot = torch.zeros(1, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    lpx.primal_solve_batched_dev(count, m, n, 0, dA.data_ptr(), None, db.data_ptr(), dc.data_ptr(), st.data_ptr(),
+                                 npv.data_ptr(), basis.data_ptr(), x.data_ptr(), z.data_ptr(), T.data_ptr(),
+                                 tot.data_ptr(), stream)
+    torch.cuda.synchronize()
+    want = orc.primal_batch(A, b, c, threads=8, want_tableau=True)
+    assert np.array_equal(st.cpu().numpy(), want["status"])
+    assert int(tot.item()) == want["total_pivots"]
+    assert_bits_equal(T.cpu().numpy(), want["tableau"], "tableau")
+    assert_bits_equal(x.cpu().numpy(), want["x"], "x")
+
+
+def test_wide_and_tall_shapes(lpx, orc):
+    for (m, n, seed) in [(3, 300, 1), (150, 5, 2), (100, 100, 3), (130, 260, 4)]:
+        A, b, c = workloads.lp_integer(m, n, seed)
+        want = orc.primal_solve(A, b, c)
+        for kernel in (F.KERNEL_AUTO, F.KERNEL_CTA_GLOBAL, F.KERNEL_STREAM):
+            got = lpx.primal_solve(A, b, c, kernel=kernel)
+            compare_primal(got, want, f"{m}x{n} kernel={kernel}")

@@ -1,0 +1,98 @@
+"""GPU parity for the whole-GPU streaming kernels (BASELINE config 3) through lpx_session_*."""
+import numpy as np
+import pytest
+
+from conftest import assert_bits_equal
+
+from linear_programming_solver_lpr381_b200 import _ffi as F
+from linear_programming_solver_lpr381_b200 import workloads
+
+pytestmark = pytest.mark.gpu
+
+
+def build_tableau(A, b, c):
+    m, n = A.shape
+    T = np.zeros((m + 1, n + m + 1))
+    T[:m, :n] = A
+    T[:m, n:n + m] = np.eye(m)
+    T[:m, -1] = b
+    T[m, :n] = -c
+    return T
+
+
+def test_medium_full_solve(lpx, orc):
+    A, b, c = workloads.lp_integer(256, 512, 7)
+    want = orc.primal_solve(A, b, c)
+    s = lpx.Session(A, b, c)
+    st, tot = F.RUNNING, 0
+    while st == F.RUNNING:
+        st, tot = s.step(64)
+    assert st == want["status"] and tot == want["n_pivots"]
+    assert s.pivots(tot)[:tot].tolist() == want["pivots"].tolist()
+    basis, x, z = s.solution()
+    assert basis.tolist() == want["basis"].tolist()
+    assert_bits_equal(x, want["x"], "x")
+    assert_bits_equal([z], [want["z"]], "z")
+    assert_bits_equal(s.tableau(), want["tableau"], "tableau")
+    s.close()
+
+
+def test_step_granularity_is_invisible(lpx):
+    A, b, c = workloads.lp_decimal(96, 200, 3)
+    s1 = lpx.Session(A, b, c)
+    s2 = lpx.Session(A, b, c)
+    s1.step(3)
+    s1.step(5)
+    st1, t1 = s1.step(4)
+    st2, t2 = s2.step(12)
+    assert (st1, t1) == (st2, t2)
+    assert_bits_equal(s1.tableau(), s2.tableau(), "tableau")
+    s1.close()
+    s2.close()
+
+
+def test_iteration_limit_and_unbounded(lpx, orc):
+    A, b, c = workloads.lp_integer(64, 128, 2)
+    want = orc.primal_solve(A, b, c, max_iterations=5)
+    s = lpx.Session(A, b, c, max_iterations=5)
+    st, tot = s.step(100)
+    assert st == F.S_ITER_LIMIT == want["status"] and tot == 5
+    assert s.pivots(5)[:5].tolist() == want["pivots"].tolist()
+    s.close()
+    A = np.array([[1.0, -1.0], [-1.0, 1.0]])
+    s = lpx.Session(A, np.array([1.0, 2.0]), np.array([1.0, 1.0]))
+    st, tot = s.step(10)
+    w = orc.primal_solve(A, np.array([1.0, 2.0]), np.array([1.0, 1.0]))
+    assert st == w["status"] == F.UNBOUNDED and tot == w["n_pivots"]
+    assert_bits_equal(s.tableau(), w["tableau"], "unbounded tableau")
+    s.close()
+
+
+def test_c3_full_size_first_pivots(lpx, orc):
+    """4096 x 8192: the first pivots against the oracle's arithmetic loop, every tableau bit."""
+    A, b, c = workloads.large_c3()
+    npiv = 6
+    s = lpx.Session(A, b, c)
+    assert (s.rows, s.cols) == (4097, 12289)
+    st, tot = s.step(npiv)
+    assert st == F.RUNNING and tot == npiv
+    T = build_tableau(A, b, c)
+    basis = np.arange(8192, 8192 + 4096, dtype=np.int32)
+    ost, onp, opiv = orc.primal_core(T, basis, npiv)
+    assert onp == npiv
+    assert s.pivots(npiv)[:npiv].tolist() == opiv.tolist()
+    got = s.tableau()
+    assert_bits_equal(got, T, "C3 tableau after %d pivots" % npiv)
+    gb, gx, gz = s.solution()
+    assert gb.tolist() == basis.tolist()
+    assert_bits_equal([gz], [T[-1, -1]], "z")
+    # size-independent property over a longer window: basic columns stay exact unit vectors
+    st, tot = s.step(40)
+    got = s.tableau()
+    gb, gx, gz = s.solution()
+    for i in (0, 17, 4095):
+        col = got[:, gb[i]]
+        unit = np.zeros(4097)
+        unit[i] = 1.0
+        assert np.array_equal(np.abs(col), unit)
+    s.close()
