@@ -1,0 +1,71 @@
+// P/Invoke declarations for liblpx.so (include/lpx.h).  Source only: this image has no .NET
+// toolchain, so the file is not compiled here; the identical C ABI is exercised by the C++ host
+// layer (../host) and by the ctypes harness (../_ffi.py).
+using System;
+using System.Runtime.InteropServices;
+
+namespace Linear_Programming_Solver.Models
+{
+    [StructLayout(LayoutKind.Sequential)]
+    internal struct LpxOptions
+    {
+        public int max_iterations, kernel, threads;
+        public int r0, r1, r2, r3, r4;
+    }
+
+    [StructLayout(LayoutKind.Sequential)]
+    internal struct LpxBnbNode
+    {
+        public int index, depth, parent, is_ceil_child, id_path_len;
+        public IntPtr id_path;
+        public int bound_var, bound_val, algo, lp_status, outcome, n_pivots, silent_pivots;
+        public IntPtr pivots;
+        public int rows, cols;
+        public double z;
+        public IntPtr x;
+        public int branch_var, floor_val, ceil_val, n_history;
+        public IntPtr history;
+    }
+
+    [UnmanagedFunctionPointer(CallingConvention.Cdecl)]
+    internal delegate void LpxBnbNodeFn(ref LpxBnbNode node, IntPtr user);
+
+    internal static class LpxNative
+    {
+        const string Lib = "lpx";   // liblpx.so on Linux
+
+        [DllImport(Lib)] public static extern void lpx_default_options(ref LpxOptions opt);
+        [DllImport(Lib)] public static extern IntPtr lpx_last_error();
+        [DllImport(Lib)] public static extern IntPtr lpx_status_message(int status);
+        [DllImport(Lib)] public static extern int lpx_init(int device);
+        [DllImport(Lib)] public static extern int lpx_tableau_dims(int m, int n, int[] rel, out int rows, out int cols);
+
+        [DllImport(Lib)]
+        public static extern int lpx_primal_solve(int m, int n, int sense, double[] A, int[] rel, double[] b, double[] c,
+            ref LpxOptions opt, out int status, out int n_pivots, int[] pivots, int pivots_cap, int[] basis,
+            double[] x, out double z, double[] tableau, double[] history, int history_cap);
+
+        [DllImport(Lib)]
+        public static extern int lpx_dual_solve(int m, int n, int sense, double[] A, int[] rel, double[] b, double[] c,
+            ref LpxOptions opt, out int status, out int n_pivots, out int silent_pivots, int[] pivots, int pivots_cap,
+            int[] basis, double[] x, out double z, double[] tableau, double[] history, int history_cap);
+
+        [DllImport(Lib)]
+        public static extern int lpx_primal_solve_batched(int count, int m, int n, int sense, double[] A, int[] rel,
+            double[] b, double[] c, ref LpxOptions opt, int[] status, int[] n_pivots, int[] basis, double[] x,
+            double[] z, double[] tableau, out long total_pivots);
+
+        [DllImport(Lib)]
+        public static extern int lpx_bnb_simplex(int m, int n, int sense, double[] A, int[] rel, double[] b, double[] c,
+            ref LpxOptions opt, int flags, out int found, out double best_z, double[] best_x, out int n_nodes,
+            out long n_lp_pivots, out int root_status, LpxBnbNodeFn on_node, IntPtr user);
+
+        [DllImport(Lib)]
+        public static extern int lpx_bnb_knapsack(int n, double[] profit, double[] weight, double capacity,
+            ref LpxOptions opt, out int found, out double best_value, int[] best_x, out long n_evals, out long n_pops,
+            int[] rank_order, IntPtr on_pop, IntPtr user);
+
+        public static string LastError() => Marshal.PtrToStringUTF8(lpx_last_error()) ?? "";
+        public static string StatusMessage(int s) => Marshal.PtrToStringUTF8(lpx_status_message(s)) ?? "";
+    }
+}

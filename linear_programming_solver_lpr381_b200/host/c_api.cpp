@@ -1,0 +1,95 @@
+// C wrappers over the host layer for ctypes (tests) — the host layer itself is C++.
+#include <cstring>
+#include <string>
+
+#include "dotnet_text.hpp"
+#include "lp_model.hpp"
+
+using namespace lpr381;
+
+struct lpr_text {
+    int code = 0, chunks = 0, highlighted = 0;
+    std::string error, log, report, summary;
+};
+
+static thread_local std::string t_buf;
+
+extern "C" {
+
+void lpr_set_newline(const char* nl) { NewLine() = nl; }
+
+// algorithm: any LPSolver key; "knapsack" constructs BranchAndBoundKnapsack directly (it has no
+// LPSolver key upstream); "controller" goes through LPController.SolvePrimalSimplex (no callback).
+lpr_text* lpr_solve_text(const char* input, const char* algorithm) {
+    lpr_text* t = new lpr_text();
+    UpdatePivot cb = [t](const std::string& s, const Highlight& h) {
+        t->log += s;
+        t->chunks++;
+        if (h.rows) t->highlighted++;
+    };
+    try {
+        LPProblem p = LPParser::ParseFromText(input);
+        SimplexResult r;
+        const std::string algo = algorithm;
+        if (algo == "knapsack") r = BranchAndBoundKnapsack().Solve(p, cb);
+        else if (algo == "controller") r = LPController::SolvePrimalSimplex(p);
+        else r = LPSolver().Solve(p, algo, cb);
+        t->report = r.Report;
+        t->summary = r.Summary;
+    } catch (const LpException& e) {
+        t->code = e.code ? e.code : -1;
+        t->error = e.what();
+    }
+    return t;
+}
+int lpr_text_code(const lpr_text* t) { return t->code; }
+int lpr_text_chunks(const lpr_text* t) { return t->chunks; }
+int lpr_text_highlighted(const lpr_text* t) { return t->highlighted; }
+const char* lpr_text_error(const lpr_text* t) { return t->error.c_str(); }
+const char* lpr_text_log(const lpr_text* t) { return t->log.c_str(); }
+const char* lpr_text_report(const lpr_text* t) { return t->report.c_str(); }
+const char* lpr_text_summary(const lpr_text* t) { return t->summary.c_str(); }
+void lpr_text_free(lpr_text* t) { delete t; }
+
+// two-phase like the oracle's: A == NULL -> sizes only
+int lpr_parse_text(const char* text, int* sense, int* m, int* n, double* A, int* rel, double* b, double* c,
+                   char* err, int err_cap) {
+    try {
+        LPProblem p = LPParser::ParseFromText(text);
+        *sense = (int)p.ObjectiveSense;
+        *m = (int)p.Constraints.size();
+        *n = p.NumVars();
+        if (A) {
+            for (int j = 0; j < *n; j++) c[j] = p.C[j];
+            for (int i = 0; i < *m; i++) {
+                for (int j = 0; j < *n; j++)
+                    A[(size_t)i * *n + j] = j < (int)p.Constraints[i].A.size() ? p.Constraints[i].A[j] : 0.0;
+                rel[i] = (int)p.Constraints[i].Relation;
+                b[i] = p.Constraints[i].B;
+            }
+        }
+        return 0;
+    } catch (const LpException& e) {
+        if (err && err_cap > 0) {
+            std::strncpy(err, e.what(), err_cap - 1);
+            err[err_cap - 1] = 0;
+        }
+        return -6;
+    }
+}
+
+const char* lpr_normalize_key(const char* algorithm) {
+    try {
+        t_buf = LPSolver::NormalizeAlgorithmKey(algorithm);
+    } catch (const LpException& e) {
+        t_buf = std::string("!") + e.what();
+    }
+    return t_buf.c_str();
+}
+
+const char* lpr_fmt_custom(double v, int decimals) { t_buf = text::custom_hash(v, decimals); return t_buf.c_str(); }
+const char* lpr_fmt_fixed(double v, int decimals) { t_buf = text::fixed(v, decimals); return t_buf.c_str(); }
+const char* lpr_fmt_roundtrip(double v) { t_buf = text::round_trip(v); return t_buf.c_str(); }
+double lpr_math_round(double v, int digits) { return text::math_round(v, digits); }
+
+}  // extern "C"

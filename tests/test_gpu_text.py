@@ -1,0 +1,129 @@
+"""GPU: the host layer (C++ mirror of the controllers over liblpx.so) must print exactly what the
+oracle's restatement of the C# prints: the updatePivot stream, Report and Summary."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import host_ffi as H
+from conftest import case_arrays
+
+from linear_programming_solver_lpr381_b200 import workloads
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def same_text(orc, text, algorithm):
+    want = orc.solve_text(text, algorithm)
+    got = H.solve_text(text, algorithm)
+    assert (got["code"] != 0) == (want["code"] != 0), (got["error"], want["error"])
+    assert got["error"] == want["error"]
+    assert got["log"] == want["log"]
+    assert got["report"] == want["report"]
+    assert got["summary"] == want["summary"]
+    assert got["chunks"] == want["chunks"]
+    return got
+
+
+def kat_text(case):
+    A, b, c, rel = case_arrays(case)
+    return workloads.lp_to_text(A, b, c, rel, case["sense"])
+
+
+def test_wyndor_primal_text(lpx, orc):
+    got = same_text(orc, workloads.WYNDOR_TEXT, "Primal Simplex")
+    assert "TABLEAU Iteration 2" in got["log"] and got["summary"].startswith("Status: OPTIMAL\nz* = 36\nx* = [2, 6]")
+    assert got["highlighted"] == 2
+
+
+@pytest.mark.parametrize("name", ["unbounded", "degenerate_tie", "near_tie_margin", "eq_expansion", "min_trivial",
+                                  "min_negative_costs", "ge_row", "neg_rhs", "zero_cost_negzero", "klee_minty3"])
+@pytest.mark.parametrize("algorithm", ["Primal Simplex", "primal simplex algorithm", "Dual Simplex"])
+def test_kat_text(lpx, orc, kat, name, algorithm):
+    same_text(orc, kat_text(kat["lp"][name]), algorithm)
+
+
+@pytest.mark.parametrize("name", ["dual_ge", "dual_mixed", "dual_eq", "dual_infeasible", "dual_ge_child_becomes_le"])
+def test_dual_text(lpx, orc, kat, name):
+    same_text(orc, kat_text(kat["dual"][name]), "Dual Simplex")
+
+
+def test_unsupported_and_empty_algorithm(lpx, orc):
+    for algo in ("Revised Primal Simplex", "Cutting Plane", "  "):
+        want = orc.solve_text(workloads.WYNDOR_TEXT, algo)
+        got = H.solve_text(workloads.WYNDOR_TEXT, algo)
+        assert got["error"] == want["error"] != ""
+
+
+def test_random_lp_text(lpx, orc):
+    rng = np.random.default_rng(8)
+    for t in range(12):
+        m, n = int(rng.integers(2, 8)), int(rng.integers(2, 9))
+        A = np.round(rng.normal(size=(m, n)) * 4, 2)
+        b = np.round(rng.random(m) * 30, 2)
+        c = np.round(rng.normal(size=n) * 5, 2)
+        rel = rng.choice([0, 0, 2], size=m)
+        text = workloads.lp_to_text(A, b, c, rel, int(rng.integers(0, 2)))
+        same_text(orc, text, "Primal Simplex")
+        same_text(orc, text, "Dual Simplex")
+
+
+@pytest.mark.parametrize("name", ["ip_floor_path", "ip_integral_root", "ip_with_ge_root", "ip_three_vars"])
+def test_bnb_text(lpx, orc, kat, name):
+    got = same_text(orc, kat_text(kat["ip"][name]), "Branch and Bound")
+    if name == "ip_floor_path":
+        assert "Subproblem 2.4: x1 <= 3 is integer feasible. Updated BestObjective = 19.000" in got["log"]
+
+
+def test_bnb_random_text(lpx, orc):
+    rng = np.random.default_rng(12)
+    for t in range(6):
+        m, n = int(rng.integers(2, 5)), int(rng.integers(2, 6))
+        A = rng.integers(1, 12, size=(m, n)).astype(float)
+        b = rng.integers(10, 60, size=m).astype(float)
+        c = rng.integers(1, 15, size=n).astype(float)
+        same_text(orc, workloads.lp_to_text(A, b, c), "bnb")
+
+
+def knap_text(p, w, cap):
+    return workloads.lp_to_text(np.array([w]), np.array([cap]), np.array(p))
+
+
+@pytest.mark.parametrize("name", ["knap_classic", "knap_ties", "knap_all_fit", "knap_zero_weight",
+                                  "knap_fractional_data", "knap_nothing_fits"])
+def test_knapsack_text(lpx, orc, kat, name):
+    from conftest import unhex
+    case = kat["knap"][name]
+    same_text(orc, knap_text(unhex(case["p"]), unhex(case["w"]), unhex(case["cap"])), "knapsack")
+
+
+def test_knapsack_medium_text(lpx, orc):
+    p, w, cap = workloads.knapsack_c5(n=40, seed=2, kind="fractional")
+    same_text(orc, knap_text(p, w, cap), "knapsack")
+
+
+def test_knapsack_requires_one_le_row(lpx, orc):
+    for text in ("Max: 1x1 + 2x2\n1x1 + 1x2 <= 3\n1x1 + 0x2 <= 1\n", "Max: 1x1 + 2x2\n1x1 + 1x2 >= 3\n"):
+        want, got = orc.solve_text(text, "knapsack"), H.solve_text(text, "knapsack")
+        assert got["error"] == want["error"] != ""
+
+
+def test_controller_entry_point(lpx, orc):
+    got = H.solve_text(workloads.WYNDOR_TEXT, "controller")
+    want = orc.solve_text(workloads.WYNDOR_TEXT, "Primal Simplex")
+    assert got["report"] == want["report"] and got["summary"] == want["summary"] and got["chunks"] == 0
+
+
+def test_cli_example_input(lpx, orc, tmp_path):
+    exe = os.path.join(ROOT, "linear_programming_solver_lpr381_b200", "lpr381")
+    example = os.path.join(ROOT, "tests", "golden", "example_input.txt")
+    out = subprocess.run([exe, "Primal Simplex", example], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    want = orc.solve_text(open(example).read(), "Primal Simplex")
+    assert out.stdout == want["log"] + "\n\nFinal Report:\n" + want["report"] + "\n\nSummary:\n" + want["summary"]
+    assert out.stdout == open(os.path.join(ROOT, "tests", "golden", "example_output.txt")).read()
+    bad = subprocess.run([exe, "Primal Simplex"], input="Max: 1x1\n1x1 >= 2\n", capture_output=True, text=True, timeout=120)
+    assert bad.returncode == 1 and "Constraint contains '>=' sign." in bad.stderr
