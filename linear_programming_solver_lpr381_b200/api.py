@@ -75,13 +75,13 @@ def dual_solve(A, b, c, rel=None, sense=0, max_iterations=10000, kernel=F.KERNEL
 
 
 def primal_solve_batched(A, b, c, rel=None, sense=0, max_iterations=10000, kernel=F.KERNEL_AUTO, threads=0,
-                         want_tableau=True, out=None):
+                         want_tableau=True, out=None, reg_variant=0):
     """Host buffers in, host buffers out (the reference-facing call).  `out` may carry
     preallocated (pinned) result arrays to reuse between calls."""
     A, b, c, rel = _prep(A, b, c, rel)
     count, m, n = A.shape
     rows, cols = tableau_dims(m, n, rel)
-    opt = F.make_options(max_iterations, kernel, threads)
+    opt = F.make_options(max_iterations, kernel, threads, reg_variant=reg_variant)
     o = out or {}
     status = o.get("status", None)
     if status is None:
@@ -102,9 +102,9 @@ def primal_solve_batched(A, b, c, rel=None, sense=0, max_iterations=10000, kerne
 
 
 def primal_solve_batched_dev(count, m, n, sense, dA, drel, db, dc, dstatus, dnpiv, dbasis, dx, dz, dtableau, dtotal,
-                             stream, max_iterations=10000, kernel=F.KERNEL_AUTO, threads=0):
+                             stream, max_iterations=10000, kernel=F.KERNEL_AUTO, threads=0, reg_variant=0):
     """All arguments are raw device pointers (ints); asynchronous on `stream` (a cudaStream_t)."""
-    opt = F.make_options(max_iterations, kernel, threads)
+    opt = F.make_options(max_iterations, kernel, threads, reg_variant=reg_variant)
     rc = F.lib().lpx_primal_solve_batched_dev(count, m, n, sense, F.ptr(dA), F.ptr(drel), F.ptr(db), F.ptr(dc),
                                               C.byref(opt), F.ptr(dstatus), F.ptr(dnpiv), F.ptr(dbasis), F.ptr(dx),
                                               F.ptr(dz), F.ptr(dtableau), F.ptr(dtotal), F.ptr(stream or 0))
@@ -114,8 +114,9 @@ def primal_solve_batched_dev(count, m, n, sense, dA, drel, db, dc, dstatus, dnpi
 class Session:
     """Large single LP whose tableau lives in HBM (lpx_session_*)."""
 
-    def __init__(self, A, b, c, rel=None, sense=0, max_iterations=10000, device_ptrs=False, m=None, n=None):
-        opt = F.make_options(max_iterations)
+    def __init__(self, A, b, c, rel=None, sense=0, max_iterations=10000, device_ptrs=False, m=None, n=None,
+                 single_cta_select=0):
+        opt = F.make_options(max_iterations, single_cta_select=single_cta_select)
         if device_ptrs:
             self.m, self.n = m, n
             relp = None if rel is None else np.ascontiguousarray(rel, dtype=np.int32)

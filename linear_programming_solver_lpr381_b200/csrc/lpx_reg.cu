@@ -1,16 +1,259 @@
-// lpx_reg.cu — register-resident batched kernel (placeholder until the kernel lands; the
-// dispatcher never selects it while reg_kernel_supports() is false).
-#include "lpx_common.cuh"
+// lpx_reg.cu — register-resident batched Primal Simplex (BASELINE config 2: 64 x 128).
+//
+// One CTA per tableau, the tableau lives in REGISTERS for the whole solve: warp w owns rows
+// w*R .. w*R+R-1, lane l owns columns l, l+32, .., l+32(C-1) of those rows (R*C doubles per
+// thread); the RHS column is spread over lanes 0..R-1 of each warp.  Per pivot only three small
+// vectors cross shared memory — the entering column (factors), the RHS and the normalised pivot
+// row — so shared-memory traffic drops from 2 x 100 KB per pivot (lpx_cta.cuh) to ~3 KB and the
+// rank-1 update issues at the FP64 rate: R*C unfused DMUL + DSUB per thread, 97 % of them useful
+// at 65 x 193 with NW = 13, R = 5, C = 6.
+//
+// Same rules, same order, same rounding as the reference (R/Models/PrimalSimplex.cs:205-257):
+// entering = warp-shuffle argmin with lowest index on ties, leaving = exact sequential margin
+// scan (every warp repeats it on the staged vectors instead of waiting for a broadcast), pivot =
+// true division then separate multiply and subtract, zero-factor rows included.
+#include "lpx_cta.cuh"
 #include "lpx_stream.hpp"
 
 namespace lpx {
 
-bool reg_kernel_supports(int, int, int, bool) { return false; }
+struct RegBatch {
+    const double* A;
+    const double* b;
+    const double* c;
+    int m, n, sense, max_iter;
+    int* status;
+    int* n_pivots;
+    int* basis;
+    double* x;
+    double* z;
+    double* tableau;
+    unsigned long long* total_pivots;
+};
 
-int reg_launch_batched(int, int, int, int, const double*, const double*, const double*, const lpx_options&, int*, int*,
-                       int*, double*, double*, double*, unsigned long long*, cudaStream_t) {
-    set_error("LPX_KERNEL_CTA_REG: no register-resident kernel is built for this shape");
-    return LPX_E_CAPACITY;
+template <int NW, int R, int C, int OCC>
+__global__ void __launch_bounds__(NW * 32, OCC) reg_simplex_kernel(const RegBatch B) {
+    constexpr int ROWS = NW * R;   // padded rows (>= m + 1)
+    constexpr int COLS = 32 * C;   // padded non-RHS columns (>= n + m)
+    __shared__ double s_f[ROWS];   // entering column = update factors
+    __shared__ double s_rhs[ROWS];
+    __shared__ double s_p[COLS + 1];  // normalised pivot row, [COLS] = its RHS
+    __shared__ int s_basis[ROWS];
+    __shared__ int s_ctl[4];
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int p = blockIdx.x;
+    const int m = B.m, n = B.n, width = n + m + 1;
+    const double* Ap = B.A + (size_t)p * m * n;
+    const double* bp = B.b + (size_t)p * m;
+    const double* cp = B.c + (size_t)p * n;
+    const int wz = m / R, rz = m % R;  // owner of the z-row
+
+    // ---- BuildTableau straight into registers (PrimalSimplex.cs:179-203) ---------------------
+    double t[R][C];
+    double rhsv = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int i = w * R + r;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const int j = lane + 32 * c;
+            double v = 0.0;
+            if (i < m) {
+                if (j < n) v = Ap[(size_t)i * n + j];
+                else if (j == n + i) v = 1.0;
+            } else if (i == m && j < n) {
+                double cj = cp[j];
+                if (B.sense == 1) cj = dneg(cj);
+                v = dneg(cj);
+            }
+            t[r][c] = v;
+        }
+    }
+    if (lane < R && w * R + lane < m) rhsv = bp[w * R + lane];
+    // the reference's up-front check (PrimalSimplex.cs:73-76); '>=' rows cannot occur here
+    if (tid == 0) s_ctl[1] = LPX_RUNNING;
+    for (int i = tid; i < m; i += NW * 32) s_basis[i] = n + i;
+    __syncthreads();
+    if (lane < R && w * R + lane < m && rhsv < -1e-9) s_ctl[1] = LPX_S_NEG_RHS;
+    __syncthreads();
+    int status = s_ctl[1];
+    int n_piv = 0;
+
+    if (status == LPX_RUNNING) {
+        int iter = 1;
+        while (true) {
+            if (iter > B.max_iter) {
+                status = LPX_S_ITER_LIMIT;
+                break;
+            }
+            // ---- ChooseEntering: the warp that owns the z-row ---------------------------------
+            if (w == wz) {
+                ArgMin a;
+                a.v = -LPX_EPS;
+                a.i = INT_MAX;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    if (r == rz) {
+#pragma unroll
+                        for (int c = 0; c < C; c++) {
+                            const double zv = t[r][c];
+                            if (zv < a.v) {
+                                a.v = zv;
+                                a.i = lane + 32 * c;
+                            }
+                        }
+                    }
+                }
+                a = warp_argmin(a);
+                if (lane == 0) s_ctl[0] = a.i == INT_MAX ? -1 : a.i;
+            }
+            __syncthreads();
+            const int e = s_ctl[0];
+            if (e < 0) {
+                status = LPX_OPTIMAL;
+                break;
+            }
+            // ---- stage the entering column and the RHS ----------------------------------------
+            if (lane == (e & 31)) {
+                const int ce = e >> 5;
+#pragma unroll
+                for (int c = 0; c < C; c++) {
+                    if (c == ce) {
+#pragma unroll
+                        for (int r = 0; r < R; r++) s_f[w * R + r] = t[r][c];
+                    }
+                }
+            }
+            if (lane < R) s_rhs[w * R + lane] = rhsv;
+            __syncthreads();
+            // ---- ChooseLeaving: every warp repeats the exact sequential scan ------------------
+            const int lr = warp_margin_scan(m, LPX_MARGIN_PRIMAL, [&](int i, double& ratio) {
+                const double a = s_f[i];
+                if (a > LPX_EPS) {
+                    ratio = __ddiv_rn(s_rhs[i], a);
+                    return true;
+                }
+                return false;
+            });
+            if (lr < 0) {
+                status = LPX_UNBOUNDED;
+                break;
+            }
+            const double piv = s_f[lr];
+            // ---- the owner of the leaving row normalises it (true division) --------------------
+            const int wl = lr / R, rl = lr - wl * R;
+            if (w == wl) {
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    if (r == rl) {
+#pragma unroll
+                        for (int c = 0; c < C; c++) s_p[lane + 32 * c] = __ddiv_rn(t[r][c], piv);
+                    }
+                }
+                if (lane == rl) s_p[COLS] = __ddiv_rn(rhsv, piv);
+            }
+            __syncthreads();
+            // ---- rank-1 update, registers only ------------------------------------------------
+            double f[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) f[r] = s_f[w * R + r];
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                const double pc = s_p[lane + 32 * c];
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const double upd = __dsub_rn(t[r][c], __dmul_rn(f[r], pc));
+                    t[r][c] = (w * R + r == lr) ? pc : upd;
+                }
+            }
+            if (lane < R) {
+                const double pr = s_p[COLS];
+                const double upd = __dsub_rn(rhsv, __dmul_rn(s_f[w * R + lane], pr));
+                rhsv = (w * R + lane == lr) ? pr : upd;
+            }
+            if (tid == 0) s_basis[lr] = e;
+            n_piv++;
+            iter++;
+        }
+        __syncthreads();
+
+        // ---- results ----------------------------------------------------------------------------
+        if (lane < R) s_rhs[w * R + lane] = rhsv;
+        if (B.tableau) {
+            double* To = B.tableau + (size_t)p * (m + 1) * width;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int i = w * R + r;
+                if (i <= m) {
+#pragma unroll
+                    for (int c = 0; c < C; c++) {
+                        const int j = lane + 32 * c;
+                        if (j < width - 1) To[(size_t)i * width + j] = t[r][c];
+                    }
+                }
+            }
+            if (lane < R && w * R + lane <= m) To[(size_t)(w * R + lane) * width + width - 1] = rhsv;
+        }
+        if (B.x) {
+            double* xo = B.x + (size_t)p * n;
+            for (int j = tid; j < n; j += NW * 32) xo[j] = 0.0;
+        }
+        __syncthreads();
+        if (B.basis)
+            for (int i = tid; i < m; i += NW * 32) B.basis[(size_t)p * m + i] = s_basis[i];
+        if (tid == 0) {
+            if (B.x) {
+                double* xo = B.x + (size_t)p * n;
+                for (int i = 0; i < m; i++)
+                    if (s_basis[i] < n) xo[s_basis[i]] = s_rhs[i];
+            }
+            if (B.z) B.z[p] = s_rhs[m];
+        }
+    }
+    if (tid == 0) {
+        B.status[p] = status;
+        if (B.n_pivots) B.n_pivots[p] = n_piv;
+        if (B.total_pivots && n_piv) atomicAdd(B.total_pivots, (unsigned long long)n_piv);
+    }
+}
+
+// Shapes served by the <13, 5, 6> instance: m + 1 <= 65 rows, n + m <= 192 columns, all '<='.
+bool reg_kernel_supports(int m, int n, int m_expanded, bool has_rel) {
+    if (has_rel || m_expanded != m) return false;
+    return m + 1 <= 65 && n + m <= 192 && m >= 1 && n >= 1;
+}
+
+int reg_launch_batched(int count, int m, int n, int sense, const double* A, const double* b, const double* c,
+                       const lpx_options& opt, int* status, int* n_pivots, int* basis, double* x, double* z,
+                       double* tableau, unsigned long long* total_pivots, cudaStream_t stream) {
+    if (!reg_kernel_supports(m, n, m, false)) {
+        set_error("LPX_KERNEL_CTA_REG: no register-resident kernel is built for this shape (need m <= 64, n + m <= 192, "
+                  "all '<=' rows)");
+        return LPX_E_CAPACITY;
+    }
+    if (count <= 0) return LPX_OK;
+    RegBatch B;
+    B.A = A;
+    B.b = b;
+    B.c = c;
+    B.m = m;
+    B.n = n;
+    B.sense = sense;
+    B.max_iter = opt.max_iterations;
+    B.status = status;
+    B.n_pivots = n_pivots;
+    B.basis = basis;
+    B.x = x;
+    B.z = z;
+    B.tableau = tableau;
+    B.total_pivots = total_pivots;
+    // reserved[3] == 2: the 2-CTAs-per-SM build (72 registers, a few spilled doubles) for comparison
+    if (opt.reserved[3] == 2) reg_simplex_kernel<13, 5, 6, 2><<<count, 13 * 32, 0, stream>>>(B);
+    else reg_simplex_kernel<13, 5, 6, 1><<<count, 13 * 32, 0, stream>>>(B);
+    LPX_CUDA(cudaGetLastError());
+    count_launch();
+    return LPX_OK;
 }
 
 }  // namespace lpx

@@ -46,7 +46,11 @@ struct StreamParams {
     int pivlog_cap;
     StreamCtl* ctl;
     int max_iter;
+    ArgMin* partial;  // per prep-CTA argmin of the look-ahead z-row (multi-CTA protocol)
+    int npartial;     // 0: single-CTA select protocol (very tall tableaux)
 };
+
+#define LPX_PREP_THREADS 256
 
 __device__ __forceinline__ double dneg_s(double v) {
     return __longlong_as_double(__double_as_longlong(v) ^ (long long)0x8000000000000000ULL);
@@ -254,15 +258,147 @@ __global__ void __launch_bounds__(1024) stream_select_kernel(StreamParams P, int
     }
 }
 
+// Multi-CTA replacement of stream_select_kernel (the single CTA took ~30 us per pivot, 18 % of the
+// step).  grid = one thread per tableau column.  EVERY CTA repeats the exact ratio test on the two
+// compact vectors (64 KB from L2, ratios parked in shared memory, rows interleaved over the
+// threads so the scan is bank-conflict free), then normalises its own 256 columns of the pivot
+// row and reduces its slice of the look-ahead z-row to one (value, column) pair.  The update
+// kernel combines the pairs.  Field ownership keeps the CTAs race-free: prep CTAs only READ
+// status/pivots/enter; CTA 0 writes leave/k/active (and a terminal status, which makes every
+// other CTA return as well); pivots/enter are advanced by the update kernel.
+__global__ void __launch_bounds__(LPX_PREP_THREADS) stream_prep_kernel(StreamParams P, int probe_only) {
+    extern __shared__ double s_ratio[];
+    __shared__ ArgMin red[34];
+    __shared__ int ired[34];
+    constexpr int TH = LPX_PREP_THREADS;
+    StreamCtl* ctl = P.ctl;
+    const int tid = threadIdx.x;
+    const bool lead = blockIdx.x == 0 && tid == 0;
+    const int status = ctl->status;
+    const int k = ctl->pivots;
+    const int e = ctl->enter;
+    if (lead) ctl->active = 0;
+    if (status != LPX_RUNNING) return;
+    if (k >= P.max_iter) {
+        if (lead) ctl->status = LPX_S_ITER_LIMIT;
+        return;
+    }
+    if (e < 0) {
+        if (lead) ctl->status = LPX_OPTIMAL;
+        return;
+    }
+    const int m = P.m;
+    const double* col = P.colbuf + (size_t)(k & 1) * P.colstride;
+    for (int i = tid; i < m; i += TH) {
+        const double a = col[i];
+        double r = __longlong_as_double(0x7ff8000000000000LL);  // NaN: never eligible
+        if (a > LPX_EPS) r = __ddiv_rn(P.rhsbuf[i], a);
+        s_ratio[i] = r;
+    }
+    __syncthreads();
+    double best = __longlong_as_double(0x7ff0000000000000LL);
+    int row = -1, start = 0;
+    while (true) {
+        const double thr = __dsub_rn(best, LPX_MARGIN_PRIMAL);
+        int cand = INT_MAX;
+        // this thread's rows are tid, tid+TH, ...: its first hit at or after `start`
+        int i = tid;
+        if (start > tid) i = tid + ((start - tid + TH - 1) / TH) * TH;
+        for (; i < m; i += TH)
+            if (s_ratio[i] < thr) {
+                cand = i;
+                break;
+            }
+        cand = block_min_int<TH>(cand, ired);
+        if (cand == INT_MAX) break;
+        best = s_ratio[cand];
+        row = cand;
+        start = cand + 1;
+    }
+    if (row < 0) {
+        if (lead) ctl->status = LPX_UNBOUNDED;
+        return;
+    }
+    if (probe_only) return;
+
+    const int l = row;
+    const double piv = col[l], fz = col[m];
+    const int j = blockIdx.x * TH + tid;
+    ArgMin a;
+    a.v = -LPX_EPS;
+    a.i = INT_MAX;
+    if (j < P.ld) {
+        double* Tl = P.T + (size_t)l * P.ld;
+        const double pj = __ddiv_rn(Tl[j], piv);
+        if (j < P.width - 1) {
+            const double zn = __dsub_rn(P.T[(size_t)m * P.ld + j], __dmul_rn(fz, pj));
+            if (zn < a.v) {
+                a.v = zn;
+                a.i = j;
+            }
+        }
+        P.prow[j] = pj;
+        Tl[j] = pj;
+    }
+    a = warp_argmin(a);
+    const int lane = tid & 31, warp = tid >> 5;
+    if (lane == 0) red[warp] = a;
+    __syncthreads();
+    if (warp == 0) {
+        ArgMin b2;
+        b2.v = -LPX_EPS;
+        b2.i = INT_MAX;
+        if (lane < TH / 32) b2 = red[lane];
+        b2 = warp_argmin(b2);
+        if (lane == 0) P.partial[blockIdx.x] = b2;
+    }
+    if (lead) {
+        P.basis[l] = e;
+        if (k < P.pivlog_cap) {
+            P.pivlog[2 * k] = e;
+            P.pivlog[2 * k + 1] = l;
+        }
+        ctl->leave = l;
+        ctl->k = k;
+        ctl->active = 1;
+    }
+}
+
 // The HBM pass.  grid = (column strips of 512, row chunks); each thread owns two adjacent
 // columns for its CTA's rows, so p[j] stays in registers and f[i] is a broadcast load.
 // The sweep direction alternates with the pivot parity: the rows written last by pivot k are
 // read first by pivot k+1, while they are still in the 126 MB L2.
 template <int UNROLL>
 __global__ void __launch_bounds__(256, 4) stream_update_kernel(StreamParams P) {
-    const StreamCtl* ctl = P.ctl;
+    StreamCtl* ctl = P.ctl;
     if (ctl->active == 0) return;
-    const int l = ctl->leave, k = ctl->k, cap = ctl->capture;
+    const int l = ctl->leave, k = ctl->k;
+    int cap;
+    if (P.npartial > 0) {
+        // combine the prep CTAs' look-ahead argmins: the next entering column (ChooseEntering)
+        __shared__ int s_cap;
+        if (threadIdx.x < 32) {
+            ArgMin a;
+            a.v = -LPX_EPS;
+            a.i = INT_MAX;
+            for (int i = threadIdx.x; i < P.npartial; i += 32) a = argmin_pick(a, P.partial[i]);
+            a = warp_argmin(a);
+            if (threadIdx.x == 0) s_cap = a.i == INT_MAX ? -1 : a.i;
+        }
+        __syncthreads();
+        cap = s_cap;
+        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+            // pivot-row entries of the two captured vectors, then advance the pivot counter
+            double* outl = P.colbuf + (size_t)((k + 1) & 1) * P.colstride;
+            if (cap >= 0) outl[l] = P.prow[cap];
+            P.rhsbuf[l] = P.prow[P.width - 1];
+            ctl->capture = cap;
+            ctl->enter = cap;
+            ctl->pivots = k + 1;
+        }
+    } else {
+        cap = ctl->capture;
+    }
     const int j0 = (blockIdx.x * 256 + threadIdx.x) * 2;
     if (j0 >= P.ld) return;
     const double* __restrict__ f = P.colbuf + (size_t)(k & 1) * P.colstride;
@@ -319,7 +455,7 @@ struct lpx_session {
     lpx_options opt{};
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    void* buffers[12] = {};
+    void* buffers[16] = {};
     int nbuf = 0;
     dim3 grid_update;
     int device = 0;
@@ -347,7 +483,10 @@ static void sess_free(lpx_session* s) {
 }
 
 static int launch_pair(lpx_session* s, int probe_only) {
-    stream_select_kernel<<<1, 1024, 0, s->stream>>>(s->P, probe_only);
+    if (s->P.npartial > 0)
+        stream_prep_kernel<<<s->P.npartial, LPX_PREP_THREADS, (size_t)s->P.m * 8, s->stream>>>(s->P, probe_only);
+    else
+        stream_select_kernel<<<1, 1024, 0, s->stream>>>(s->P, probe_only);
     count_launch();
     if (!probe_only) {
         stream_update_kernel<4><<<s->grid_update, 256, 0, s->stream>>>(s->P);
@@ -408,9 +547,19 @@ static lpx_session* session_create(int m, int n, int sense, const double* dA, co
     P.basis = (int*)sess_alloc(s, (size_t)mm * 4);
     P.pivlog = (int*)sess_alloc(s, (size_t)P.pivlog_cap * 8);
     P.ctl = (StreamCtl*)sess_alloc(s, sizeof(StreamCtl));
+    // multi-CTA prep when the ratio vector fits in one CTA's shared memory (m <= ~25 K rows)
+    const int prep_ctas = (P.ld + LPX_PREP_THREADS - 1) / LPX_PREP_THREADS;
+    const size_t prep_smem = (size_t)mm * 8;
+    P.npartial = (prep_smem + 2048 <= (size_t)max_smem_optin() && s->opt.reserved[2] == 0) ? prep_ctas : 0;
+    P.partial = (ArgMin*)sess_alloc(s, (size_t)prep_ctas * sizeof(ArgMin));
+    if (P.npartial > 0 && prep_smem > 40 * 1024 &&
+        cudaFuncSetAttribute(stream_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem) !=
+            cudaSuccess)
+        P.npartial = 0;
     int* drsrc = (int*)sess_alloc(s, (size_t)mm * 4);
     int* drsgn = (int*)sess_alloc(s, (size_t)mm * 4);
-    if (!P.T || !P.colbuf || !P.rhsbuf || !P.prow || !P.ratio || !P.basis || !P.pivlog || !P.ctl || !drsrc || !drsgn) {
+    if (!P.T || !P.colbuf || !P.rhsbuf || !P.prow || !P.ratio || !P.basis || !P.pivlog || !P.ctl || !P.partial || !drsrc ||
+        !drsgn) {
         sess_free(s);
         return nullptr;
     }

@@ -201,3 +201,45 @@ def test_wide_and_tall_shapes(lpx, orc):
         for kernel in (F.KERNEL_AUTO, F.KERNEL_CTA_GLOBAL, F.KERNEL_STREAM):
             got = lpx.primal_solve(A, b, c, kernel=kernel)
             compare_primal(got, want, f"{m}x{n} kernel={kernel}")
+
+
+@pytest.mark.parametrize("reg_variant", [1, 2])
+def test_register_resident_kernel(lpx, orc, reg_variant):
+    """LPX_KERNEL_CTA_REG on every shape class it serves, against the oracle, bit for bit."""
+    rng = np.random.default_rng(17)
+    shapes = [(64, 128), (64, 100), (60, 120), (10, 20), (1, 1), (33, 7), (64, 1), (5, 187)]
+    for (m, n) in shapes:
+        for kind, sense in (("integer", 0), ("decimal", 0), ("integer", 1)):
+            A, b, c = workloads.batch_c2(count=24, m=m, n=n, seed=3 + m + n, kind=kind)
+            if sense == 1:
+                c = -c
+            want = orc.primal_batch(A, b, c if sense == 0 else -c, threads=8, want_tableau=True)
+            got = lpx.primal_solve_batched(A, b, c, sense=sense, kernel=F.KERNEL_CTA_REG, reg_variant=reg_variant)
+            what = f"{m}x{n} {kind} sense={sense}"
+            assert np.array_equal(got["status"], want["status"]), what
+            assert np.array_equal(got["n_pivots"], want["n_pivots"]), what
+            assert np.array_equal(got["basis"], want["basis"]), what
+            assert_bits_equal(got["tableau"], want["tableau"], what + " tableau")
+            assert_bits_equal(got["x"], want["x"], what + " x")
+            assert_bits_equal(got["z"], want["z"], what + " z")
+    # unbounded, negative RHS, iteration limit and degenerate instances in one batch
+    A = rng.integers(-3, 8, size=(60, 12, 15)).astype(float)
+    b = rng.integers(-1, 30, size=(60, 12)).astype(float)
+    c = rng.integers(-3, 9, size=(60, 15)).astype(float)
+    A[50:, :, 0] = -1.0  # column 0 enters first (largest cost) and has no positive entry: unbounded
+    b[50:] = np.abs(b[50:])
+    c[50:, 0] = 9.0
+    got = lpx.primal_solve_batched(A, b, c, max_iterations=9, kernel=F.KERNEL_CTA_REG, reg_variant=reg_variant)
+    seen = set()
+    for k in range(60):
+        want = orc.primal_solve(A[k], b[k], c[k], None, 0, max_iterations=9)
+        assert got["status"][k] == want["status"], k
+        seen.add(want["status"])
+        if want["status"] >= 0:
+            assert got["n_pivots"][k] == want["n_pivots"]
+            assert_bits_equal(got["tableau"][k], want["tableau"], f"tableau {k}")
+            assert_bits_equal(got["x"][k], want["x"], f"x {k}")
+    assert {0, 1, -2, -3} <= seen
+    # shapes it does not serve are refused, not silently rerouted
+    with pytest.raises(F.LpxError):
+        lpx.primal_solve_batched(np.ones((2, 70, 10)), np.ones((2, 70)), np.ones((2, 10)), kernel=F.KERNEL_CTA_REG)

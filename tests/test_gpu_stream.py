@@ -20,10 +20,11 @@ def build_tableau(A, b, c):
     return T
 
 
-def test_medium_full_solve(lpx, orc):
+@pytest.mark.parametrize("single_cta_select", [0, 1])
+def test_medium_full_solve(lpx, orc, single_cta_select):
     A, b, c = workloads.lp_integer(256, 512, 7)
     want = orc.primal_solve(A, b, c)
-    s = lpx.Session(A, b, c)
+    s = lpx.Session(A, b, c, single_cta_select=single_cta_select)
     st, tot = F.RUNNING, 0
     while st == F.RUNNING:
         st, tot = s.step(64)

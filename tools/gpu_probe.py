@@ -1,0 +1,76 @@
+"""Kernel-variant timing probe (development aid, run under gpurun).  CUDA events on torch's
+current stream for the batched kernels, on the session stream for the streaming kernels."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from linear_programming_solver_lpr381_b200 import _ffi as F  # noqa: E402
+from linear_programming_solver_lpr381_b200 import api, workloads  # noqa: E402
+
+F.check(F.lib().lpx_init(0))
+dev = torch.device("cuda:0")
+stream = torch.cuda.current_stream()
+
+
+def time_batched(kernel, threads=0, reg_variant=0, count=4096, m=64, n=128, reps=5):
+    A, b, c = workloads.batch_c2(count=count, m=m, n=n, seed=1)
+    dA, db, dc = (torch.from_numpy(v).to(dev) for v in (A, b, c))
+    st = torch.zeros(count, dtype=torch.int32, device=dev)
+    npv = torch.zeros(count, dtype=torch.int32, device=dev)
+    basis = torch.zeros((count, m), dtype=torch.int32, device=dev)
+    x = torch.zeros((count, n), dtype=torch.float64, device=dev)
+    z = torch.zeros(count, dtype=torch.float64, device=dev)
+    T = torch.zeros((count, m + 1, n + m + 1), dtype=torch.float64, device=dev)
+    tot = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def launch():
+        api.primal_solve_batched_dev(count, m, n, 0, dA.data_ptr(), None, db.data_ptr(), dc.data_ptr(), st.data_ptr(),
+                                     npv.data_ptr(), basis.data_ptr(), x.data_ptr(), z.data_ptr(), T.data_ptr(),
+                                     tot.data_ptr(), stream.cuda_stream, kernel=kernel, threads=threads,
+                                     reg_variant=reg_variant)
+    for _ in range(3):
+        launch()
+    torch.cuda.synchronize()
+    tot.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        launch()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    piv = int(tot.item()) / reps
+    return dict(kernel=kernel, threads=threads, reg_variant=reg_variant, ms=ms, pivots=piv, mpivots_s=piv / ms / 1e3)
+
+
+def time_large(single_cta_select, per=40, reps=3):
+    A, b, c = workloads.large_c3()
+    s = api.Session(A, b, c, max_iterations=1 << 30, single_cta_select=single_cta_select)
+    ss = torch.cuda.ExternalStream(s.stream)
+    s.step_async(per)
+    s.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ss)
+    s.step_async(per * reps)
+    e1.record(ss)
+    s.sync()
+    us = e0.elapsed_time(e1) * 1e3 / (per * reps)
+    bytes_pp = 2 * 8 * s.rows * s.cols
+    s.close()
+    return dict(single_cta_select=single_cta_select, us_per_pivot=us, gbs=bytes_pp / us / 1e3, frac=bytes_pp / us / 1e3 / 6555.2)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("all", "batched"):
+        for kw in (dict(kernel=F.KERNEL_CTA_SMEM, threads=256), dict(kernel=F.KERNEL_CTA_SMEM, threads=512),
+                   dict(kernel=F.KERNEL_CTA_REG, reg_variant=1), dict(kernel=F.KERNEL_CTA_REG, reg_variant=2)):
+            print(json.dumps(time_batched(**kw)), flush=True)
+    if what in ("all", "large"):
+        for sc in (1, 0):
+            print(json.dumps(time_large(sc)), flush=True)
