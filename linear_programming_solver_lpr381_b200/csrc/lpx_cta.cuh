@@ -128,6 +128,20 @@ __device__ __forceinline__ void cta_pivot(double* T, int ld, int rows, int width
     __syncthreads();
 }
 
+// Ratios of the min-ratio test, one division per thread (a double division is a ~40-instruction
+// dependent chain: never let one warp do them one after another).  NaN marks "not eligible".
+// Parked in prow, which is free until the pivot itself.
+template <int THREADS>
+__device__ __forceinline__ void cta_stage_ratios(const double* T, int ld, int m, int e, int rhs, double* prow) {
+    for (int i = threadIdx.x; i < m; i += THREADS) {
+        const double a = T[(size_t)i * ld + e];
+        double r = __longlong_as_double(0x7ff8000000000000LL);
+        if (a > LPX_EPS) r = __ddiv_rn(T[(size_t)i * ld + rhs], a);
+        prow[i] = r;
+    }
+    __syncthreads();
+}
+
 template <int THREADS>
 __device__ __forceinline__ void cta_copy_out(double* dst, const double* T, int ld, int rows, int width) {
     if (ld == width) {
@@ -275,14 +289,11 @@ __global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) 
             for (int guard = 0; guard < 100; guard++) {
                 const int e = block_argmin_below<THREADS>(zrow, width - 1, -LPX_EPS, red);
                 if (e < 0) break;
+                cta_stage_ratios<THREADS>(T, ld, m, e, rhs, prow);
                 if (warp == 0) {
                     const int l = warp_margin_scan(m, LPX_MARGIN_DUAL, [&](int i, double& r) {
-                        const double a = T[(size_t)i * ld + e];
-                        if (a > LPX_EPS) {
-                            r = __ddiv_rn(T[(size_t)i * ld + rhs], a);
-                            return true;
-                        }
-                        return false;
+                        r = prow[i];
+                        return r == r;
                     });
                     if (lane == 0) ctl[2] = l;
                 }
@@ -322,14 +333,11 @@ __global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) 
                     break;
                 }
                 // ChooseLeaving: sequential margin scan over rows with T[i,e] > 1e-9
+                cta_stage_ratios<THREADS>(T, ld, m, e, rhs, prow);
                 if (warp == 0) {
                     const int lv = warp_margin_scan(m, LPX_MARGIN_PRIMAL, [&](int i, double& r) {
-                        const double a = T[(size_t)i * ld + e];
-                        if (a > LPX_EPS) {
-                            r = __ddiv_rn(T[(size_t)i * ld + rhs], a);
-                            return true;
-                        }
-                        return false;
+                        r = prow[i];
+                        return r == r;
                     });
                     if (lane == 0) ctl[2] = lv;
                 }
@@ -347,15 +355,20 @@ __global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) 
                     break;
                 }
                 // entering column: min z_j / (-a) over a < -1e-9, margin 1e-12 (DualSimplex.cs:76-91)
-                if (warp == 0) {
+                {
                     const double* lrow = T + (size_t)l * ld;
-                    const int ev = warp_margin_scan(width - 1, LPX_MARGIN_DUAL, [&](int j, double& r) {
+                    for (int j = tid; j < width - 1; j += THREADS) {
                         const double a = lrow[j];
-                        if (a < -LPX_EPS) {
-                            r = __ddiv_rn(zrow[j], dneg(a));
-                            return true;
-                        }
-                        return false;
+                        double r = __longlong_as_double(0x7ff8000000000000LL);
+                        if (a < -LPX_EPS) r = __ddiv_rn(zrow[j], dneg(a));
+                        prow[j] = r;
+                    }
+                    __syncthreads();
+                }
+                if (warp == 0) {
+                    const int ev = warp_margin_scan(width - 1, LPX_MARGIN_DUAL, [&](int j, double& r) {
+                        r = prow[j];
+                        return r == r;
                     });
                     if (lane == 0) ctl[2] = ev;
                 }

@@ -37,7 +37,9 @@ __global__ void __launch_bounds__(NW * 32, OCC) reg_simplex_kernel(const RegBatc
     constexpr int COLS = 32 * C;   // padded non-RHS columns (>= n + m)
     __shared__ double s_f[ROWS];   // entering column = update factors
     __shared__ double s_rhs[ROWS];
-    __shared__ double s_p[COLS + 1];  // normalised pivot row, [COLS] = its RHS
+    __shared__ double s_p[COLS + 1];    // normalised pivot row, [COLS] = its RHS
+    __shared__ double s_raw[COLS + 1];  // the leaving row before normalisation
+    __shared__ double s_ratio[ROWS];
     __shared__ int s_basis[ROWS];
     __shared__ int s_ctl[4];
 
@@ -81,90 +83,123 @@ __global__ void __launch_bounds__(NW * 32, OCC) reg_simplex_kernel(const RegBatc
     int n_piv = 0;
 
     if (status == LPX_RUNNING) {
+        // entering column of the first pivot (ChooseEntering on the initial z-row)
+        auto choose_entering = [&]() {
+            ArgMin a;
+            a.v = -LPX_EPS;
+            a.i = INT_MAX;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (r == rz) {
+#pragma unroll
+                    for (int c = 0; c < C; c++) {
+                        const double zv = t[r][c];
+                        if (zv < a.v) {
+                            a.v = zv;
+                            a.i = lane + 32 * c;
+                        }
+                    }
+                }
+            }
+            a = warp_argmin(a);
+            if (lane == 0) s_ctl[0] = a.i == INT_MAX ? -1 : a.i;
+        };
+        if (w == wz) choose_entering();
+
+        // Serial latency, not throughput, bounds a pivot: a double division is a ~40-instruction
+        // dependent chain, so every division below is done by a DIFFERENT thread (ratios: one per
+        // row, lanes 0..R-1 of each warp; pivot row: one per column), never several by one warp.
         int iter = 1;
         while (true) {
+            __syncthreads();  // (A) s_ctl[0] holds the entering column; all updates are done
             if (iter > B.max_iter) {
                 status = LPX_S_ITER_LIMIT;
                 break;
             }
-            // ---- ChooseEntering: the warp that owns the z-row ---------------------------------
-            if (w == wz) {
-                ArgMin a;
-                a.v = -LPX_EPS;
-                a.i = INT_MAX;
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    if (r == rz) {
-#pragma unroll
-                        for (int c = 0; c < C; c++) {
-                            const double zv = t[r][c];
-                            if (zv < a.v) {
-                                a.v = zv;
-                                a.i = lane + 32 * c;
-                            }
-                        }
-                    }
-                }
-                a = warp_argmin(a);
-                if (lane == 0) s_ctl[0] = a.i == INT_MAX ? -1 : a.i;
-            }
-            __syncthreads();
             const int e = s_ctl[0];
             if (e < 0) {
                 status = LPX_OPTIMAL;
                 break;
             }
-            // ---- stage the entering column and the RHS ----------------------------------------
-            if (lane == (e & 31)) {
-                const int ce = e >> 5;
+            // ---- entering column -> factors and ratios, inside each warp by shuffle -------------
+            const int ce = e >> 5, le = e & 31;
+            double my_a = 0.0;
 #pragma unroll
-                for (int c = 0; c < C; c++) {
-                    if (c == ce) {
+            for (int r = 0; r < R; r++) {
+                double v = 0.0;
 #pragma unroll
-                        for (int r = 0; r < R; r++) s_f[w * R + r] = t[r][c];
-                    }
-                }
+                for (int c = 0; c < C; c++)
+                    if (c == ce) v = t[r][c];
+                v = __shfl_sync(0xffffffffu, v, le);
+                if (lane == r) my_a = v;
             }
-            if (lane < R) s_rhs[w * R + lane] = rhsv;
-            __syncthreads();
-            // ---- ChooseLeaving: every warp repeats the exact sequential scan ------------------
+            if (lane < R) {
+                const int i = w * R + lane;
+                double ratio = __longlong_as_double(0x7ff8000000000000LL);  // NaN = not eligible
+                if (i < m && my_a > LPX_EPS) ratio = __ddiv_rn(rhsv, my_a);
+                s_f[i] = my_a;
+                s_ratio[i] = ratio;
+            }
+            __syncthreads();  // (B)
+            // ---- ChooseLeaving: every warp repeats the exact sequential scan on the ratios -------
             const int lr = warp_margin_scan(m, LPX_MARGIN_PRIMAL, [&](int i, double& ratio) {
-                const double a = s_f[i];
-                if (a > LPX_EPS) {
-                    ratio = __ddiv_rn(s_rhs[i], a);
-                    return true;
-                }
-                return false;
+                ratio = s_ratio[i];
+                return ratio == ratio;
             });
             if (lr < 0) {
                 status = LPX_UNBOUNDED;
                 break;
             }
             const double piv = s_f[lr];
-            // ---- the owner of the leaving row normalises it (true division) --------------------
+            // ---- the owner of the leaving row publishes it; one division per thread -------------
             const int wl = lr / R, rl = lr - wl * R;
             if (w == wl) {
 #pragma unroll
                 for (int r = 0; r < R; r++) {
                     if (r == rl) {
 #pragma unroll
-                        for (int c = 0; c < C; c++) s_p[lane + 32 * c] = __ddiv_rn(t[r][c], piv);
+                        for (int c = 0; c < C; c++) s_raw[lane + 32 * c] = t[r][c];
                     }
                 }
-                if (lane == rl) s_p[COLS] = __ddiv_rn(rhsv, piv);
+                if (lane == rl) s_raw[COLS] = rhsv;
             }
-            __syncthreads();
-            // ---- rank-1 update, registers only ------------------------------------------------
+            __syncthreads();  // (D)
+            for (int j = tid; j <= COLS; j += NW * 32) s_p[j] = __ddiv_rn(s_raw[j], piv);
+            __syncthreads();  // (E)
+            // ---- rank-1 update in registers.  The warp that owns the z-row updates that row
+            // first and picks the NEXT entering column while the other warps are still updating.
             double f[R];
 #pragma unroll
             for (int r = 0; r < R; r++) f[r] = s_f[w * R + r];
+            if (w == wz) {
 #pragma unroll
-            for (int c = 0; c < C; c++) {
-                const double pc = s_p[lane + 32 * c];
+                for (int c = 0; c < C; c++) {
+                    const double pc = s_p[lane + 32 * c];
 #pragma unroll
-                for (int r = 0; r < R; r++) {
-                    const double upd = __dsub_rn(t[r][c], __dmul_rn(f[r], pc));
-                    t[r][c] = (w * R + r == lr) ? pc : upd;
+                    for (int r = 0; r < R; r++)
+                        if (r == rz) t[r][c] = __dsub_rn(t[r][c], __dmul_rn(f[r], pc));
+                }
+                choose_entering();
+#pragma unroll
+                for (int c = 0; c < C; c++) {
+                    const double pc = s_p[lane + 32 * c];
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        if (r != rz) {
+                            const double upd = __dsub_rn(t[r][c], __dmul_rn(f[r], pc));
+                            t[r][c] = (w * R + r == lr) ? pc : upd;
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < C; c++) {
+                    const double pc = s_p[lane + 32 * c];
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        const double upd = __dsub_rn(t[r][c], __dmul_rn(f[r], pc));
+                        t[r][c] = (w * R + r == lr) ? pc : upd;
+                    }
                 }
             }
             if (lane < R) {

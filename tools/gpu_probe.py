@@ -74,3 +74,7 @@ if __name__ == "__main__":
     if what in ("all", "large"):
         for sc in (1, 0):
             print(json.dumps(time_large(sc)), flush=True)
+    if what == "prof_reg":
+        print(json.dumps(time_batched(kernel=F.KERNEL_CTA_REG, reg_variant=1, count=592, reps=1)), flush=True)
+    if what == "prof_smem":
+        print(json.dumps(time_batched(kernel=F.KERNEL_CTA_SMEM, threads=256, count=592, reps=1)), flush=True)
