@@ -148,7 +148,7 @@ def check(rc):
         raise LpxError(rc, last_error())
 
 
-def make_options(max_iterations=10000, kernel=KERNEL_AUTO, threads=0, spec_nodes=0, spec_depth=0, single_cta_select=0, reg_variant=0):
+def make_options(max_iterations=10000, kernel=KERNEL_AUTO, threads=0, spec_nodes=0, spec_depth=0, single_cta_select=0, reg_variant=0, kblock=0):
     o = Options()
     lib().lpx_default_options(C.byref(o))
     o.max_iterations = max_iterations
@@ -156,8 +156,9 @@ def make_options(max_iterations=10000, kernel=KERNEL_AUTO, threads=0, spec_nodes
     o.threads = threads
     o.reserved[0] = spec_nodes
     o.reserved[1] = spec_depth
-    o.reserved[2] = single_cta_select  # streaming kernels: force the single-CTA select protocol
+    o.reserved[2] = single_cta_select  # streaming kernels: 0 blocked look-ahead, 1 / 2 per-pivot protocols
     o.reserved[3] = reg_variant  # register kernel: 2 = the 2-CTAs-per-SM build
+    o.reserved[4] = kblock  # streaming kernels: pivots per HBM pass (0 = default 8, max 16)
     return o
 
 

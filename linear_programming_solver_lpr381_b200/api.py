@@ -115,8 +115,8 @@ class Session:
     """Large single LP whose tableau lives in HBM (lpx_session_*)."""
 
     def __init__(self, A, b, c, rel=None, sense=0, max_iterations=10000, device_ptrs=False, m=None, n=None,
-                 single_cta_select=0):
-        opt = F.make_options(max_iterations, single_cta_select=single_cta_select)
+                 single_cta_select=0, kblock=0):
+        opt = F.make_options(max_iterations, single_cta_select=single_cta_select, kblock=kblock)
         if device_ptrs:
             self.m, self.n = m, n
             relp = None if rel is None else np.ascontiguousarray(rel, dtype=np.int32)

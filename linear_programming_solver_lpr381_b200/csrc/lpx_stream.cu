@@ -30,7 +30,7 @@ struct StreamCtl {
     int active;   // 1: the update kernel has a pivot to apply
     int capture;  // entering column of the pivot after this one (-1: none)
     int k;        // index of the pivot being applied
-    int pad;
+    int block_cnt;  // blocked protocol: pivots decided by the last look-ahead, applied by the next pass
 };
 
 struct StreamParams {
@@ -48,9 +48,14 @@ struct StreamParams {
     int max_iter;
     ArgMin* partial;  // per prep-CTA argmin of the look-ahead z-row (multi-CTA protocol)
     int npartial;     // 0: single-CTA select protocol (very tall tableaux)
+    // blocked look-ahead protocol (lpx_stream_block.cuh)
+    double* Fbuf;  // kblock x colstride factor columns
+    double* Pbuf;  // kblock x ld normalised pivot rows
+    int* Lbuf;     // kblock leaving rows
+    int kblock;    // 0: per-pivot protocol
 };
 
-#define LPX_PREP_THREADS 256
+#define LPX_PREP_THREADS 1024
 
 __device__ __forceinline__ double dneg_s(double v) {
     return __longlong_as_double(__double_as_longlong(v) ^ (long long)0x8000000000000000ULL);
@@ -96,6 +101,7 @@ __global__ void __launch_bounds__(1024) stream_validate_kernel(StreamCtl* ctl, c
         ctl->active = 0;
         ctl->capture = -1;
         ctl->k = 0;
+        ctl->block_cnt = 0;
     }
 }
 
@@ -289,11 +295,23 @@ __global__ void __launch_bounds__(LPX_PREP_THREADS) stream_prep_kernel(StreamPar
     }
     const int m = P.m;
     const double* col = P.colbuf + (size_t)(k & 1) * P.colstride;
-    for (int i = tid; i < m; i += TH) {
-        const double a = col[i];
-        double r = __longlong_as_double(0x7ff8000000000000LL);  // NaN: never eligible
-        if (a > LPX_EPS) r = __ddiv_rn(P.rhsbuf[i], a);
-        s_ratio[i] = r;
+    // all loads of a batch are issued before the first division: dependent global loads in a
+    // loop (load a, branch, load rhs, divide) cost ~1.4k cycles per row and made this phase 10 us
+    for (int base = 0; base < m; base += 4 * TH) {
+        double a[4], bb[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = base + u * TH + tid;
+            a[u] = i < m ? col[i] : 0.0;
+            bb[u] = i < m ? P.rhsbuf[i] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = base + u * TH + tid;
+            double r = __longlong_as_double(0x7ff8000000000000LL);  // NaN: never eligible
+            if (a[u] > LPX_EPS) r = __ddiv_rn(bb[u], a[u]);
+            if (i < m) s_ratio[i] = r;
+        }
     }
     __syncthreads();
     double best = __longlong_as_double(0x7ff0000000000000LL);
@@ -445,6 +463,9 @@ __global__ void __launch_bounds__(256, 4) stream_update_kernel(StreamParams P) {
 
 }  // namespace lpx
 
+#include "lpx_stream_block.cuh"
+
+
 // ---- session object -----------------------------------------------------------------------------
 
 using namespace lpx;
@@ -455,9 +476,10 @@ struct lpx_session {
     lpx_options opt{};
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    void* buffers[16] = {};
+    void* buffers[24] = {};
     int nbuf = 0;
     dim3 grid_update;
+    dim3 grid_block;
     int device = 0;
 };
 
@@ -490,6 +512,21 @@ static int launch_pair(lpx_session* s, int probe_only) {
     count_launch();
     if (!probe_only) {
         stream_update_kernel<4><<<s->grid_update, 256, 0, s->stream>>>(s->P);
+        count_launch();
+    }
+    LPX_CUDA(cudaGetLastError());
+    return LPX_OK;
+}
+
+static size_t lookahead_smem(const StreamParams& P) { return ((size_t)P.ld + 3 * (size_t)P.colstride) * 8; }
+
+// One block of the look-ahead protocol: decide up to `budget` pivots, then one HBM pass.
+static int launch_block(lpx_session* s, int budget) {
+    stream_lookahead_kernel<<<1, 1024, lookahead_smem(s->P), s->stream>>>(s->P, budget);
+    count_launch();
+    if (budget > 0) {
+        if (s->P.kblock <= 8) stream_update_block_kernel<8, 4><<<s->grid_block, 256, 0, s->stream>>>(s->P);
+        else stream_update_block_kernel<16, 2><<<s->grid_block, 256, 0, s->stream>>>(s->P);
         count_launch();
     }
     LPX_CUDA(cudaGetLastError());
@@ -550,16 +587,31 @@ static lpx_session* session_create(int m, int n, int sense, const double* dA, co
     // multi-CTA prep when the ratio vector fits in one CTA's shared memory (m <= ~25 K rows)
     const int prep_ctas = (P.ld + LPX_PREP_THREADS - 1) / LPX_PREP_THREADS;
     const size_t prep_smem = (size_t)mm * 8;
-    P.npartial = (prep_smem + 2048 <= (size_t)max_smem_optin() && s->opt.reserved[2] == 0) ? prep_ctas : 0;
+    P.npartial = (prep_smem + 2048 <= (size_t)max_smem_optin()) ? prep_ctas : 0;
     P.partial = (ArgMin*)sess_alloc(s, (size_t)prep_ctas * sizeof(ArgMin));
+    // blocked look-ahead protocol: needs z-row + three row-length vectors in one CTA's shared memory.
+    // reserved[2]: 0 auto, 1 single-CTA select per pivot, 2 multi-CTA prep per pivot.  reserved[4]: block size.
+    P.kblock = 0;
+    if (s->opt.reserved[2] == 0 && lookahead_smem(P) + 4096 <= (size_t)max_smem_optin()) {
+        P.kblock = s->opt.reserved[4] > 0 ? std::min(s->opt.reserved[4], LPX_BLOCK_KMAX) : 8;
+        if (cudaFuncSetAttribute(stream_lookahead_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)lookahead_smem(P)) != cudaSuccess) {
+            cudaGetLastError();
+            P.kblock = 0;
+        }
+    }
+    if (s->opt.reserved[2] == 1) P.npartial = 0;
+    P.Fbuf = (double*)sess_alloc(s, (size_t)LPX_BLOCK_KMAX * P.colstride * 8);
+    P.Pbuf = (double*)sess_alloc(s, (size_t)LPX_BLOCK_KMAX * P.ld * 8);
+    P.Lbuf = (int*)sess_alloc(s, (size_t)LPX_BLOCK_KMAX * 4);
     if (P.npartial > 0 && prep_smem > 40 * 1024 &&
         cudaFuncSetAttribute(stream_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem) !=
             cudaSuccess)
         P.npartial = 0;
     int* drsrc = (int*)sess_alloc(s, (size_t)mm * 4);
     int* drsgn = (int*)sess_alloc(s, (size_t)mm * 4);
-    if (!P.T || !P.colbuf || !P.rhsbuf || !P.prow || !P.ratio || !P.basis || !P.pivlog || !P.ctl || !P.partial || !drsrc ||
-        !drsgn) {
+    if (!P.T || !P.colbuf || !P.rhsbuf || !P.prow || !P.ratio || !P.basis || !P.pivlog || !P.ctl || !P.partial || !P.Fbuf ||
+        !P.Pbuf || !P.Lbuf || !drsrc || !drsgn) {
         sess_free(s);
         return nullptr;
     }
@@ -591,6 +643,13 @@ static lpx_session* session_create(int m, int n, int sense, const double* dA, co
     int chunks = (sm_count() * occ) / strips;
     chunks = std::max(1, std::min(chunks, P.rows));
     s->grid_update = dim3(strips, chunks, 1);
+    occ = 0;
+    if (P.kblock <= 8) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stream_update_block_kernel<8, 4>, 256, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stream_update_block_kernel<16, 2>, 256, 0);
+    if (occ < 1) occ = 1;
+    chunks = (sm_count() * occ) / strips;
+    chunks = std::max(1, std::min(chunks, P.rows));
+    s->grid_block = dim3(strips, chunks, 1);
     return s;
 }
 
@@ -660,10 +719,50 @@ int lpx_session_step_async(lpx_session* s, int max_pivots) {
         set_error("lpx_session_step_async: bad arguments");
         return LPX_E_BAD_ARGS;
     }
+    if (s->P.kblock > 0) {
+        for (int left = max_pivots; left > 0; left -= s->P.kblock) {
+            int rc = launch_block(s, std::min(left, s->P.kblock));
+            if (rc != LPX_OK) return rc;
+        }
+        return LPX_OK;
+    }
     for (int k = 0; k < max_pivots; k++) {
         int rc = launch_pair(s, 0);
         if (rc != LPX_OK) return rc;
     }
+    return LPX_OK;
+}
+
+// Development aid: n pivots with CUDA events around each of the two kernels.  us[0] = mean
+// prep/select time, us[1] = mean update time, us[2] = mean time per pivot including the gaps.
+int lpx_session_profile(lpx_session* s, int n, double* us) {
+    if (!s || n < 1 || !us) return LPX_E_BAD_ARGS;
+    std::vector<cudaEvent_t> ev((size_t)3 * n);
+    for (auto& e : ev) LPX_CUDA(cudaEventCreate(&e));
+    for (int k = 0; k < n; k++) {
+        LPX_CUDA(cudaEventRecord(ev[3 * k], s->stream));
+        if (s->P.npartial > 0)
+            stream_prep_kernel<<<s->P.npartial, LPX_PREP_THREADS, (size_t)s->P.m * 8, s->stream>>>(s->P, 0);
+        else
+            stream_select_kernel<<<1, 1024, 0, s->stream>>>(s->P, 0);
+        LPX_CUDA(cudaEventRecord(ev[3 * k + 1], s->stream));
+        stream_update_kernel<4><<<s->grid_update, 256, 0, s->stream>>>(s->P);
+        LPX_CUDA(cudaEventRecord(ev[3 * k + 2], s->stream));
+    }
+    LPX_CUDA(cudaStreamSynchronize(s->stream));
+    double a = 0, b = 0;
+    float ms = 0;
+    for (int k = 0; k < n; k++) {
+        cudaEventElapsedTime(&ms, ev[3 * k], ev[3 * k + 1]);
+        a += ms;
+        cudaEventElapsedTime(&ms, ev[3 * k + 1], ev[3 * k + 2]);
+        b += ms;
+    }
+    cudaEventElapsedTime(&ms, ev[0], ev[3 * (n - 1) + 2]);
+    us[0] = a * 1e3 / n;
+    us[1] = b * 1e3 / n;
+    us[2] = ms * 1e3 / n;
+    for (auto& e : ev) cudaEventDestroy(e);
     return LPX_OK;
 }
 
@@ -673,7 +772,7 @@ int lpx_session_sync(lpx_session* s, int* status, int* pivots_total) {
         return LPX_E_BAD_ARGS;
     }
     // probe: resolves OPTIMAL / UNBOUNDED / ITER_LIMIT for the tableau as it stands, no pivot
-    int rc = launch_pair(s, 1);
+    int rc = s->P.kblock > 0 ? launch_block(s, 0) : launch_pair(s, 1);
     if (rc != LPX_OK) return rc;
     StreamCtl h;
     LPX_CUDA(cudaMemcpyAsync(&h, s->P.ctl, sizeof h, cudaMemcpyDeviceToHost, s->stream));

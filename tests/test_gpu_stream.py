@@ -20,11 +20,14 @@ def build_tableau(A, b, c):
     return T
 
 
-@pytest.mark.parametrize("single_cta_select", [0, 1])
-def test_medium_full_solve(lpx, orc, single_cta_select):
+PROTOCOLS = [(0, 0), (0, 1), (0, 3), (0, 16), (1, 0), (2, 0)]  # (protocol, pivots per HBM pass)
+
+
+@pytest.mark.parametrize("protocol,kblock", PROTOCOLS)
+def test_medium_full_solve(lpx, orc, protocol, kblock):
     A, b, c = workloads.lp_integer(256, 512, 7)
     want = orc.primal_solve(A, b, c)
-    s = lpx.Session(A, b, c, single_cta_select=single_cta_select)
+    s = lpx.Session(A, b, c, single_cta_select=protocol, kblock=kblock)
     st, tot = F.RUNNING, 0
     while st == F.RUNNING:
         st, tot = s.step(64)
@@ -38,10 +41,34 @@ def test_medium_full_solve(lpx, orc, single_cta_select):
     s.close()
 
 
+@pytest.mark.parametrize("protocol,kblock", PROTOCOLS)
+def test_degenerate_and_repeated_rows_inside_a_block(lpx, orc, protocol, kblock):
+    """Small dense LPs where the same row leaves several times within one look-ahead block and
+    ties are frequent; plus EQ rows (negative RHS rows) and a Min objective."""
+    rng = np.random.default_rng(23)
+    for t in range(8):
+        m, n = int(rng.integers(3, 12)), int(rng.integers(3, 14))
+        A = rng.integers(-2, 7, size=(m, n)).astype(float)
+        b = rng.integers(0, 12, size=m).astype(float)
+        c = rng.integers(-2, 9, size=n).astype(float)
+        rel = rng.choice([0, 0, 0, 2], size=m).astype(np.int32)
+        sense = t % 2
+        want = orc.primal_solve(A, b, c, rel, sense, max_iterations=60)
+        s = lpx.Session(A, b, c, rel=rel, sense=sense, max_iterations=60, single_cta_select=protocol, kblock=kblock)
+        st, tot = F.RUNNING, 0
+        while st == F.RUNNING:
+            st, tot = s.step(7)
+        assert st == want["status"] and tot == want["n_pivots"], t
+        assert s.pivots(max(tot, 1))[:tot].tolist() == want["pivots"].tolist(), t
+        if st >= 0:
+            assert_bits_equal(s.tableau(), want["tableau"], f"tableau {t}")
+        s.close()
+
+
 def test_step_granularity_is_invisible(lpx):
     A, b, c = workloads.lp_decimal(96, 200, 3)
     s1 = lpx.Session(A, b, c)
-    s2 = lpx.Session(A, b, c)
+    s2 = lpx.Session(A, b, c, single_cta_select=2)
     s1.step(3)
     s1.step(5)
     st1, t1 = s1.step(4)

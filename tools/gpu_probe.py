@@ -78,3 +78,30 @@ if __name__ == "__main__":
         print(json.dumps(time_batched(kernel=F.KERNEL_CTA_REG, reg_variant=1, count=592, reps=1)), flush=True)
     if what == "prof_smem":
         print(json.dumps(time_batched(kernel=F.KERNEL_CTA_SMEM, threads=256, count=592, reps=1)), flush=True)
+    if what == "largeprof":
+        import ctypes as C
+        A, b, c = workloads.large_c3()
+        for sc in (1, 0):
+            s = api.Session(A, b, c, max_iterations=1 << 30, single_cta_select=sc)
+            s.step(20)
+            us = (C.c_double * 3)()
+            F.lib().lpx_session_profile.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+            F.check(F.lib().lpx_session_profile(s._h, 60, us))
+            print(json.dumps(dict(single_cta_select=sc, prep_us=us[0], update_us=us[1], per_pivot_us=us[2])), flush=True)
+            s.close()
+    if what == "block":
+        A, b, c = workloads.large_c3()
+        for kb in (1, 4, 8, 12, 16):
+            s = api.Session(A, b, c, max_iterations=1 << 30, kblock=kb)
+            ss = torch.cuda.ExternalStream(s.stream)
+            s.step(32)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            npv = 192
+            e0.record(ss)
+            s.step_async(npv)
+            e1.record(ss)
+            st, tot = s.sync()
+            us = e0.elapsed_time(e1) * 1e3 / npv
+            print(json.dumps(dict(kblock=kb, us_per_pivot=us, pivots_s=1e6 / us, status=st, total=tot,
+                                  x_roofline=805568528 / us / 1e3 / 6555.2)), flush=True)
+            s.close()
