@@ -53,6 +53,7 @@ struct StreamParams {
     double* Pbuf;  // kblock x ld normalised pivot rows
     int* Lbuf;     // kblock leaving rows
     int kblock;    // 0: per-pivot protocol
+    unsigned long long* dbg;  // optional phase timestamps (development aid)
 };
 
 #define LPX_PREP_THREADS 1024
@@ -480,6 +481,7 @@ struct lpx_session {
     int nbuf = 0;
     dim3 grid_update;
     dim3 grid_block;
+    bool la_cluster = false;  // look-ahead on a thread-block cluster (else one CTA)
     int device = 0;
 };
 
@@ -521,8 +523,22 @@ static int launch_pair(lpx_session* s, int probe_only) {
 static size_t lookahead_smem(const StreamParams& P) { return ((size_t)P.ld + 3 * (size_t)P.colstride) * 8; }
 
 // One block of the look-ahead protocol: decide up to `budget` pivots, then one HBM pass.
+static size_t lookahead_cluster_smem(const StreamParams& P) {
+    const size_t cw = ((((size_t)P.ld + LPX_LA_CLUSTER - 1) / LPX_LA_CLUSTER) + 1) & ~(size_t)1;
+    const size_t q = ((size_t)P.m + LPX_LA_THREADS - 1) / LPX_LA_THREADS;
+    return (cw + 2 * (size_t)P.colstride + q * LPX_LA_THREADS) * 8;
+}
+
+static void launch_lookahead(lpx_session* s, int budget) {
+    if (s->la_cluster)
+        stream_lookahead_cluster_kernel<<<LPX_LA_CLUSTER, LPX_LA_THREADS, lookahead_cluster_smem(s->P), s->stream>>>(
+            s->P, budget);
+    else
+        stream_lookahead_kernel<<<1, 1024, lookahead_smem(s->P), s->stream>>>(s->P, budget);
+}
+
 static int launch_block(lpx_session* s, int budget) {
-    stream_lookahead_kernel<<<1, 1024, lookahead_smem(s->P), s->stream>>>(s->P, budget);
+    launch_lookahead(s, budget);
     count_launch();
     if (budget > 0) {
         if (s->P.kblock <= 8) stream_update_block_kernel<8, 4><<<s->grid_block, 256, 0, s->stream>>>(s->P);
@@ -592,18 +608,27 @@ static lpx_session* session_create(int m, int n, int sense, const double* dA, co
     // blocked look-ahead protocol: needs z-row + three row-length vectors in one CTA's shared memory.
     // reserved[2]: 0 auto, 1 single-CTA select per pivot, 2 multi-CTA prep per pivot.  reserved[4]: block size.
     P.kblock = 0;
-    if (s->opt.reserved[2] == 0 && lookahead_smem(P) + 4096 <= (size_t)max_smem_optin()) {
-        P.kblock = s->opt.reserved[4] > 0 ? std::min(s->opt.reserved[4], LPX_BLOCK_KMAX) : 8;
-        if (cudaFuncSetAttribute(stream_lookahead_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)lookahead_smem(P)) != cudaSuccess) {
-            cudaGetLastError();
-            P.kblock = 0;
+    // reserved[2] == 3 forces the single-CTA look-ahead (tests); otherwise the cluster version is preferred.
+    const bool blocked_wanted = s->opt.reserved[2] == 0 || s->opt.reserved[2] == 3;
+    if (blocked_wanted) {
+        const int kb = s->opt.reserved[4] > 0 ? std::min(s->opt.reserved[4], LPX_BLOCK_KMAX) : 8;
+        if (s->opt.reserved[2] == 0 && lookahead_cluster_smem(P) + 24 * 1024 <= (size_t)max_smem_optin() &&
+            cudaFuncSetAttribute(stream_lookahead_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)lookahead_cluster_smem(P)) == cudaSuccess) {
+            P.kblock = kb;
+            s->la_cluster = true;
+        } else if (lookahead_smem(P) + 4096 <= (size_t)max_smem_optin() &&
+                   cudaFuncSetAttribute(stream_lookahead_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)lookahead_smem(P)) == cudaSuccess) {
+            P.kblock = kb;
         }
+        cudaGetLastError();
     }
     if (s->opt.reserved[2] == 1) P.npartial = 0;
     P.Fbuf = (double*)sess_alloc(s, (size_t)LPX_BLOCK_KMAX * P.colstride * 8);
     P.Pbuf = (double*)sess_alloc(s, (size_t)LPX_BLOCK_KMAX * P.ld * 8);
     P.Lbuf = (int*)sess_alloc(s, (size_t)LPX_BLOCK_KMAX * 4);
+    P.dbg = (unsigned long long*)sess_alloc(s, 16 * 8);
     if (P.npartial > 0 && prep_smem > 40 * 1024 &&
         cudaFuncSetAttribute(stream_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem) !=
             cudaSuccess)
@@ -741,6 +766,14 @@ int lpx_session_profile(lpx_session* s, int n, double* us) {
     for (auto& e : ev) LPX_CUDA(cudaEventCreate(&e));
     for (int k = 0; k < n; k++) {
         LPX_CUDA(cudaEventRecord(ev[3 * k], s->stream));
+        if (s->P.kblock > 0) {
+            launch_lookahead(s, s->P.kblock);
+            LPX_CUDA(cudaEventRecord(ev[3 * k + 1], s->stream));
+            if (s->P.kblock <= 8) stream_update_block_kernel<8, 4><<<s->grid_block, 256, 0, s->stream>>>(s->P);
+            else stream_update_block_kernel<16, 2><<<s->grid_block, 256, 0, s->stream>>>(s->P);
+            LPX_CUDA(cudaEventRecord(ev[3 * k + 2], s->stream));
+            continue;
+        }
         if (s->P.npartial > 0)
             stream_prep_kernel<<<s->P.npartial, LPX_PREP_THREADS, (size_t)s->P.m * 8, s->stream>>>(s->P, 0);
         else
@@ -763,6 +796,14 @@ int lpx_session_profile(lpx_session* s, int n, double* us) {
     us[1] = b * 1e3 / n;
     us[2] = ms * 1e3 / n;
     for (auto& e : ev) cudaEventDestroy(e);
+    return LPX_OK;
+}
+
+// Development aid: phase timestamps (ns) of the first step of the last look-ahead launch.
+int lpx_session_debug_stamps(lpx_session* s, unsigned long long* out8) {
+    if (!s || !out8 || !s->P.dbg) return LPX_E_BAD_ARGS;
+    LPX_CUDA(cudaStreamSynchronize(s->stream));
+    LPX_CUDA(cudaMemcpy(out8, s->P.dbg, 8 * 8, cudaMemcpyDeviceToHost));
     return LPX_OK;
 }
 

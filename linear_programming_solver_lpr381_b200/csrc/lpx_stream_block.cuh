@@ -13,10 +13,19 @@
 //
 // Included by lpx_stream.cu (uses its StreamParams / StreamCtl / block_min_int).
 #pragma once
+#include <cooperative_groups.h>
 
 namespace lpx {
 
 #define LPX_BLOCK_KMAX 16
+
+__device__ __forceinline__ unsigned long long lpx_gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// phase timestamps of the first look-ahead step of a launch (development aid; P.dbg may be null)
+#define LPX_STAMP(k_) do { if (P.dbg && tid == 0 && cnt == 0) P.dbg[k_] = lpx_gtime(); } while (0)
 
 // One CTA, 1024 threads.  Dynamic shared memory: z[ld] | rhs[cs] | ratio[cs] | col[cs].
 // budget = 0: probe only (resolve OPTIMAL / UNBOUNDED / ITER_LIMIT for the tableau as it stands).
@@ -48,6 +57,7 @@ __global__ void __launch_bounds__(1024) stream_lookahead_kernel(StreamParams P, 
     const bool probe = budget <= 0;
     const int steps = probe ? 1 : min(budget, P.kblock);
     int cnt = 0, st = LPX_RUNNING;
+    LPX_STAMP(0);
     for (int k = 0; k < steps; k++) {
         if (done + cnt >= P.max_iter) {  // "if (iter > MaxIterations) throw" precedes the optimality test
             st = LPX_S_ITER_LIMIT;
@@ -59,25 +69,40 @@ __global__ void __launch_bounds__(1024) stream_lookahead_kernel(StreamParams P, 
             st = LPX_OPTIMAL;
             break;
         }
+        LPX_STAMP(1);
         // ---- column e: gather from HBM, apply the pivots decided so far, form the ratios ---------
         if (tid < cnt) s_pe[tid] = P.Pbuf[(size_t)tid * ld + e];
         __syncthreads();
-        for (int base = 0; base < rows; base += 4 * TH) {
-            double c[4];
+        // s is the OUTER loop so that each round issues all of a thread's loads together: with s
+        // inside, the f_s[i] loads of one element are serialised by the dependent chain and this
+        // phase cost ~1 us per decided pivot and element column
+        for (int base = 0; base < rows; base += 8 * TH) {
+            double c[8];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < 8; u++) {
                 const int i = base + u * TH + tid;
                 c[u] = i < rows ? P.T[(size_t)i * ld + e] : 0.0;
             }
+            for (int s = 0; s < cnt; s++) {
+                const double ps = s_pe[s];
+                const int ls = s_L[s];
+                double f[8];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < 8; u++) {
+                    const int i = base + u * TH + tid;
+                    f[u] = i < rows ? P.Fbuf[(size_t)s * cs + i] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int i = base + u * TH + tid;
+                    c[u] = (i == ls) ? ps : __dsub_rn(c[u], __dmul_rn(f[u], ps));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
                 const int i = base + u * TH + tid;
                 if (i < rows) {
-                    double v = c[u];
-                    for (int s = 0; s < cnt; s++) {
-                        const double ps = s_pe[s];
-                        v = (i == s_L[s]) ? ps : __dsub_rn(v, __dmul_rn(P.Fbuf[(size_t)s * cs + i], ps));
-                    }
+                    const double v = c[u];
                     col[i] = v;
                     if (i < m) {
                         double r = __longlong_as_double(0x7ff8000000000000LL);
@@ -88,10 +113,13 @@ __global__ void __launch_bounds__(1024) stream_lookahead_kernel(StreamParams P, 
             }
         }
         __syncthreads();
+        LPX_STAMP(2);
         // ---- ChooseLeaving: the exact sequential margin rule (first-hit rounds) -----------------
         double best = __longlong_as_double(0x7ff0000000000000LL);
         int row = -1, start = 0;
+        int rounds = 0;
         while (true) {
+            rounds++;
             const double thr = __dsub_rn(best, LPX_MARGIN_PRIMAL);
             int cand = INT_MAX;
             int i = tid;
@@ -112,6 +140,8 @@ __global__ void __launch_bounds__(1024) stream_lookahead_kernel(StreamParams P, 
             break;
         }
         if (probe) break;
+        LPX_STAMP(3);
+        if (P.dbg && tid == 0 && cnt == 0) P.dbg[7] = rounds;
         const int l = row;
         const double piv = col[l], fz = col[m];
         // ---- row l: gather, apply the pivots decided so far, normalise, advance the z-row -------
@@ -119,23 +149,30 @@ __global__ void __launch_bounds__(1024) stream_lookahead_kernel(StreamParams P, 
         __syncthreads();
         double* pout = P.Pbuf + (size_t)cnt * ld;
         const double* Tl = P.T + (size_t)l * ld;
-        for (int base = 0; base < ld; base += 4 * TH) {
-            double r4[4];
+        for (int base = 0; base < ld; base += 8 * TH) {
+            double r8[8];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < 8; u++) {
                 const int j = base + u * TH + tid;
-                r4[u] = j < ld ? Tl[j] : 0.0;
+                r8[u] = j < ld ? Tl[j] : 0.0;
+            }
+            for (int s = 0; s < cnt; s++) {
+                const double fs = s_fl[s];
+                const bool same = l == s_L[s];
+                double ps[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int j = base + u * TH + tid;
+                    ps[u] = j < ld ? P.Pbuf[(size_t)s * ld + j] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) r8[u] = same ? ps[u] : __dsub_rn(r8[u], __dmul_rn(fs, ps[u]));
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < 8; u++) {
                 const int j = base + u * TH + tid;
                 if (j < ld) {
-                    double v = r4[u];
-                    for (int s = 0; s < cnt; s++) {
-                        const double ps = P.Pbuf[(size_t)s * ld + j];
-                        v = (l == s_L[s]) ? ps : __dsub_rn(v, __dmul_rn(s_fl[s], ps));
-                    }
-                    const double pj = __ddiv_rn(v, piv);
+                    const double pj = __ddiv_rn(r8[u], piv);
                     pout[j] = pj;
                     if (j < width - 1) z[j] = __dsub_rn(z[j], __dmul_rn(fz, pj));
                 }
@@ -144,6 +181,7 @@ __global__ void __launch_bounds__(1024) stream_lookahead_kernel(StreamParams P, 
         // ---- RHS column and bookkeeping ----------------------------------------------------------
         const double prhs = __ddiv_rn(rhs[l], piv);
         __syncthreads();  // every thread has read rhs[l]; z is complete for the next argmin
+        LPX_STAMP(4);
         double* fout = P.Fbuf + (size_t)cnt * cs;
         for (int i = tid; i < rows; i += TH) {
             const double f = col[i];
@@ -159,15 +197,350 @@ __global__ void __launch_bounds__(1024) stream_lookahead_kernel(StreamParams P, 
                 P.pivlog[2 * (done + cnt) + 1] = l;
             }
         }
+        LPX_STAMP(5);
         cnt++;
         __syncthreads();
     }
+    if (P.dbg && tid == 0) P.dbg[6] = lpx_gtime();
     for (int i = tid; i < rows; i += TH) P.rhsbuf[i] = rhs[i];
     if (tid == 0) {
         ctl->block_cnt = cnt;
         ctl->pivots = done + cnt;
         if (st != LPX_RUNNING) ctl->status = st;
     }
+}
+
+// ---- cluster look-ahead ----------------------------------------------------------------------
+// One SM cannot keep enough loads in flight: gathering one tableau column (4097 scattered 32-byte
+// sectors) or one row (98 KB) from HBM takes 6-7 us from a single CTA, and a look-ahead step
+// needs both.  The same step spread over a thread-block cluster of 8 CTAs: CTA r owns rows
+// [r*RS, (r+1)*RS) for the column phase and columns [r*CW, (r+1)*CW) for the row phase and the
+// z-row; the up-to-date column is all-gathered through distributed shared memory, after which
+// every CTA repeats the (cheap, exact) ratio scan on its own copy, so no decision ever has to be
+// broadcast.  Three cluster barriers per decided pivot.
+//
+// The ratio scan itself uses the record property of the reference's rule: a row can only be
+// accepted by "ratio < best - 1e-9" if its ratio is a strict prefix minimum, so a
+// parallel prefix-min marks the few records (about ln m) and one thread replays the sequential
+// rule over them.
+#define LPX_LA_CLUSTER 8
+#define LPX_LA_THREADS 512
+#define LPX_LA_RECCAP 1024
+
+struct LaRecord {
+    double v;
+    int i;
+    int pad;
+};
+
+// Exact ChooseLeaving over ratio[0..m) (NaN = not eligible) by one CTA of LPX_LA_THREADS threads.
+// ratio is stored permuted: element i lives at (i % Q) * TH + i / Q with Q = ceil(m / TH), so that
+// thread t reads its Q consecutive rows t*Q .. t*Q+Q-1 without bank conflicts.
+__device__ __forceinline__ int la_leaving_scan(const double* ratio, int m, int Q, double* s_wmin, int* s_wcnt,
+                                               LaRecord* s_rec, int* s_out, int* s_ired) {
+    constexpr int TH = LPX_LA_THREADS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    double lmin = INF;
+    for (int u = 0; u < Q; u++) {
+        const int i = tid * Q + u;
+        double r = i < m ? ratio[u * TH + tid] : INF;
+        if (!(r == r)) r = INF;
+        lmin = fmin(lmin, r);
+    }
+    // exclusive prefix-min over threads
+    double incl = lmin;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const double o = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl = fmin(incl, o);
+    }
+    if (lane == 31) s_wmin[warp] = incl;
+    __syncthreads();
+    double pm = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) pm = INF;
+    for (int w = 0; w < warp; w++) pm = fmin(pm, s_wmin[w]);
+    // records of this thread, in row order
+    int cnt = 0;
+    double run = pm;
+    for (int u = 0; u < Q; u++) {
+        const int i = tid * Q + u;
+        const double r = i < m ? ratio[u * TH + tid] : INF;
+        if (r < run) {
+            run = r;
+            cnt++;
+        }
+    }
+    int incl_c = cnt;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl_c, off);
+        if (lane >= off) incl_c += o;
+    }
+    if (lane == 31) s_wcnt[warp] = incl_c;
+    __syncthreads();
+    int offset = incl_c - cnt;
+    int total = 0;
+    for (int w = 0; w < TH / 32; w++) {
+        const int c = s_wcnt[w];
+        if (w < warp) offset += c;
+        total += c;
+    }
+    if (total <= LPX_LA_RECCAP) {
+        run = pm;
+        for (int u = 0; u < Q; u++) {
+            const int i = tid * Q + u;
+            const double r = i < m ? ratio[u * TH + tid] : INF;
+            if (r < run) {
+                run = r;
+                s_rec[offset].v = r;
+                s_rec[offset].i = i;
+                offset++;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double best = INF;
+            int row = -1;
+            for (int k = 0; k < total; k++) {
+                const double r = s_rec[k].v;
+                if (r < __dsub_rn(best, LPX_MARGIN_PRIMAL)) {
+                    best = r;
+                    row = s_rec[k].i;
+                }
+            }
+            *s_out = row;
+        }
+        __syncthreads();
+        return *s_out;
+    }
+    // more records than the list holds (monotone ratios): first-hit rounds, still exact
+    double best = INF;
+    int row = -1, start = 0;
+    while (true) {
+        const double thr = __dsub_rn(best, LPX_MARGIN_PRIMAL);
+        int cand = INT_MAX;
+        for (int u = 0; u < Q; u++) {
+            const int i = tid * Q + u;
+            if (i >= start && i < m && ratio[u * TH + tid] < thr) {
+                cand = i;
+                break;
+            }
+        }
+        cand = block_min_int<TH>(cand, s_ired);
+        if (cand == INT_MAX) break;
+        best = ratio[(cand % Q) * TH + cand / Q];
+        row = cand;
+        start = cand + 1;
+    }
+    return row;
+}
+
+__global__ void __cluster_dims__(LPX_LA_CLUSTER, 1, 1) __launch_bounds__(LPX_LA_THREADS)
+    stream_lookahead_cluster_kernel(StreamParams P, int budget) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ double sm_lc[];
+    __shared__ ArgMin red[34];
+    __shared__ ArgMin s_part[LPX_LA_CLUSTER];  // every CTA's z-slice argmin, written by its owner
+    __shared__ double s_wmin[LPX_LA_THREADS / 32];
+    __shared__ int s_wcnt[LPX_LA_THREADS / 32 + 2];
+    __shared__ LaRecord s_rec[LPX_LA_RECCAP];
+    __shared__ int s_out;
+    __shared__ int s_ired[34];
+    __shared__ int s_L[LPX_BLOCK_KMAX];
+    __shared__ double s_pe[LPX_BLOCK_KMAX];
+    __shared__ double s_fl[LPX_BLOCK_KMAX];
+    constexpr int TH = LPX_LA_THREADS, CL = LPX_LA_CLUSTER;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rank = (int)cluster.block_rank();
+    const int ld = P.ld, cs = P.colstride, m = P.m, rows = P.rows, width = P.width;
+    const int RS = (rows + CL - 1) / CL;            // rows per CTA (column phase)
+    const int CW = (((ld + CL - 1) / CL) + 1) & ~1;  // columns per CTA (row phase, z slice)
+    const int i_lo = rank * RS, i_hi = min(rows, i_lo + RS);
+    const int j_lo = rank * CW, j_hi = min(ld, j_lo + CW);
+    const int Q = (m + TH - 1) / TH;
+    double* zloc = sm_lc;          // CW
+    double* rhs = zloc + CW;       // cs, full copy in every CTA
+    double* col = rhs + cs;        // cs, full copy (all-gathered)
+    double* ratio = col + cs;      // Q * TH, permuted
+    StreamCtl* ctl = P.ctl;
+    const int status0 = ctl->status;
+    const int done = ctl->pivots;
+    cluster.sync();  // every CTA has read the control block before rank 0 rewrites it
+    if (rank == 0 && tid == 0) ctl->block_cnt = 0;
+    if (status0 != LPX_RUNNING) return;
+
+    const double* Tz = P.T + (size_t)m * ld;
+    for (int j = j_lo + tid; j < j_hi; j += TH) zloc[j - j_lo] = Tz[j];
+    for (int i = tid; i < rows; i += TH) rhs[i] = P.rhsbuf[i];
+    __syncthreads();
+
+    const bool probe = budget <= 0;
+    const int steps = probe ? 1 : min(budget, P.kblock);
+    int cnt = 0, st = LPX_RUNNING;
+    for (int k = 0; k < steps; k++) {
+        if (done + cnt >= P.max_iter) {
+            st = LPX_S_ITER_LIMIT;
+            break;
+        }
+        // ---- ChooseEntering: slice argmin, exchanged through distributed shared memory -----------
+        {
+            ArgMin a;
+            a.v = -LPX_EPS;
+            a.i = INT_MAX;
+            for (int j = j_lo + tid; j < j_hi && j < width - 1; j += TH) {
+                const double zv = zloc[j - j_lo];
+                if (zv < a.v) {
+                    a.v = zv;
+                    a.i = j;
+                }
+            }
+            a = warp_argmin(a);
+            if (lane == 0) red[warp] = a;
+            __syncthreads();
+            if (warp == 0) {
+                ArgMin b2;
+                b2.v = -LPX_EPS;
+                b2.i = INT_MAX;
+                if (lane < TH / 32) b2 = red[lane];
+                b2 = warp_argmin(b2);
+                if (lane < CL) {
+                    ArgMin* dst = cluster.map_shared_rank(s_part, lane);
+                    dst[rank] = b2;
+                }
+            }
+        }
+        cluster.sync();  // (1)
+        ArgMin g = s_part[0];
+#pragma unroll
+        for (int r = 1; r < CL; r++) g = argmin_pick(g, s_part[r]);
+        const int e = g.i == INT_MAX ? -1 : g.i;
+        if (e < 0) {
+            st = LPX_OPTIMAL;
+            break;
+        }
+        // ---- column e, rows of this CTA: gather, bring up to date, all-gather -------------------
+        if (tid < cnt) s_pe[tid] = P.Pbuf[(size_t)tid * ld + e];
+        __syncthreads();
+        for (int base = i_lo; base < i_hi; base += 2 * TH) {
+            double c[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int i = base + u * TH + tid;
+                c[u] = i < i_hi ? P.T[(size_t)i * ld + e] : 0.0;
+            }
+            for (int s = 0; s < cnt; s++) {
+                const double ps = s_pe[s];
+                const int ls = s_L[s];
+                double f[2];
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int i = base + u * TH + tid;
+                    f[u] = i < i_hi ? P.Fbuf[(size_t)s * cs + i] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int i = base + u * TH + tid;
+                    c[u] = (i == ls) ? ps : __dsub_rn(c[u], __dmul_rn(f[u], ps));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int i = base + u * TH + tid;
+                if (i < i_hi) {
+#pragma unroll
+                    for (int r = 0; r < CL; r++) cluster.map_shared_rank(col, r)[i] = c[u];
+                }
+            }
+        }
+        cluster.sync();  // (2) every CTA holds the whole up-to-date column
+        for (int i = tid; i < Q * TH; i += TH) {
+            // permuted slot (u, t) <-> row t*Q + u
+            const int t = i % TH, u = i / TH;
+            const int row_i = t * Q + u;
+            double r = __longlong_as_double(0x7ff8000000000000LL);
+            if (row_i < m) {
+                const double a = col[row_i];
+                if (a > LPX_EPS) r = __ddiv_rn(rhs[row_i], a);
+            }
+            ratio[i] = r;
+        }
+        __syncthreads();
+        const int l = la_leaving_scan(ratio, m, Q, s_wmin, s_wcnt, s_rec, &s_out, s_ired);
+        if (l < 0) {
+            st = LPX_UNBOUNDED;
+            break;
+        }
+        if (probe) break;
+        const double piv = col[l], fz = col[m];
+        // ---- row l, columns of this CTA: gather, bring up to date, normalise, advance z ----------
+        if (tid < cnt) s_fl[tid] = P.Fbuf[(size_t)tid * cs + l];
+        __syncthreads();
+        double* pout = P.Pbuf + (size_t)cnt * ld;
+        const double* Tl = P.T + (size_t)l * ld;
+        for (int base = j_lo; base < j_hi; base += 4 * TH) {
+            double r4[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int j = base + u * TH + tid;
+                r4[u] = j < j_hi ? Tl[j] : 0.0;
+            }
+            for (int s = 0; s < cnt; s++) {
+                const double fs = s_fl[s];
+                const bool same = l == s_L[s];
+                double ps[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int j = base + u * TH + tid;
+                    ps[u] = j < j_hi ? P.Pbuf[(size_t)s * ld + j] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) r4[u] = same ? ps[u] : __dsub_rn(r4[u], __dmul_rn(fs, ps[u]));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int j = base + u * TH + tid;
+                if (j < j_hi) {
+                    const double pj = __ddiv_rn(r4[u], piv);
+                    pout[j] = pj;
+                    if (j < width - 1) zloc[j - j_lo] = __dsub_rn(zloc[j - j_lo], __dmul_rn(fz, pj));
+                }
+            }
+        }
+        // ---- RHS (every CTA keeps the full vector), factor column slice, bookkeeping ------------
+        const double prhs = __ddiv_rn(rhs[l], piv);
+        __syncthreads();
+        double* fout = P.Fbuf + (size_t)cnt * cs;
+        for (int i = tid; i < rows; i += TH) {
+            const double f = col[i];
+            if (i >= i_lo && i < i_hi) fout[i] = f;
+            rhs[i] = (i == l) ? prhs : __dsub_rn(rhs[i], __dmul_rn(f, prhs));
+        }
+        if (tid == 0) {
+            s_L[cnt] = l;
+            if (rank == 0) {
+                P.Lbuf[cnt] = l;
+                P.basis[l] = e;
+                if (done + cnt < P.pivlog_cap) {
+                    P.pivlog[2 * (done + cnt)] = e;
+                    P.pivlog[2 * (done + cnt) + 1] = l;
+                }
+            }
+        }
+        cnt++;
+        __threadfence();
+        cluster.sync();  // (3) Pbuf / Fbuf slices of this pivot are visible to the whole cluster
+    }
+    if (rank == 0) {
+        for (int i = tid; i < rows; i += TH) P.rhsbuf[i] = rhs[i];
+        if (tid == 0) {
+            ctl->block_cnt = cnt;
+            ctl->pivots = done + cnt;
+            if (st != LPX_RUNNING) ctl->status = st;
+        }
+    }
+    cluster.sync();  // no CTA may exit while a peer can still write into its shared memory
 }
 
 // The HBM pass of a block: every element takes the block's updates in pivot order.

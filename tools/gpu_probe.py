@@ -105,3 +105,35 @@ if __name__ == "__main__":
             print(json.dumps(dict(kblock=kb, us_per_pivot=us, pivots_s=1e6 / us, status=st, total=tot,
                                   x_roofline=805568528 / us / 1e3 / 6555.2)), flush=True)
             s.close()
+    if what == "stamps":
+        import ctypes as C
+        A, b, c = workloads.large_c3()
+        s = api.Session(A, b, c, max_iterations=1 << 30, kblock=8)
+        s.step(24)
+        for rep in range(3):
+            s.step(8)
+            out = (C.c_ulonglong * 8)()
+            F.lib().lpx_session_debug_stamps.argtypes = [C.c_void_p, C.c_void_p]
+            F.check(F.lib().lpx_session_debug_stamps(s._h, out))
+            t = list(out)
+            print(json.dumps(dict(argmin=t[1] - t[0], column=t[2] - t[1], ratio_rounds=t[3] - t[2], rounds=t[7],
+                                  row=t[4] - t[3], rhs=t[5] - t[4], whole_block=t[6] - t[0])), flush=True)
+        s.close()
+    if what == "block8":
+        A, b, c = workloads.large_c3()
+        s = api.Session(A, b, c, max_iterations=1 << 30, kblock=8)
+        s.step(32)
+        st, tot = s.step(16)
+        print(st, tot)
+        s.close()
+    if what == "blockprof":
+        import ctypes as C
+        A, b, c = workloads.large_c3()
+        for kb in (1, 8, 16):
+            s = api.Session(A, b, c, max_iterations=1 << 30, kblock=kb)
+            s.step(32)
+            us = (C.c_double * 3)()
+            F.lib().lpx_session_profile.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+            F.check(F.lib().lpx_session_profile(s._h, 12, us))
+            print(json.dumps(dict(kblock=kb, lookahead_us=us[0], pass_us=us[1], per_block_us=us[2])), flush=True)
+            s.close()
