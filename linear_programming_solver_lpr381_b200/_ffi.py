@@ -40,7 +40,9 @@ class LpxError(RuntimeError):
 
 
 class Options(C.Structure):
-    _fields_ = [("max_iterations", C.c_int), ("kernel", C.c_int), ("threads", C.c_int), ("reserved", C.c_int * 5)]
+    _fields_ = [("max_iterations", C.c_int), ("kernel", C.c_int), ("threads", C.c_int), ("knap_spec_nodes", C.c_int),
+                ("knap_spec_depth", C.c_int), ("stream_protocol", C.c_int), ("reg_variant", C.c_int),
+                ("stream_block", C.c_int), ("stream_pass_variant", C.c_int), ("reserved", C.c_int * 7)]
 
 
 class BnbNode(C.Structure):
@@ -148,17 +150,18 @@ def check(rc):
         raise LpxError(rc, last_error())
 
 
-def make_options(max_iterations=10000, kernel=KERNEL_AUTO, threads=0, spec_nodes=0, spec_depth=0, single_cta_select=0, reg_variant=0, kblock=0):
+def make_options(max_iterations=10000, kernel=KERNEL_AUTO, threads=0, spec_nodes=0, spec_depth=0, single_cta_select=0, reg_variant=0, kblock=0, pass_variant=0):
     o = Options()
     lib().lpx_default_options(C.byref(o))
     o.max_iterations = max_iterations
     o.kernel = kernel
     o.threads = threads
-    o.reserved[0] = spec_nodes
-    o.reserved[1] = spec_depth
-    o.reserved[2] = single_cta_select  # streaming kernels: 0 blocked look-ahead, 1 / 2 per-pivot protocols
-    o.reserved[3] = reg_variant  # register kernel: 2 = the 2-CTAs-per-SM build
-    o.reserved[4] = kblock  # streaming kernels: pivots per HBM pass (0 = default 8, max 16)
+    o.knap_spec_nodes = spec_nodes
+    o.knap_spec_depth = spec_depth
+    o.stream_protocol = single_cta_select  # 0 blocked look-ahead (cluster), 3 blocked (one CTA), 1 / 2 per pivot
+    o.reg_variant = reg_variant
+    o.stream_block = kblock
+    o.stream_pass_variant = pass_variant
     return o
 
 

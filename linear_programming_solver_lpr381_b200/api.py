@@ -115,8 +115,9 @@ class Session:
     """Large single LP whose tableau lives in HBM (lpx_session_*)."""
 
     def __init__(self, A, b, c, rel=None, sense=0, max_iterations=10000, device_ptrs=False, m=None, n=None,
-                 single_cta_select=0, kblock=0):
-        opt = F.make_options(max_iterations, single_cta_select=single_cta_select, kblock=kblock)
+                 single_cta_select=0, kblock=0, pass_variant=0):
+        opt = F.make_options(max_iterations, single_cta_select=single_cta_select, kblock=kblock,
+                             pass_variant=pass_variant)
         if device_ptrs:
             self.m, self.n = m, n
             relp = None if rel is None else np.ascontiguousarray(rel, dtype=np.int32)

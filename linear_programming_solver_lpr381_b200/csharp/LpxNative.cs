@@ -10,7 +10,8 @@ namespace Linear_Programming_Solver.Models
     internal struct LpxOptions
     {
         public int max_iterations, kernel, threads;
-        public int r0, r1, r2, r3, r4;
+        public int knap_spec_nodes, knap_spec_depth, stream_protocol, reg_variant, stream_block, stream_pass_variant;
+        public int r0, r1, r2, r3, r4, r5, r6;
     }
 
     [StructLayout(LayoutKind.Sequential)]

@@ -757,8 +757,8 @@ static int knapsack_entry(int count, int n, const double* profit, const double* 
     d.capacity = capacity;
     lpx_default_options(&d.opt);
     if (opt) d.opt = *opt;
-    if (d.opt.reserved[0] > 0) d.spec_nodes = d.opt.reserved[0];
-    if (d.opt.reserved[1] > 0) d.spec_depth = d.opt.reserved[1];
+    if (d.opt.knap_spec_nodes > 0) d.spec_nodes = d.opt.knap_spec_nodes;
+    if (d.opt.knap_spec_depth > 0) d.spec_depth = d.opt.knap_spec_depth;
     d.on_pop = on_pop;
     d.user = user;
     rc = d.run();

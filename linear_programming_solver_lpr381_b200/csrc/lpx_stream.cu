@@ -482,6 +482,7 @@ struct lpx_session {
     dim3 grid_update;
     dim3 grid_block;
     bool la_cluster = false;  // look-ahead on a thread-block cluster (else one CTA)
+    int rpc_block = 0;        // rows per CTA of the blocked pass
     int device = 0;
 };
 
@@ -537,12 +538,31 @@ static void launch_lookahead(lpx_session* s, int budget) {
         stream_lookahead_kernel<<<1, 1024, lookahead_smem(s->P), s->stream>>>(s->P, budget);
 }
 
+// pass variants: <KMAX, doubles per thread, rows in flight>
+typedef void (*BlockPassFn)(StreamParams, int);
+static BlockPassFn block_pass_fn(const lpx_session* s) {
+    const int variant = s->opt.stream_pass_variant;  // 0 auto; 1: VEC 2 (128-bit accesses); 2: VEC 1
+    if (s->P.kblock <= 8) return variant == 2 ? stream_update_block_kernel<8, 1, 4> : stream_update_block_kernel<8, 2, 4>;
+    return variant == 1 ? stream_update_block_kernel<16, 2, 2> : stream_update_block_kernel<16, 1, 4>;
+}
+static int block_pass_vec(const lpx_session* s) {
+    const int variant = s->opt.stream_pass_variant;
+    if (s->P.kblock <= 8) return variant == 2 ? 1 : 2;
+    return variant == 1 ? 2 : 1;
+}
+static size_t block_pass_smem(const lpx_session* s) {
+    const int kmax = s->P.kblock <= 8 ? 8 : 16;
+    return (size_t)kmax * s->rpc_block * 8 + (size_t)((s->rpc_block + 15) & ~15);
+}
+static void launch_block_pass(lpx_session* s) {
+    block_pass_fn(s)<<<s->grid_block, 256, block_pass_smem(s), s->stream>>>(s->P, s->rpc_block);
+}
+
 static int launch_block(lpx_session* s, int budget) {
     launch_lookahead(s, budget);
     count_launch();
     if (budget > 0) {
-        if (s->P.kblock <= 8) stream_update_block_kernel<8, 4><<<s->grid_block, 256, 0, s->stream>>>(s->P);
-        else stream_update_block_kernel<16, 2><<<s->grid_block, 256, 0, s->stream>>>(s->P);
+        launch_block_pass(s);
         count_launch();
     }
     LPX_CUDA(cudaGetLastError());
@@ -606,13 +626,13 @@ static lpx_session* session_create(int m, int n, int sense, const double* dA, co
     P.npartial = (prep_smem + 2048 <= (size_t)max_smem_optin()) ? prep_ctas : 0;
     P.partial = (ArgMin*)sess_alloc(s, (size_t)prep_ctas * sizeof(ArgMin));
     // blocked look-ahead protocol: needs z-row + three row-length vectors in one CTA's shared memory.
-    // reserved[2]: 0 auto, 1 single-CTA select per pivot, 2 multi-CTA prep per pivot.  reserved[4]: block size.
+    // stream_protocol: 0 auto, 1 single-CTA select per pivot, 2 multi-CTA prep per pivot.  stream_block: pivots per pass.
     P.kblock = 0;
-    // reserved[2] == 3 forces the single-CTA look-ahead (tests); otherwise the cluster version is preferred.
-    const bool blocked_wanted = s->opt.reserved[2] == 0 || s->opt.reserved[2] == 3;
+    // stream_protocol == 3 forces the single-CTA look-ahead (tests); otherwise the cluster version is preferred.
+    const bool blocked_wanted = s->opt.stream_protocol == 0 || s->opt.stream_protocol == 3;
     if (blocked_wanted) {
-        const int kb = s->opt.reserved[4] > 0 ? std::min(s->opt.reserved[4], LPX_BLOCK_KMAX) : 8;
-        if (s->opt.reserved[2] == 0 && lookahead_cluster_smem(P) + 24 * 1024 <= (size_t)max_smem_optin() &&
+        const int kb = s->opt.stream_block > 0 ? std::min(s->opt.stream_block, LPX_BLOCK_KMAX) : 8;
+        if (s->opt.stream_protocol == 0 && lookahead_cluster_smem(P) + 24 * 1024 <= (size_t)max_smem_optin() &&
             cudaFuncSetAttribute(stream_lookahead_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)lookahead_cluster_smem(P)) == cudaSuccess) {
             P.kblock = kb;
@@ -624,7 +644,7 @@ static lpx_session* session_create(int m, int n, int sense, const double* dA, co
         }
         cudaGetLastError();
     }
-    if (s->opt.reserved[2] == 1) P.npartial = 0;
+    if (s->opt.stream_protocol == 1) P.npartial = 0;
     P.Fbuf = (double*)sess_alloc(s, (size_t)LPX_BLOCK_KMAX * P.colstride * 8);
     P.Pbuf = (double*)sess_alloc(s, (size_t)LPX_BLOCK_KMAX * P.ld * 8);
     P.Lbuf = (int*)sess_alloc(s, (size_t)LPX_BLOCK_KMAX * 4);
@@ -668,14 +688,33 @@ static lpx_session* session_create(int m, int n, int sense, const double* dA, co
     int chunks = (sm_count() * occ) / strips;
     chunks = std::max(1, std::min(chunks, P.rows));
     s->grid_update = dim3(strips, chunks, 1);
-    occ = 0;
-    if (P.kblock <= 8) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stream_update_block_kernel<8, 4>, 256, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stream_update_block_kernel<16, 2>, 256, 0);
-    if (occ < 1) occ = 1;
-    chunks = (sm_count() * occ) / strips;
-    chunks = std::max(1, std::min(chunks, P.rows));
-    s->grid_block = dim3(strips, chunks, 1);
+    if (P.kblock > 0) {
+        // blocked pass: column strips x row chunks sized to one resident wave; the factor slices of a
+        // chunk must fit in shared memory next to the other resident CTAs
+        const int vec = block_pass_vec(s);
+        const int kmax = P.kblock <= 8 ? 8 : 16;
+        const int bstrips = (P.ld / vec + 255) / 256;
+        int best_rpc = 0;
+        for (int want_occ = 4; want_occ >= 1 && !best_rpc; want_occ--) {
+            int ch = std::max(1, (sm_count() * want_occ) / bstrips);
+            ch = std::min(ch, P.rows);
+            const int rpc = (P.rows + ch - 1) / ch;
+            const size_t smem = (size_t)kmax * rpc * 8 + (size_t)((rpc + 15) & ~15);
+            if (smem > (size_t)max_smem_optin()) continue;
+            cudaFuncSetAttribute(block_pass_fn(s), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            int got = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&got, block_pass_fn(s), 256, smem);
+            if (got >= want_occ || want_occ == 1) best_rpc = rpc;
+        }
+        if (!best_rpc) best_rpc = 64;
+        s->rpc_block = best_rpc;
+        const size_t smem = (size_t)kmax * best_rpc * 8 + (size_t)((best_rpc + 15) & ~15);
+        cudaFuncSetAttribute(block_pass_fn(s), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaGetLastError();
+        s->grid_block = dim3(bstrips, (P.rows + best_rpc - 1) / best_rpc, 1);
+    }
     return s;
+
 }
 
 int stream_solve_host(int m, int n, int sense, const double* A, const int* rel, const double* b, const double* c,
@@ -769,8 +808,7 @@ int lpx_session_profile(lpx_session* s, int n, double* us) {
         if (s->P.kblock > 0) {
             launch_lookahead(s, s->P.kblock);
             LPX_CUDA(cudaEventRecord(ev[3 * k + 1], s->stream));
-            if (s->P.kblock <= 8) stream_update_block_kernel<8, 4><<<s->grid_block, 256, 0, s->stream>>>(s->P);
-            else stream_update_block_kernel<16, 2><<<s->grid_block, 256, 0, s->stream>>>(s->P);
+            launch_block_pass(s);
             LPX_CUDA(cudaEventRecord(ev[3 * k + 2], s->stream));
             continue;
         }

@@ -544,73 +544,99 @@ __global__ void __cluster_dims__(LPX_LA_CLUSTER, 1, 1) __launch_bounds__(LPX_LA_
 }
 
 // The HBM pass of a block: every element takes the block's updates in pivot order.
-// grid = (column strips of 512, row chunks); p_s[j] for the thread's two columns stay in
-// registers, f_s[i] are CTA-uniform loads.  Rows that were a pivot row inside the block take the
-// select path; all others (4097 - K of them) the straight multiply/subtract chain.
-template <int KMAX, int UNROLL>
-__global__ void __launch_bounds__(256, 2) stream_update_block_kernel(StreamParams P) {
+// grid = (column strips of 256 * VEC, row chunks).  p_s[j] for the thread's VEC columns stay in
+// registers; the factor entries f_s[i] of the CTA's row chunk are staged once in shared memory
+// (K x rows-per-CTA doubles), so the inner loop is one broadcast LDS plus an unfused multiply and
+// subtract per pivot and element, and the only global traffic is the tableau itself.
+// Rows that were a pivot row inside the block take the select path; all others the straight chain.
+template <int KMAX, int VEC, int UNROLL>
+__global__ void __launch_bounds__(256) stream_update_block_kernel(StreamParams P, int rpc) {
+    extern __shared__ double sF[];  // [s][ii], ii < rpc
+    __shared__ int sL[KMAX];
     const int cnt = P.ctl->block_cnt;
     if (cnt <= 0) return;
-    __shared__ int sL[KMAX];
-    if (threadIdx.x < KMAX) sL[threadIdx.x] = threadIdx.x < cnt ? P.Lbuf[threadIdx.x] : -1;
-    __syncthreads();
-    const int j0 = (blockIdx.x * 256 + threadIdx.x) * 2;
-    if (j0 >= P.ld) return;
-    const int rpc = (P.rows + gridDim.y - 1) / gridDim.y;
     const int r0 = blockIdx.y * rpc;
     const int r1 = min(P.rows, r0 + rpc);
     const int n_rows = r1 - r0;
     if (n_rows <= 0) return;
-    double2 p[KMAX];
+    unsigned char* sPiv = reinterpret_cast<unsigned char*>(sF + (size_t)KMAX * rpc);
+    if (threadIdx.x < KMAX) sL[threadIdx.x] = threadIdx.x < cnt ? P.Lbuf[threadIdx.x] : -1;
+    __syncthreads();
+    const size_t cs = (size_t)P.colstride;
+    for (int s = 0; s < cnt; s++)
+        for (int ii = threadIdx.x; ii < n_rows; ii += 256) sF[s * rpc + ii] = P.Fbuf[(size_t)s * cs + r0 + ii];
+    for (int ii = threadIdx.x; ii < n_rows; ii += 256) {
+        bool pv = false;
+#pragma unroll
+        for (int s = 0; s < KMAX; s++) pv = pv || (r0 + ii == sL[s]);
+        sPiv[ii] = pv ? 1 : 0;
+    }
+    __syncthreads();
+    const int j0 = (blockIdx.x * 256 + threadIdx.x) * VEC;
+    if (j0 >= P.ld) return;
+    double p[KMAX][VEC];
 #pragma unroll
     for (int s = 0; s < KMAX; s++) {
-        p[s].x = 0.0;
-        p[s].y = 0.0;
-        if (s < cnt) p[s] = *reinterpret_cast<const double2*>(P.Pbuf + (size_t)s * P.ld + j0);
+#pragma unroll
+        for (int v = 0; v < VEC; v++) p[s][v] = s < cnt ? P.Pbuf[(size_t)s * P.ld + j0 + v] : 0.0;
     }
-    const size_t ld = (size_t)P.ld, cs = (size_t)P.colstride;
+    const size_t ld = (size_t)P.ld;
     double* __restrict__ Tc = P.T + j0;
-    const double* __restrict__ F = P.Fbuf;
-    const bool rev = (P.ctl->pivots & 1) != 0;  // alternate the sweep direction between passes (L2 reuse)
+    const bool rev = ((P.ctl->pivots / max(P.kblock, 1)) & 1) != 0;  // alternate the sweep direction (L2 reuse)
 
     for (int q = 0; q < n_rows; q += UNROLL) {
-        double2 t[UNROLL];
+        double t[UNROLL][VEC];
         int ri[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
             const int qq = q + u;
-            ri[u] = qq < n_rows ? (rev ? r1 - 1 - qq : r0 + qq) : -1;
-            if (ri[u] >= 0) t[u] = *reinterpret_cast<const double2*>(Tc + (size_t)ri[u] * ld);
+            ri[u] = qq < n_rows ? (rev ? n_rows - 1 - qq : qq) : -1;
+            if (ri[u] >= 0) {
+                const double* src = Tc + (size_t)(r0 + ri[u]) * ld;
+                if (VEC == 2) {
+                    const double2 d = *reinterpret_cast<const double2*>(src);
+                    t[u][0] = d.x;
+                    t[u][VEC - 1] = d.y;
+                } else {
+                    t[u][0] = *src;
+                }
+            }
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
-            const int i = ri[u];
-            if (i < 0) continue;
-            bool pivot_row = false;
-#pragma unroll
-            for (int s = 0; s < KMAX; s++) pivot_row = pivot_row || (i == sL[s]);
-            double2 v = t[u];
-            if (!pivot_row) {
+            const int ii = ri[u];
+            if (ii < 0) continue;
+            if (!sPiv[ii]) {
 #pragma unroll
                 for (int s = 0; s < KMAX; s++) {
                     if (s < cnt) {
-                        const double f = __ldg(F + (size_t)s * cs + i);
-                        v.x = __dsub_rn(v.x, __dmul_rn(f, p[s].x));
-                        v.y = __dsub_rn(v.y, __dmul_rn(f, p[s].y));
+                        const double f = sF[s * rpc + ii];
+#pragma unroll
+                        for (int v = 0; v < VEC; v++) t[u][v] = __dsub_rn(t[u][v], __dmul_rn(f, p[s][v]));
                     }
                 }
             } else {
+                const int i = r0 + ii;
 #pragma unroll
                 for (int s = 0; s < KMAX; s++) {
                     if (s < cnt) {
-                        const double f = __ldg(F + (size_t)s * cs + i);
+                        const double f = sF[s * rpc + ii];
                         const bool is_l = i == sL[s];
-                        v.x = is_l ? p[s].x : __dsub_rn(v.x, __dmul_rn(f, p[s].x));
-                        v.y = is_l ? p[s].y : __dsub_rn(v.y, __dmul_rn(f, p[s].y));
+#pragma unroll
+                        for (int v = 0; v < VEC; v++)
+                            t[u][v] = is_l ? p[s][v] : __dsub_rn(t[u][v], __dmul_rn(f, p[s][v]));
                     }
                 }
             }
-            *reinterpret_cast<double2*>(Tc + (size_t)i * ld) = v;
+            double* dst = Tc + (size_t)(r0 + ii) * ld;
+            if (VEC == 2) {
+                double2 d;
+                d.x = t[u][0];
+                d.y = t[u][VEC - 1];
+                *reinterpret_cast<double2*>(dst) = d;
+            } else {
+                *dst = t[u][0];
+            }
         }
     }
 }

@@ -129,11 +129,12 @@ if __name__ == "__main__":
     if what == "blockprof":
         import ctypes as C
         A, b, c = workloads.large_c3()
-        for kb in (1, 8, 16):
-            s = api.Session(A, b, c, max_iterations=1 << 30, kblock=kb)
+        for kb, pv in ((1, 1), (8, 1), (8, 2), (12, 2), (16, 1), (16, 2)):
+            s = api.Session(A, b, c, max_iterations=1 << 30, kblock=kb, pass_variant=pv)
             s.step(32)
             us = (C.c_double * 3)()
             F.lib().lpx_session_profile.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
             F.check(F.lib().lpx_session_profile(s._h, 12, us))
-            print(json.dumps(dict(kblock=kb, lookahead_us=us[0], pass_us=us[1], per_block_us=us[2])), flush=True)
+            print(json.dumps(dict(kblock=kb, pass_variant=pv, lookahead_us=us[0], pass_us=us[1], per_block_us=us[2],
+                                  us_per_pivot=us[2] / kb)), flush=True)
             s.close()
