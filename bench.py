@@ -167,6 +167,8 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     F.check(F.lib().lpx_init(local_rank))
     hbm_peak, peak_kind = load_peaks()
@@ -417,7 +419,7 @@ def run_ours(args):
             except Exception as e:  # a section must not take the headline down
                 extras["large_tableau"] = {"error": str(e)}
             try:
-                extras["bnb_simplex"] = bench_bnb(16)
+                extras["bnb_simplex"] = bench_bnb(256)
             except Exception as e:
                 extras["bnb_simplex"] = {"error": str(e)}
             try:

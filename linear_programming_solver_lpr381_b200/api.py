@@ -232,11 +232,13 @@ def bnb_simplex(A, b, c, rel=None, sense=0, trace=False, want_history=False, **k
     return out
 
 
-def bnb_knapsack(profit, weight, capacity, trace=False, spec_nodes=0, spec_depth=0):
+def bnb_knapsack(profit, weight, capacity, trace=False, spec_nodes=0, spec_depth=0, sequential=False):
     p = np.ascontiguousarray(profit, dtype=np.float64)
     w = np.ascontiguousarray(weight, dtype=np.float64)
     n = p.shape[0]
-    opt = F.make_options(spec_nodes=spec_nodes, spec_depth=spec_depth)
+    # sequential=True forces the ordered-summation kernel path even for exactly summable integer data
+    opt = F.make_options(spec_nodes=spec_nodes, spec_depth=spec_depth,
+                         kernel=F.KERNEL_CTA_GLOBAL if sequential else F.KERNEL_AUTO)
     found = C.c_int()
     best = C.c_double()
     bx = np.zeros(n, dtype=np.int32)

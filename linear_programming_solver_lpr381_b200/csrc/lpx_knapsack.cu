@@ -56,6 +56,7 @@ struct KnParams {
     const double* p_o;   // [inst][n]
     const double* cap;   // [inst]
     const double* best;  // [inst] incumbent when the round was planned
+    const int* exact;    // [inst] 1: all weights/profits are integers with exact sums (order-free adds)
     int n;
     signed char* chunks[KN_MAX_CHUNKS];
     const KnIn* in;
@@ -110,8 +111,6 @@ __global__ void __launch_bounds__(256) knap_eval_kernel(const KnParams P) {
         dst[i] = a;
     }
     __syncwarp();
-    if (lane != 0) return;
-
     const double* w_o = P.w_o + (size_t)in.inst * n;
     const double* p_o = P.p_o + (size_t)in.inst * n;
     const double* w_s = P.w_s + (size_t)in.inst * n;
@@ -119,6 +118,81 @@ __global__ void __launch_bounds__(256) knap_eval_kernel(const KnParams P) {
     const int* orig_s = P.orig_s + (size_t)in.inst * n;
     const double capacity = P.cap[in.inst];
     const double limit = __dadd_rn(capacity, KN_EPS);
+
+    if (P.exact[in.inst]) {
+        // Integer data whose every partial sum is exactly representable: floating point addition
+        // is then exact and order-free, so the two sums can be formed by the whole warp (reduction
+        // and prefix scan) with results identical to the reference's sequential order.  Data that
+        // do not qualify take the sequential path below.
+        double w1 = 0.0, p1 = 0.0;
+        for (int i = lane; i < n; i += 32)
+            if (sa[i] == 1) {
+                w1 += w_o[i];
+                p1 += p_o[i];
+            }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            w1 += __shfl_xor_sync(0xffffffffu, w1, off);
+            p1 += __shfl_xor_sync(0xffffffffu, p1, off);
+        }
+        double weight = w1, profit = p1;
+        if (weight > limit) {
+            o.bound = profit;
+            o.weight = weight;
+            o.flags = KF_INFEASIBLE | KF_EARLY;
+            if (lane == 0) P.out[e] = o;
+            return;
+        }
+        int s_break = n;
+        for (int base = 0; base < n; base += 32) {
+            const int s = base + lane;
+            const bool und = s < n && sa[orig_s[s]] < 0;
+            const double wv = und ? w_s[s] : 0.0, pv = und ? p_s[s] : 0.0;
+            double cw = wv, cp = pv;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const double ow = __shfl_up_sync(0xffffffffu, cw, off);
+                const double op = __shfl_up_sync(0xffffffffu, cp, off);
+                if (lane >= off) {
+                    cw += ow;
+                    cp += op;
+                }
+            }
+            const bool fail = und && !((weight + cw) <= limit);
+            const unsigned mask = __ballot_sync(0xffffffffu, fail);
+            if (mask) {
+                const int first = __ffs(mask) - 1;
+                s_break = base + first;
+                weight = __shfl_sync(0xffffffffu, weight + (cw - wv), first);
+                profit = __shfl_sync(0xffffffffu, profit + (cp - pv), first);
+                break;
+            }
+            weight += __shfl_sync(0xffffffffu, cw, 31);
+            profit += __shfl_sync(0xffffffffu, cp, 31);
+        }
+        if (lane != 0) return;
+        if (s_break < n) {
+            const double wi = w_s[s_break];
+            const double remain = __dsub_rn(capacity, weight);
+            if (remain > KN_EPS && wi > KN_EPS) {
+                const double frac = __ddiv_rn(remain, wi);
+                profit = __dadd_rn(profit, __dmul_rn(p_s[s_break], frac));
+                weight = __dadd_rn(weight, __dmul_rn(wi, frac));
+                o.frac_rank = s_break;
+                o.frac = frac;
+            }
+        }
+        o.break_rank = s_break;
+        o.bound = profit;
+        o.weight = weight;
+        bool allint = true;
+        if (o.frac_rank >= 0) allint = fabs(__dsub_rn(o.frac, rint(o.frac))) < KN_EPS;
+        if (allint) o.flags |= KF_ALLINT;
+        if (weight > limit) o.flags |= KF_INFEASIBLE;
+        P.out[e] = o;
+        return;
+    }
+    if (lane != 0) return;
 
     // 1) items fixed to 1, in original index order (:442-452)
     double weight = 0.0, profit = 0.0;
@@ -242,6 +316,7 @@ struct KnDriver {
     lpx_knap_pop_fn on_pop;
     void* user;
     int spec_nodes = 8, spec_depth = 3;
+    bool force_sequential = false;  // tests: take the ordered-summation path even for integer data
 
     std::vector<KInstance> inst;
     std::vector<EvalRec> recs;
@@ -251,7 +326,7 @@ struct KnDriver {
     signed char* chunks[KN_MAX_CHUNKS] = {};
     KnParams P{};
     double *d_ws, *d_ps, *d_wo, *d_po, *d_cap, *d_best;
-    int* d_orig;
+    int *d_orig, *d_exact;
 
     ~KnDriver() {
         for (int k = 0; k < n_chunks; k++) cudaFree(chunks[k]);
@@ -615,6 +690,23 @@ struct KnDriver {
             }
         }
         const size_t cn = (size_t)count * n;
+        // order-free summation is allowed only where it is provably exact: integer weights and
+        // profits whose absolute sums stay below 2^53
+        std::vector<int> h_exact(count);
+        for (int k = 0; k < count; k++) {
+            double aw = 0, ap = 0;
+            bool ok = true;
+            for (int i = 0; i < n && ok; i++) {
+                const double wv = weight[(size_t)k * n + i], pv = profit[(size_t)k * n + i];
+                ok = std::isfinite(wv) && std::isfinite(pv) && wv == std::nearbyint(wv) && pv == std::nearbyint(pv);
+                aw += std::fabs(wv);
+                ap += std::fabs(pv);
+            }
+            h_exact[k] = ok && aw < 4503599627370496.0 && ap < 4503599627370496.0 && !force_sequential;
+        }
+        d_exact = ws_dev_as<int>(WS_KN_EXACT, count);
+        if (!d_exact) return LPX_E_CUDA;
+        LPX_CUDA(cudaMemcpyAsync(d_exact, h_exact.data(), (size_t)count * 4, cudaMemcpyHostToDevice, rt().stream));
         d_ws = ws_dev_as<double>(WS_KN_ITEMS, cn * 4);
         d_orig = ws_dev_as<int>(WS_KN_ASSIGN, cn);
         d_cap = ws_dev_as<double>(WS_MISC1, count);
@@ -638,6 +730,7 @@ struct KnDriver {
         P.p_o = d_po;
         P.cap = d_cap;
         P.best = d_best;
+        P.exact = d_exact;
         P.n = n;
         LPX_CUDA(cudaFuncSetAttribute(knap_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * n)));
 
@@ -759,6 +852,7 @@ static int knapsack_entry(int count, int n, const double* profit, const double* 
     if (opt) d.opt = *opt;
     if (d.opt.knap_spec_nodes > 0) d.spec_nodes = d.opt.knap_spec_nodes;
     if (d.opt.knap_spec_depth > 0) d.spec_depth = d.opt.knap_spec_depth;
+    d.force_sequential = d.opt.kernel == LPX_KERNEL_CTA_GLOBAL;  // reuse of the kernel selector for tests
     d.on_pop = on_pop;
     d.user = user;
     rc = d.run();

@@ -143,12 +143,28 @@ def test_knapsack_random_any_speculation(lpx, orc, spec):
 
 
 @pytest.mark.parametrize("kind", ["uncorrelated", "weak", "fractional"])
-def test_knapsack_c5(lpx, orc, kind):
-    """BASELINE config 5: 2000 items."""
+@pytest.mark.parametrize("sequential", [False, True])
+def test_knapsack_c5(lpx, orc, kind, sequential):
+    """BASELINE config 5: 2000 items.  Integer data take the warp-parallel exact-sum path unless
+    `sequential` forces the ordered-summation path; both must reproduce the reference."""
     p, w, cap = workloads.knapsack_c5(kind=kind)
     want = orc.knapsack(p, w, cap)
-    got = lpx.bnb_knapsack(p, w, cap)
+    got = lpx.bnb_knapsack(p, w, cap, sequential=sequential)
     compare_knap(got, want, kind)
+
+
+def test_knapsack_integer_edge_values(lpx, orc):
+    """Zero and repeated weights, zero profits, capacity hit exactly: the exact-sum path."""
+    rng = np.random.default_rng(91)
+    for t in range(12):
+        n = int(rng.integers(4, 70))
+        w = rng.integers(0, 9, size=n).astype(float)
+        p = rng.integers(0, 12, size=n).astype(float)
+        cap = float(rng.integers(1, max(2, int(w.sum()))))
+        want = orc.knapsack(p, w, cap, eval_cap=1 << 20)
+        for seq in (False, True):
+            got = lpx.bnb_knapsack(p, w, cap, trace=True, sequential=seq)
+            compare_knap(got, want, f"case {t} sequential={seq}")
 
 
 def test_knapsack_c5_trace(lpx, orc):
