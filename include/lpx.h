@@ -59,8 +59,8 @@ typedef struct lpx_options {
     int max_iterations;   /* PrimalSimplex.MaxIterations = 10000 (R/Models/PrimalSimplex.cs:54) */
     int kernel;           /* LPX_KERNEL_*: force a kernel family (tests/benchmarks); 0 = auto */
     int threads;          /* CTA size override for the per-tableau kernels; 0 = auto */
-    int knap_spec_nodes;  /* knapsack B&B: heap nodes speculated per round (0 = default 8) */
-    int knap_spec_depth;  /* knapsack B&B: look-ahead depth under the front runner (0 = default 3) */
+    int knap_spec_nodes;  /* knapsack B&B: heap nodes speculated per round (0 = default 16) */
+    int knap_spec_depth;  /* knapsack B&B: look-ahead depth under the front runner (0 = default 4) */
     int stream_protocol;  /* streaming kernels: 0 auto (blocked look-ahead on a cluster), 1 single-CTA
                              select per pivot, 2 multi-CTA prep per pivot, 3 blocked with one-CTA look-ahead */
     int reg_variant;      /* register-resident kernel: 0/1 one CTA per SM, 2 two CTAs per SM (spills) */

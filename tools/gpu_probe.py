@@ -138,3 +138,20 @@ if __name__ == "__main__":
             print(json.dumps(dict(kblock=kb, pass_variant=pv, lookahead_us=us[0], pass_us=us[1], per_block_us=us[2],
                                   us_per_pivot=us[2] / kb)), flush=True)
             s.close()
+    if what == "knap":
+        import time
+        ps, ws, caps = zip(*[workloads.knapsack_c5(seed=13 + k) for k in range(16)])
+        p, w, cap = np.stack(ps), np.stack(ws), np.array(caps)
+        api.bnb_knapsack_batched(p[:1], w[:1], cap[:1])
+        for sn, sd in ((8, 3), (8, 5), (16, 4), (4, 6), (2, 8), (1, 10), (32, 2)):
+            l0 = F.lib().lpx_kernel_launches()
+            t0 = time.perf_counter()
+            try:
+                r = api.bnb_knapsack_batched(p, w, cap, spec_nodes=sn, spec_depth=sd)
+            except Exception as ex:
+                print(json.dumps(dict(spec_nodes=sn, spec_depth=sd, error=str(ex))), flush=True)
+                continue
+            dt = time.perf_counter() - t0
+            print(json.dumps(dict(spec_nodes=sn, spec_depth=sd, nodes=int(r["n_evals"].sum()), seconds=dt,
+                                  nodes_s=int(r["n_evals"].sum()) / dt, launches=F.lib().lpx_kernel_launches() - l0)),
+                  flush=True)
