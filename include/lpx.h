@@ -65,7 +65,8 @@ typedef struct lpx_options {
                              select per pivot, 2 multi-CTA prep per pivot, 3 blocked with one-CTA look-ahead */
     int reg_variant;      /* register-resident kernel: 0/1 one CTA per SM, 2 two CTAs per SM (spills) */
     int stream_block;     /* streaming kernels: pivots applied per HBM pass (0 = default, max 16) */
-    int stream_pass_variant; /* blocked pass: 0 auto, 1 two doubles per thread, 2 one double per thread */
+    int stream_pass_variant; /* blocked pass: 0 auto, 1 two doubles per thread, 2 one double per thread,
+                                3 TMA-staged (cp.async.bulk + mbarrier pipeline) */
     int reserved[7];
 } lpx_options;
 

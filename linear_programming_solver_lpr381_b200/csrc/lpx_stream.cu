@@ -538,20 +538,23 @@ static void launch_lookahead(lpx_session* s, int budget) {
         stream_lookahead_kernel<<<1, 1024, lookahead_smem(s->P), s->stream>>>(s->P, budget);
 }
 
-// pass variants: <KMAX, doubles per thread, rows in flight>
+// pass variants: LDG/STG kernels <KMAX, doubles per thread, rows in flight> or the TMA-staged kernel
 typedef void (*BlockPassFn)(StreamParams, int);
+static bool block_pass_is_tma(const lpx_session* s) { return s->opt.stream_pass_variant == 3; }
 static BlockPassFn block_pass_fn(const lpx_session* s) {
-    const int variant = s->opt.stream_pass_variant;  // 0 auto; 1: VEC 2 (128-bit accesses); 2: VEC 1
+    const int variant = s->opt.stream_pass_variant;  // 0 auto; 1: two doubles/thread; 2: one; 3: TMA-staged
+    if (variant == 3) return s->P.kblock <= 8 ? stream_update_block_tma_kernel<8> : stream_update_block_tma_kernel<16>;
     if (s->P.kblock <= 8) return variant == 2 ? stream_update_block_kernel<8, 1, 4> : stream_update_block_kernel<8, 2, 4>;
-    return variant == 1 ? stream_update_block_kernel<16, 2, 2> : stream_update_block_kernel<16, 1, 4>;
+    return variant == 2 ? stream_update_block_kernel<16, 1, 4> : stream_update_block_kernel<16, 2, 2>;
 }
 static int block_pass_vec(const lpx_session* s) {
     const int variant = s->opt.stream_pass_variant;
-    if (s->P.kblock <= 8) return variant == 2 ? 1 : 2;
-    return variant == 1 ? 2 : 1;
+    return variant == 2 ? 1 : 2;
 }
 static size_t block_pass_smem(const lpx_session* s) {
     const int kmax = s->P.kblock <= 8 ? 8 : 16;
+    if (block_pass_is_tma(s))
+        return (size_t)LPX_TMA_STAGES * (s->P.kblock <= 8 ? sizeof(TmaTile<8>) : sizeof(TmaTile<16>)) + 128;
     return (size_t)kmax * s->rpc_block * 8 + (size_t)((s->rpc_block + 15) & ~15);
 }
 static void launch_block_pass(lpx_session* s) {
@@ -688,7 +691,21 @@ static lpx_session* session_create(int m, int n, int sense, const double* dA, co
     int chunks = (sm_count() * occ) / strips;
     chunks = std::max(1, std::min(chunks, P.rows));
     s->grid_update = dim3(strips, chunks, 1);
-    if (P.kblock > 0) {
+    if (P.kblock > 0 && block_pass_is_tma(s)) {
+        // TMA-staged pass: strips of 256 columns, row chunks (multiples of 8 rows) sized to one wave
+        const size_t smem = block_pass_smem(s);
+        cudaFuncSetAttribute(block_pass_fn(s), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int got = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&got, block_pass_fn(s), 256, smem);
+        if (got < 1) got = 1;
+        const int bstrips = (P.ld + LPX_TMA_COLS - 1) / LPX_TMA_COLS;
+        int ch = std::max(1, (sm_count() * got) / bstrips);
+        int rpc = (P.rows + ch - 1) / ch;
+        rpc = (rpc + 7) & ~7;
+        s->rpc_block = rpc;
+        s->grid_block = dim3(bstrips, (P.rows + rpc - 1) / rpc, 1);
+        cudaGetLastError();
+    } else if (P.kblock > 0) {
         // blocked pass: column strips x row chunks sized to one resident wave; the factor slices of a
         // chunk must fit in shared memory next to the other resident CTAs
         const int vec = block_pass_vec(s);
@@ -714,7 +731,6 @@ static lpx_session* session_create(int m, int n, int sense, const double* dA, co
         s->grid_block = dim3(bstrips, (P.rows + best_rpc - 1) / best_rpc, 1);
     }
     return s;
-
 }
 
 int stream_solve_host(int m, int n, int sense, const double* A, const int* rel, const double* b, const double* c,

@@ -641,4 +641,156 @@ __global__ void __launch_bounds__(256) stream_update_block_kernel(StreamParams P
     }
 }
 
+// ---- TMA-staged variant of the blocked pass -----------------------------------------------------
+// Same arithmetic, different data movement: row segments are brought into shared memory by the
+// bulk-copy engine (cp.async.bulk, completion on an mbarrier), updated in place by the compute
+// threads, and written back with cp.async.bulk shared->global.  Loads in flight no longer depend on
+// registers or resident warps (4 stages x 16 KB per CTA), the factor entries of a tile arrive with it
+// (K copies of 64 B), and the compute threads only issue LDS / DMUL / DSUB / STS.
+//   tile  = 8 rows x 256 columns (2 KB per row segment) + f[K][8]
+//   CTA   = 256 threads: thread t owns the column pair t % 128 of rows 4*(t / 128) .. +3 of a tile
+//   grid  = (column strips of 256, row chunks) sized to one resident wave
+#define LPX_TMA_ROWS 8
+#define LPX_TMA_COLS 256
+#define LPX_TMA_STAGES 4
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+template <int KMAX>
+struct TmaTile {
+    double t[LPX_TMA_ROWS][LPX_TMA_COLS];  // 16 KB
+    double f[KMAX][LPX_TMA_ROWS];          // factor entries of the tile's rows
+};
+
+template <int KMAX>
+__global__ void __launch_bounds__(256) stream_update_block_tma_kernel(StreamParams P, int rpc) {
+    extern __shared__ __align__(128) unsigned char smem_tma[];
+    __shared__ __align__(8) unsigned long long full[LPX_TMA_STAGES];
+    __shared__ int sL[KMAX];
+    constexpr int TR = LPX_TMA_ROWS, TC = LPX_TMA_COLS, ST = LPX_TMA_STAGES;
+    typedef TmaTile<KMAX> Tile;
+    Tile* tiles = reinterpret_cast<Tile*>(smem_tma);
+    const int cnt = P.ctl->block_cnt;
+    if (cnt <= 0) return;
+    const int tid = threadIdx.x;
+    const int r0 = blockIdx.y * rpc;
+    const int r1 = min(P.rows, r0 + rpc);
+    const int jbase = blockIdx.x * TC;
+    if (r1 <= r0 || jbase >= P.ld) return;
+    const int seg = min(TC, P.ld - jbase);            // columns of this strip (multiple of 16)
+    const unsigned seg_bytes = (unsigned)seg * 8;
+    const int n_tiles = (r1 - r0 + TR - 1) / TR;
+    const size_t ld = (size_t)P.ld, cs = (size_t)P.colstride;
+
+    if (tid < KMAX) sL[tid] = tid < cnt ? P.Lbuf[tid] : -1;
+    if (tid == 0) {
+        for (int s = 0; s < ST; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // producer side (thread 0): one tile = its row segments + K slices of the factor columns
+    auto issue_load = [&](int k) {
+        Tile& tl = tiles[k % ST];
+        const int rr = r0 + k * TR;
+        const int nr = min(TR, r1 - rr);
+        // factor slices: 8 doubles per pivot; the vectors are padded so reading past `rows` is safe
+        mbar_expect_tx(&full[k % ST], (unsigned)nr * seg_bytes + (unsigned)cnt * TR * 8);
+        for (int i = 0; i < nr; i++) bulk_g2s(&tl.t[i][0], P.T + (size_t)(rr + i) * ld + jbase, seg_bytes, &full[k % ST]);
+        for (int s = 0; s < cnt; s++) bulk_g2s(&tl.f[s][0], P.Fbuf + (size_t)s * cs + rr, TR * 8, &full[k % ST]);
+    };
+    if (tid == 0)
+        for (int k = 0; k < ST - 1 && k < n_tiles; k++) issue_load(k);
+
+    // this thread's columns and pivot-row entries
+    const int cp2 = (tid & 127) * 2;       // column pair inside the strip
+    const int rsub = (tid >> 7) * 4;       // first of its 4 rows inside a tile
+    const bool col_ok = cp2 < seg;
+    double p[KMAX][2];
+#pragma unroll
+    for (int s = 0; s < KMAX; s++) {
+        p[s][0] = (s < cnt && col_ok) ? P.Pbuf[(size_t)s * ld + jbase + cp2] : 0.0;
+        p[s][1] = (s < cnt && col_ok) ? P.Pbuf[(size_t)s * ld + jbase + cp2 + 1] : 0.0;
+    }
+
+    for (int k = 0; k < n_tiles; k++) {
+        Tile& tl = tiles[k % ST];
+        mbar_wait(&full[k % ST], (unsigned)((k / ST) & 1));
+        const int rr = r0 + k * TR;
+        const int nr = min(TR, r1 - rr);
+        bool has_pivot_row = false;
+#pragma unroll
+        for (int s = 0; s < KMAX; s++) has_pivot_row = has_pivot_row || (sL[s] >= rr && sL[s] < rr + nr);
+        if (col_ok) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int i = rsub + q;
+                if (i < nr) {
+                    double2 v = *reinterpret_cast<double2*>(&tl.t[i][cp2]);
+                    if (!has_pivot_row) {
+#pragma unroll
+                        for (int s = 0; s < KMAX; s++) {
+                            if (s < cnt) {
+                                const double f = tl.f[s][i];
+                                v.x = __dsub_rn(v.x, __dmul_rn(f, p[s][0]));
+                                v.y = __dsub_rn(v.y, __dmul_rn(f, p[s][1]));
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < KMAX; s++) {
+                            if (s < cnt) {
+                                const double f = tl.f[s][i];
+                                const bool is_l = (rr + i) == sL[s];
+                                v.x = is_l ? p[s][0] : __dsub_rn(v.x, __dmul_rn(f, p[s][0]));
+                                v.y = is_l ? p[s][1] : __dsub_rn(v.y, __dmul_rn(f, p[s][1]));
+                            }
+                        }
+                    }
+                    *reinterpret_cast<double2*>(&tl.t[i][cp2]) = v;
+                }
+            }
+        }
+        // make the generic-proxy writes visible to the bulk-copy engine, then write the tile back
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            for (int i = 0; i < nr; i++) bulk_s2g(P.T + (size_t)(rr + i) * ld + jbase, &tl.t[i][0], seg_bytes);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            // the stage of tile k-1 may be refilled once its write-back has finished reading shared memory
+            const int nxt = k + ST - 1;
+            if (nxt < n_tiles) {
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                issue_load(nxt);
+            }
+        }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 }  // namespace lpx

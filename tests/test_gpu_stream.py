@@ -124,3 +124,35 @@ def test_c3_full_size_first_pivots(lpx, orc):
         unit[i] = 1.0
         assert np.array_equal(np.abs(col), unit)
     s.close()
+
+
+@pytest.mark.parametrize("kblock", [0, 3, 16])
+def test_tma_staged_pass(lpx, orc, kblock):
+    """pass_variant 3: the blocked HBM pass staged through shared memory by cp.async.bulk."""
+    for (m, n, seed) in [(256, 512, 7), (100, 37, 3), (9, 700, 5)]:
+        A, b, c = workloads.lp_integer(m, n, seed)
+        want = orc.primal_solve(A, b, c)
+        s = lpx.Session(A, b, c, kblock=kblock, pass_variant=3)
+        st, tot = F.RUNNING, 0
+        while st == F.RUNNING:
+            st, tot = s.step(50)
+        assert st == want["status"] and tot == want["n_pivots"], (m, n)
+        assert s.pivots(tot)[:tot].tolist() == want["pivots"].tolist()
+        assert_bits_equal(s.tableau(), want["tableau"], f"tableau {m}x{n}")
+        s.close()
+    rng = np.random.default_rng(5)
+    for t in range(6):
+        m, n = int(rng.integers(3, 12)), int(rng.integers(3, 14))
+        A = rng.integers(-2, 7, size=(m, n)).astype(float)
+        b = rng.integers(0, 12, size=m).astype(float)
+        c = rng.integers(-2, 9, size=n).astype(float)
+        rel = rng.choice([0, 0, 0, 2], size=m).astype(np.int32)
+        want = orc.primal_solve(A, b, c, rel, 0, max_iterations=60)
+        s = lpx.Session(A, b, c, rel=rel, max_iterations=60, kblock=kblock, pass_variant=3)
+        st, tot = F.RUNNING, 0
+        while st == F.RUNNING:
+            st, tot = s.step(7)
+        assert st == want["status"] and tot == want["n_pivots"], t
+        if st >= 0:
+            assert_bits_equal(s.tableau(), want["tableau"], f"tableau {t}")
+        s.close()
