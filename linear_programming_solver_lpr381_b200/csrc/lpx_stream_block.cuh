@@ -423,26 +423,34 @@ __global__ void __cluster_dims__(LPX_LA_CLUSTER, 1, 1) __launch_bounds__(LPX_LA_
         // ---- column e, rows of this CTA: gather, bring up to date, all-gather -------------------
         if (tid < cnt) s_pe[tid] = P.Pbuf[(size_t)tid * ld + e];
         __syncthreads();
+        // All factor entries a thread needs are loaded BEFORE the dependent multiply/subtract chain:
+        // with the load inside the chain each decided pivot cost one L2 round trip (~0.7 us).
         for (int base = i_lo; base < i_hi; base += 2 * TH) {
             double c[2];
+            double f[2][LPX_BLOCK_KMAX];
 #pragma unroll
             for (int u = 0; u < 2; u++) {
                 const int i = base + u * TH + tid;
                 c[u] = i < i_hi ? P.T[(size_t)i * ld + e] : 0.0;
             }
-            for (int s = 0; s < cnt; s++) {
-                const double ps = s_pe[s];
-                const int ls = s_L[s];
-                double f[2];
+#pragma unroll
+            for (int s = 0; s < LPX_BLOCK_KMAX; s++) {
 #pragma unroll
                 for (int u = 0; u < 2; u++) {
                     const int i = base + u * TH + tid;
-                    f[u] = i < i_hi ? P.Fbuf[(size_t)s * cs + i] : 0.0;
+                    f[u][s] = (s < cnt && i < i_hi) ? P.Fbuf[(size_t)s * cs + i] : 0.0;
                 }
+            }
 #pragma unroll
-                for (int u = 0; u < 2; u++) {
-                    const int i = base + u * TH + tid;
-                    c[u] = (i == ls) ? ps : __dsub_rn(c[u], __dmul_rn(f[u], ps));
+            for (int s = 0; s < LPX_BLOCK_KMAX; s++) {
+                if (s < cnt) {
+                    const double ps = s_pe[s];
+                    const int ls = s_L[s];
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const int i = base + u * TH + tid;
+                        c[u] = (i == ls) ? ps : __dsub_rn(c[u], __dmul_rn(f[u][s], ps));
+                    }
                 }
             }
 #pragma unroll
@@ -479,30 +487,36 @@ __global__ void __cluster_dims__(LPX_LA_CLUSTER, 1, 1) __launch_bounds__(LPX_LA_
         __syncthreads();
         double* pout = P.Pbuf + (size_t)cnt * ld;
         const double* Tl = P.T + (size_t)l * ld;
-        for (int base = j_lo; base < j_hi; base += 4 * TH) {
-            double r4[4];
+        for (int base = j_lo; base < j_hi; base += 2 * TH) {
+            double r2[2];
+            double pp[2][LPX_BLOCK_KMAX];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < 2; u++) {
                 const int j = base + u * TH + tid;
-                r4[u] = j < j_hi ? Tl[j] : 0.0;
+                r2[u] = j < j_hi ? Tl[j] : 0.0;
             }
-            for (int s = 0; s < cnt; s++) {
-                const double fs = s_fl[s];
-                const bool same = l == s_L[s];
-                double ps[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+            for (int s = 0; s < LPX_BLOCK_KMAX; s++) {
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
                     const int j = base + u * TH + tid;
-                    ps[u] = j < j_hi ? P.Pbuf[(size_t)s * ld + j] : 0.0;
+                    pp[u][s] = (s < cnt && j < j_hi) ? P.Pbuf[(size_t)s * ld + j] : 0.0;
                 }
-#pragma unroll
-                for (int u = 0; u < 4; u++) r4[u] = same ? ps[u] : __dsub_rn(r4[u], __dmul_rn(fs, ps[u]));
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int s = 0; s < LPX_BLOCK_KMAX; s++) {
+                if (s < cnt) {
+                    const double fs = s_fl[s];
+                    const bool same = l == s_L[s];
+#pragma unroll
+                    for (int u = 0; u < 2; u++) r2[u] = same ? pp[u][s] : __dsub_rn(r2[u], __dmul_rn(fs, pp[u][s]));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
                 const int j = base + u * TH + tid;
                 if (j < j_hi) {
-                    const double pj = __ddiv_rn(r4[u], piv);
+                    const double pj = __ddiv_rn(r2[u], piv);
                     pout[j] = pj;
                     if (j < width - 1) zloc[j - j_lo] = __dsub_rn(zloc[j - j_lo], __dmul_rn(fz, pj));
                 }

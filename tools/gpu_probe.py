@@ -129,7 +129,7 @@ if __name__ == "__main__":
     if what == "blockprof":
         import ctypes as C
         A, b, c = workloads.large_c3()
-        for kb, pv in ((8, 1), (8, 3), (16, 1), (16, 3)):
+        for kb, pv in ((8, 0), (12, 0), (16, 0), (16, 1)):
             s = api.Session(A, b, c, max_iterations=1 << 30, kblock=kb, pass_variant=pv)
             s.step(32)
             us = (C.c_double * 3)()
