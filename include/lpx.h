@@ -61,8 +61,9 @@ typedef struct lpx_options {
     int threads;          /* CTA size override for the per-tableau kernels; 0 = auto */
     int knap_spec_nodes;  /* knapsack B&B: heap nodes speculated per round (0 = default 16) */
     int knap_spec_depth;  /* knapsack B&B: look-ahead depth under the front runner (0 = default 4) */
-    int stream_protocol;  /* streaming kernels: 0 auto (blocked look-ahead on a cluster), 1 single-CTA
-                             select per pivot, 2 multi-CTA prep per pivot, 3 blocked with one-CTA look-ahead */
+    int stream_protocol;  /* streaming kernels: 0 auto (pipelined blocked look-ahead: the look-ahead of block
+                             B+1 overlaps the HBM pass of block B), 1 single-CTA select per pivot, 2 multi-CTA
+                             prep per pivot, 3 blocked with a one-CTA look-ahead, 4 blocked, not pipelined */
     int reg_variant;      /* register-resident kernel: 0/1 one CTA per SM, 2 two CTAs per SM (spills) */
     int stream_block;     /* streaming kernels: pivots applied per HBM pass (0 = default, max 16) */
     int stream_pass_variant; /* blocked pass: 0 auto, 1 two doubles per thread, 2 one double per thread,

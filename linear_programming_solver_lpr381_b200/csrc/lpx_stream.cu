@@ -31,6 +31,8 @@ struct StreamCtl {
     int capture;  // entering column of the pivot after this one (-1: none)
     int k;        // index of the pivot being applied
     int block_cnt;  // blocked protocol: pivots decided by the last look-ahead, applied by the next pass
+    int blk_in[2];   // pipelined protocol, per block parity: tableau buffer the block's pass reads
+    int blk_cnt[2];  // pipelined protocol, per block parity: pivots decided for the block
 };
 
 struct StreamParams {
@@ -54,6 +56,8 @@ struct StreamParams {
     int* Lbuf;     // kblock leaving rows
     int kblock;    // 0: per-pivot protocol
     unsigned long long* dbg;  // optional phase timestamps (development aid)
+    double* T1;    // second tableau buffer (pipelined protocol: passes are out of place)
+    double* zbuf;  // ld: z-row after every decided pivot, handed from look-ahead to look-ahead
 };
 
 #define LPX_PREP_THREADS 1024
@@ -103,6 +107,8 @@ __global__ void __launch_bounds__(1024) stream_validate_kernel(StreamCtl* ctl, c
         ctl->capture = -1;
         ctl->k = 0;
         ctl->block_cnt = 0;
+        ctl->blk_in[0] = ctl->blk_in[1] = 0;
+        ctl->blk_cnt[0] = ctl->blk_cnt[1] = 0;
     }
 }
 
@@ -152,6 +158,9 @@ __global__ void __launch_bounds__(1024) stream_first_kernel(StreamParams P) {
 __global__ void __launch_bounds__(256) stream_gather_kernel(StreamParams P) {
     if (P.ctl->status != LPX_RUNNING) return;
     const int e = P.ctl->enter;
+    if (P.zbuf)
+        for (int j = blockIdx.x * 256 + threadIdx.x; j < P.ld; j += gridDim.x * 256)
+            P.zbuf[j] = P.T[(size_t)P.m * P.ld + j];
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= P.rows) return;
     const double* Ti = P.T + (size_t)i * P.ld;
@@ -465,6 +474,7 @@ __global__ void __launch_bounds__(256, 4) stream_update_kernel(StreamParams P) {
 }  // namespace lpx
 
 #include "lpx_stream_block.cuh"
+#include "lpx_stream_pipe.cuh"
 
 
 // ---- session object -----------------------------------------------------------------------------
@@ -483,6 +493,13 @@ struct lpx_session {
     dim3 grid_block;
     bool la_cluster = false;  // look-ahead on a thread-block cluster (else one CTA)
     int rpc_block = 0;        // rows per CTA of the blocked pass
+    // pipelined protocol: look-ahead of block B+1 overlaps the pass of block B
+    bool pipe = false;
+    cudaStream_t streamL = nullptr;
+    cudaEvent_t evL[2] = {nullptr, nullptr}, evP[2] = {nullptr, nullptr}, evStart = nullptr;
+    long long blocks = 0;  // blocks launched so far (parity selects the buffer halves)
+    dim3 grid_pipe;
+    int rpc_pipe = 0;
     int device = 0;
 };
 
@@ -503,6 +520,15 @@ static void sess_free(lpx_session* s) {
     if (!s) return;
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (int i = 0; i < s->nbuf; i++) cudaFree(s->buffers[i]);
+    if (s->streamL) {
+        cudaStreamSynchronize(s->streamL);
+        cudaStreamDestroy(s->streamL);
+    }
+    for (int k = 0; k < 2; k++) {
+        if (s->evL[k]) cudaEventDestroy(s->evL[k]);
+        if (s->evP[k]) cudaEventDestroy(s->evP[k]);
+    }
+    if (s->evStart) cudaEventDestroy(s->evStart);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -563,6 +589,46 @@ static size_t block_pass_smem(const lpx_session* s) {
 }
 static void launch_block_pass(lpx_session* s) {
     block_pass_fn(s)<<<s->grid_block, 256, block_pass_smem(s), s->stream>>>(s->P, s->rpc_block);
+}
+
+static size_t pipe_pass_smem() { return (size_t)LPX_TMA_STAGES * sizeof(TmaTile<LPX_PIPE_K>) + 128; }
+
+// One block of the pipelined protocol.  Dependencies (B = block index):
+//   look-ahead(B) after look-ahead(B-1) and pass(B-2)   [it overwrites the buffer halves of block B-2]
+//   pass(B)       after look-ahead(B)   and pass(B-1)   [it reads what pass(B-1) wrote]
+// so look-ahead(B+1) runs while pass(B) streams the tableau.  serialize = both on the main stream.
+static int launch_pipe_block(lpx_session* s, int budget, bool serialize) {
+    const int par = (int)(s->blocks & 1);
+    cudaStream_t sl = serialize ? s->stream : s->streamL;
+    LPX_CUDA(cudaStreamWaitEvent(sl, s->evL[par ^ 1], 0));
+    LPX_CUDA(cudaStreamWaitEvent(sl, s->evP[par], 0));
+    stream_lookahead_pipe_kernel<<<LPX_LA_CLUSTER, LPX_LA_THREADS, lookahead_cluster_smem(s->P), sl>>>(s->P, budget, par, 1);
+    LPX_CUDA(cudaEventRecord(s->evL[par], sl));
+    LPX_CUDA(cudaStreamWaitEvent(s->stream, s->evL[par], 0));
+    LPX_CUDA(cudaStreamWaitEvent(s->stream, s->evP[par ^ 1], 0));
+    stream_update_pipe_tma_kernel<LPX_PIPE_K><<<s->grid_pipe, 256, pipe_pass_smem(), s->stream>>>(s->P, s->rpc_pipe, par);
+    LPX_CUDA(cudaEventRecord(s->evP[par], s->stream));
+    LPX_CUDA(cudaGetLastError());
+    count_launch(2);
+    s->blocks++;
+    return LPX_OK;
+}
+
+// Resolve the status of the tableau as it stands (all passes applied), no pivot.
+static int launch_pipe_probe(lpx_session* s) {
+    const int par = (int)(s->blocks & 1);
+    LPX_CUDA(cudaStreamWaitEvent(s->stream, s->evL[par ^ 1], 0));
+    stream_lookahead_pipe_kernel<<<LPX_LA_CLUSTER, LPX_LA_THREADS, lookahead_cluster_smem(s->P), s->stream>>>(s->P, 0, par, 0);
+    LPX_CUDA(cudaGetLastError());
+    count_launch();
+    return LPX_OK;
+}
+
+// tableau buffer that holds the current tableau once every launched pass has finished
+static int pipe_current_buffer(lpx_session* s, const StreamCtl& h) {
+    if (!s->pipe || s->blocks == 0) return 0;
+    const int q = (int)((s->blocks - 1) & 1);
+    return h.blk_in[q] ^ (h.blk_cnt[q] > 0 ? 1 : 0);
 }
 
 static int launch_block(lpx_session* s, int budget) {
@@ -636,10 +702,10 @@ static lpx_session* session_create(int m, int n, int sense, const double* dA, co
     // stream_protocol: 0 auto, 1 single-CTA select per pivot, 2 multi-CTA prep per pivot.  stream_block: pivots per pass.
     P.kblock = 0;
     // stream_protocol == 3 forces the single-CTA look-ahead (tests); otherwise the cluster version is preferred.
-    const bool blocked_wanted = s->opt.stream_protocol == 0 || s->opt.stream_protocol == 3;
+    const bool blocked_wanted = s->opt.stream_protocol == 0 || s->opt.stream_protocol == 3 || s->opt.stream_protocol == 4;
     if (blocked_wanted) {
         const int kb = s->opt.stream_block > 0 ? std::min(s->opt.stream_block, LPX_BLOCK_KMAX) : 8;
-        if (s->opt.stream_protocol == 0 && lookahead_cluster_smem(P) + 24 * 1024 <= (size_t)max_smem_optin() &&
+        if (s->opt.stream_protocol != 3 && lookahead_cluster_smem(P) + 24 * 1024 <= (size_t)max_smem_optin() &&
             cudaFuncSetAttribute(stream_lookahead_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)lookahead_cluster_smem(P)) == cudaSuccess) {
             P.kblock = kb;
@@ -652,10 +718,32 @@ static lpx_session* session_create(int m, int n, int sense, const double* dA, co
         cudaGetLastError();
     }
     if (s->opt.stream_protocol == 1) P.npartial = 0;
+    // stream_protocol 0: pipelined when the cluster look-ahead is available and the block size allows it
+    // (<= 8 pivots per block); 4 forces the non-pipelined blocked protocol.
+    const bool want_pipe = s->opt.stream_protocol == 0 && s->la_cluster && P.kblock > 0 && P.kblock <= LPX_PIPE_K;
     P.Fbuf = (double*)sess_alloc(s, (size_t)LPX_BLOCK_KMAX * P.colstride * 8);
     P.Pbuf = (double*)sess_alloc(s, (size_t)LPX_BLOCK_KMAX * P.ld * 8);
     P.Lbuf = (int*)sess_alloc(s, (size_t)LPX_BLOCK_KMAX * 4);
     P.dbg = (unsigned long long*)sess_alloc(s, 16 * 8);
+    P.T1 = nullptr;
+    P.zbuf = nullptr;
+    if (want_pipe) {
+        P.T1 = (double*)sess_alloc(s, tbytes);
+        P.zbuf = (double*)sess_alloc(s, (size_t)P.ld * 8);
+        bool ok = P.T1 && P.zbuf &&
+                  cudaFuncSetAttribute(stream_lookahead_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)lookahead_cluster_smem(P)) == cudaSuccess &&
+                  cudaFuncSetAttribute(stream_update_pipe_tma_kernel<LPX_PIPE_K>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_pass_smem()) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&s->streamL, cudaStreamNonBlocking) == cudaSuccess;
+        for (int k = 0; k < 2 && ok; k++)
+            ok = cudaEventCreateWithFlags(&s->evL[k], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&s->evP[k], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&s->evStart, cudaEventDisableTiming) == cudaSuccess;
+        cudaGetLastError();
+        s->pipe = ok;
+        if (!ok) P.zbuf = nullptr;  // fall back to the non-pipelined blocked protocol
+    }
     if (P.npartial > 0 && prep_smem > 40 * 1024 &&
         cudaFuncSetAttribute(stream_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem) !=
             cudaSuccess)
@@ -695,6 +783,20 @@ static lpx_session* session_create(int m, int n, int sense, const double* dA, co
     int chunks = (sm_count() * occ) / strips;
     chunks = std::max(1, std::min(chunks, P.rows));
     s->grid_update = dim3(strips, chunks, 1);
+    if (s->pipe) {
+        int got = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&got, stream_update_pipe_tma_kernel<LPX_PIPE_K>, 256, pipe_pass_smem());
+        if (got < 1) got = 1;
+        // the look-ahead cluster of the next block occupies LPX_LA_CLUSTER SMs while the pass runs
+        const int sms = sm_count() > 4 * LPX_LA_CLUSTER ? sm_count() - LPX_LA_CLUSTER : sm_count();
+        const int bstrips = (P.ld + LPX_TMA_COLS - 1) / LPX_TMA_COLS;
+        const int ch = std::max(1, (sms * got) / bstrips);
+        int rpc = (P.rows + ch - 1) / ch;
+        rpc = (rpc + 7) & ~7;
+        s->rpc_pipe = rpc;
+        s->grid_pipe = dim3(bstrips, (P.rows + rpc - 1) / rpc, 1);
+        cudaGetLastError();
+    }
     if (P.kblock > 0 && block_pass_is_tma(s)) {
         // TMA-staged pass: strips of 256 columns, row chunks (multiples of 8 rows) sized to one wave
         const size_t smem = block_pass_smem(s);
@@ -803,6 +905,16 @@ int lpx_session_step_async(lpx_session* s, int max_pivots) {
         set_error("lpx_session_step_async: bad arguments");
         return LPX_E_BAD_ARGS;
     }
+    if (s->pipe) {
+        // the look-ahead stream starts after whatever the caller has queued on the main stream
+        LPX_CUDA(cudaEventRecord(s->evStart, s->stream));
+        LPX_CUDA(cudaStreamWaitEvent(s->streamL, s->evStart, 0));
+        for (int left = max_pivots; left > 0; left -= s->P.kblock) {
+            int rc = launch_pipe_block(s, std::min(left, s->P.kblock), false);
+            if (rc != LPX_OK) return rc;
+        }
+        return LPX_OK;
+    }
     if (s->P.kblock > 0) {
         for (int left = max_pivots; left > 0; left -= s->P.kblock) {
             int rc = launch_block(s, std::min(left, s->P.kblock));
@@ -825,6 +937,19 @@ int lpx_session_profile(lpx_session* s, int n, double* us) {
     for (auto& e : ev) LPX_CUDA(cudaEventCreate(&e));
     for (int k = 0; k < n; k++) {
         LPX_CUDA(cudaEventRecord(ev[3 * k], s->stream));
+        if (s->pipe) {
+            const int par = (int)(s->blocks & 1);
+            LPX_CUDA(cudaStreamWaitEvent(s->stream, s->evL[par ^ 1], 0));
+            stream_lookahead_pipe_kernel<<<LPX_LA_CLUSTER, LPX_LA_THREADS, lookahead_cluster_smem(s->P), s->stream>>>(
+                s->P, s->P.kblock, par, 1);
+            LPX_CUDA(cudaEventRecord(s->evL[par], s->stream));
+            LPX_CUDA(cudaEventRecord(ev[3 * k + 1], s->stream));
+            stream_update_pipe_tma_kernel<LPX_PIPE_K><<<s->grid_pipe, 256, pipe_pass_smem(), s->stream>>>(s->P, s->rpc_pipe, par);
+            LPX_CUDA(cudaEventRecord(s->evP[par], s->stream));
+            LPX_CUDA(cudaEventRecord(ev[3 * k + 2], s->stream));
+            s->blocks++;
+            continue;
+        }
         if (s->P.kblock > 0) {
             launch_lookahead(s, s->P.kblock);
             LPX_CUDA(cudaEventRecord(ev[3 * k + 1], s->stream));
@@ -871,7 +996,7 @@ int lpx_session_sync(lpx_session* s, int* status, int* pivots_total) {
         return LPX_E_BAD_ARGS;
     }
     // probe: resolves OPTIMAL / UNBOUNDED / ITER_LIMIT for the tableau as it stands, no pivot
-    int rc = s->P.kblock > 0 ? launch_block(s, 0) : launch_pair(s, 1);
+    int rc = s->pipe ? launch_pipe_probe(s) : (s->P.kblock > 0 ? launch_block(s, 0) : launch_pair(s, 1));
     if (rc != LPX_OK) return rc;
     StreamCtl h;
     LPX_CUDA(cudaMemcpyAsync(&h, s->P.ctl, sizeof h, cudaMemcpyDeviceToHost, s->stream));
@@ -898,7 +1023,14 @@ int lpx_session_dims(const lpx_session* s, int* rows, int* cols) {
 
 int lpx_session_read_tableau(lpx_session* s, double* tableau) {
     if (!s || !tableau) return LPX_E_BAD_ARGS;
-    LPX_CUDA(cudaMemcpy2DAsync(tableau, (size_t)s->P.width * 8, s->P.T, (size_t)s->P.ld * 8, (size_t)s->P.width * 8,
+    const double* Tcur = s->P.T;
+    if (s->pipe) {
+        StreamCtl h;
+        LPX_CUDA(cudaMemcpyAsync(&h, s->P.ctl, sizeof h, cudaMemcpyDeviceToHost, s->stream));
+        LPX_CUDA(cudaStreamSynchronize(s->stream));
+        if (pipe_current_buffer(s, h)) Tcur = s->P.T1;
+    }
+    LPX_CUDA(cudaMemcpy2DAsync(tableau, (size_t)s->P.width * 8, Tcur, (size_t)s->P.ld * 8, (size_t)s->P.width * 8,
                                s->P.rows, cudaMemcpyDeviceToHost, s->stream));
     LPX_CUDA(cudaStreamSynchronize(s->stream));
     return LPX_OK;

@@ -384,6 +384,7 @@ __global__ void __cluster_dims__(LPX_LA_CLUSTER, 1, 1) __launch_bounds__(LPX_LA_
             st = LPX_S_ITER_LIMIT;
             break;
         }
+        if (P.dbg && rank == 0 && tid == 0 && cnt == 2) P.dbg[0] = lpx_gtime();
         // ---- ChooseEntering: slice argmin, exchanged through distributed shared memory -----------
         {
             ArgMin a;
@@ -412,6 +413,7 @@ __global__ void __cluster_dims__(LPX_LA_CLUSTER, 1, 1) __launch_bounds__(LPX_LA_
             }
         }
         cluster.sync();  // (1)
+        if (P.dbg && rank == 0 && tid == 0 && cnt == 2) P.dbg[1] = lpx_gtime();
         ArgMin g = s_part[0];
 #pragma unroll
         for (int r = 1; r < CL; r++) g = argmin_pick(g, s_part[r]);
@@ -463,6 +465,7 @@ __global__ void __cluster_dims__(LPX_LA_CLUSTER, 1, 1) __launch_bounds__(LPX_LA_
             }
         }
         cluster.sync();  // (2) every CTA holds the whole up-to-date column
+        if (P.dbg && rank == 0 && tid == 0 && cnt == 2) P.dbg[2] = lpx_gtime();
         for (int i = tid; i < Q * TH; i += TH) {
             // permuted slot (u, t) <-> row t*Q + u
             const int t = i % TH, u = i / TH;
@@ -476,6 +479,7 @@ __global__ void __cluster_dims__(LPX_LA_CLUSTER, 1, 1) __launch_bounds__(LPX_LA_
         }
         __syncthreads();
         const int l = la_leaving_scan(ratio, m, Q, s_wmin, s_wcnt, s_rec, &s_out, s_ired);
+        if (P.dbg && rank == 0 && tid == 0 && cnt == 2) P.dbg[3] = lpx_gtime();
         if (l < 0) {
             st = LPX_UNBOUNDED;
             break;
@@ -523,6 +527,7 @@ __global__ void __cluster_dims__(LPX_LA_CLUSTER, 1, 1) __launch_bounds__(LPX_LA_
             }
         }
         // ---- RHS (every CTA keeps the full vector), factor column slice, bookkeeping ------------
+        if (P.dbg && rank == 0 && tid == 0 && cnt == 2) P.dbg[4] = lpx_gtime();
         const double prhs = __ddiv_rn(rhs[l], piv);
         __syncthreads();
         double* fout = P.Fbuf + (size_t)cnt * cs;
@@ -545,6 +550,7 @@ __global__ void __cluster_dims__(LPX_LA_CLUSTER, 1, 1) __launch_bounds__(LPX_LA_
         cnt++;
         __threadfence();
         cluster.sync();  // (3) Pbuf / Fbuf slices of this pivot are visible to the whole cluster
+        if (P.dbg && rank == 0 && tid == 0 && cnt == 3) P.dbg[5] = lpx_gtime();
     }
     if (rank == 0) {
         for (int i = tid; i < rows; i += TH) P.rhsbuf[i] = rhs[i];

@@ -20,7 +20,7 @@ def build_tableau(A, b, c):
     return T
 
 
-PROTOCOLS = [(0, 0), (0, 1), (0, 3), (0, 16), (0, 11), (3, 0), (3, 5), (1, 0), (2, 0)]  # (protocol, pivots per HBM pass)
+PROTOCOLS = [(0, 0), (0, 1), (0, 3), (0, 5), (0, 16), (0, 11), (4, 0), (4, 3), (3, 0), (3, 5), (1, 0), (2, 0)]  # (protocol, pivots per HBM pass)
 
 
 @pytest.mark.parametrize("protocol,kblock", PROTOCOLS)

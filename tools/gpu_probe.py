@@ -91,8 +91,8 @@ if __name__ == "__main__":
             s.close()
     if what == "block":
         A, b, c = workloads.large_c3()
-        for kb in (1, 4, 8, 12, 16):
-            s = api.Session(A, b, c, max_iterations=1 << 30, kblock=kb)
+        for kb, proto in ((8, 0), (4, 0), (6, 0), (8, 4), (16, 4)):
+            s = api.Session(A, b, c, max_iterations=1 << 30, kblock=kb, single_cta_select=proto)
             ss = torch.cuda.ExternalStream(s.stream)
             s.step(32)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -102,7 +102,7 @@ if __name__ == "__main__":
             e1.record(ss)
             st, tot = s.sync()
             us = e0.elapsed_time(e1) * 1e3 / npv
-            print(json.dumps(dict(kblock=kb, us_per_pivot=us, pivots_s=1e6 / us, status=st, total=tot,
+            print(json.dumps(dict(kblock=kb, protocol=proto, us_per_pivot=us, pivots_s=1e6 / us, status=st, total=tot,
                                   x_roofline=805568528 / us / 1e3 / 6555.2)), flush=True)
             s.close()
     if what == "stamps":
@@ -116,8 +116,9 @@ if __name__ == "__main__":
             F.lib().lpx_session_debug_stamps.argtypes = [C.c_void_p, C.c_void_p]
             F.check(F.lib().lpx_session_debug_stamps(s._h, out))
             t = list(out)
-            print(json.dumps(dict(argmin=t[1] - t[0], column=t[2] - t[1], ratio_rounds=t[3] - t[2], rounds=t[7],
-                                  row=t[4] - t[3], rhs=t[5] - t[4], whole_block=t[6] - t[0])), flush=True)
+            print(t, flush=True)
+            print(json.dumps(dict(argmin_sync1=t[1] - t[0], column_sync2=t[2] - t[1], ratio_scan=t[3] - t[2],
+                                  row=t[4] - t[3], rhs_sync3=t[5] - t[4], step=t[5] - t[0])), flush=True)
         s.close()
     if what == "block8":
         A, b, c = workloads.large_c3()
