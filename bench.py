@@ -202,9 +202,9 @@ def run_ours(args):
         A, b, c = workloads.large_c3(**C3, seed=7 + rank)
         dA, db, dc = (torch.from_numpy(v).to(dev) for v in (A, b, c))
         torch.cuda.synchronize()
-        kblock = 8
+        kblock = 8  # the engine's default: 8 pivots per HBM pass, look-ahead pipelined with the pass
         s = api.Session(dA.data_ptr(), db.data_ptr(), dc.data_ptr(), device_ptrs=True, m=C3["m"], n=C3["n"],
-                        max_iterations=1 << 30, kblock=kblock)
+                        max_iterations=1 << 30)
         del dA
         rows, cols = s.rows, s.cols
         sstream = torch.cuda.ExternalStream(s.stream)
@@ -243,9 +243,11 @@ def run_ours(args):
                     pivots_per_step=per_step, clocks=clocks,
                     roofline={"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                               "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_kind,
-                              "kernel": "stream_update_block_kernel (one HBM pass applying a block of pivots)",
+                              "kernel": "stream_update_pipe_tma_kernel (one TMA-staged HBM pass applying a block of pivots; "
+                                        "timed alone, the look-ahead of the next block normally runs beside it)",
                               "algorithmic_bytes_per_launch": bytes_per_pass, "launch_us": pass_us,
                               "pivots_per_launch": kblock, "lookahead_us_per_block": lookahead_us,
+                              "block_us_overlapped": 1e3 * sum(ms) / (done / kblock),
                               "per_pivot_roofline": {
                                   "note": "SURVEY 8d counts one read + one write of the tableau PER PIVOT "
                                           "(805.6 MB, 8137 pivots/s at the measured HBM peak).  The blocked "

@@ -591,26 +591,57 @@ static void launch_block_pass(lpx_session* s) {
     block_pass_fn(s)<<<s->grid_block, 256, block_pass_smem(s), s->stream>>>(s->P, s->rpc_block);
 }
 
+static bool create_priority_stream(cudaStream_t* st) {
+    int lo = 0, hi = 0;
+    if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) hi = 0;
+    return cudaStreamCreateWithPriority(st, cudaStreamNonBlocking, hi) == cudaSuccess;  // hi = greatest priority
+}
+
 static size_t pipe_pass_smem() { return (size_t)LPX_TMA_STAGES * sizeof(TmaTile<LPX_PIPE_K>) + 128; }
 
-// One block of the pipelined protocol.  Dependencies (B = block index):
+// The pipelined protocol.  Dependencies (B = block index):
 //   look-ahead(B) after look-ahead(B-1) and pass(B-2)   [it overwrites the buffer halves of block B-2]
 //   pass(B)       after look-ahead(B)   and pass(B-1)   [it reads what pass(B-1) wrote]
-// so look-ahead(B+1) runs while pass(B) streams the tableau.  serialize = both on the main stream.
-static int launch_pipe_block(lpx_session* s, int budget, bool serialize) {
-    const int par = (int)(s->blocks & 1);
-    cudaStream_t sl = serialize ? s->stream : s->streamL;
+// so look-ahead(B+1) runs while pass(B) streams the tableau.  The look-ahead is a cluster of 8 CTAs
+// that each need a whole SM; pass(B) and look-ahead(B+1) become ready at the same moment, so the
+// look-ahead is enqueued FIRST and on a higher-priority stream: it takes its 8 SMs, the pass (whose
+// grid is sized for the remaining SMs) fills the rest.
+static int enqueue_pipe_lookahead(lpx_session* s, long long B, int budget, cudaStream_t sl) {
+    const int par = (int)(B & 1);
     LPX_CUDA(cudaStreamWaitEvent(sl, s->evL[par ^ 1], 0));
     LPX_CUDA(cudaStreamWaitEvent(sl, s->evP[par], 0));
     stream_lookahead_pipe_kernel<<<LPX_LA_CLUSTER, LPX_LA_THREADS, lookahead_cluster_smem(s->P), sl>>>(s->P, budget, par, 1);
     LPX_CUDA(cudaEventRecord(s->evL[par], sl));
+    count_launch();
+    return LPX_OK;
+}
+static int enqueue_pipe_pass(lpx_session* s, long long B) {
+    const int par = (int)(B & 1);
     LPX_CUDA(cudaStreamWaitEvent(s->stream, s->evL[par], 0));
     LPX_CUDA(cudaStreamWaitEvent(s->stream, s->evP[par ^ 1], 0));
     stream_update_pipe_tma_kernel<LPX_PIPE_K><<<s->grid_pipe, 256, pipe_pass_smem(), s->stream>>>(s->P, s->rpc_pipe, par);
     LPX_CUDA(cudaEventRecord(s->evP[par], s->stream));
+    count_launch();
+    return LPX_OK;
+}
+// `pivots` more pivots: blocks B0 .. B0+nb-1, enqueued as LA(B0), [LA(B0+1), pass(B0)], ..., pass(B0+nb-1)
+static int launch_pipe_blocks(lpx_session* s, int pivots, bool serialize) {
+    const int K = s->P.kblock;
+    const int nb = (pivots + K - 1) / K;
+    if (nb <= 0) return LPX_OK;
+    cudaStream_t sl = serialize ? s->stream : s->streamL;
+    const long long B0 = s->blocks;
+    int left = pivots, rc;
+    if ((rc = enqueue_pipe_lookahead(s, B0, std::min(left, K), sl)) != LPX_OK) return rc;
+    left -= std::min(left, K);
+    for (int i = 1; i < nb; i++) {
+        if ((rc = enqueue_pipe_lookahead(s, B0 + i, std::min(left, K), sl)) != LPX_OK) return rc;
+        left -= std::min(left, K);
+        if ((rc = enqueue_pipe_pass(s, B0 + i - 1)) != LPX_OK) return rc;
+    }
+    if ((rc = enqueue_pipe_pass(s, B0 + nb - 1)) != LPX_OK) return rc;
     LPX_CUDA(cudaGetLastError());
-    count_launch(2);
-    s->blocks++;
+    s->blocks += nb;
     return LPX_OK;
 }
 
@@ -735,7 +766,7 @@ static lpx_session* session_create(int m, int n, int sense, const double* dA, co
                                        (int)lookahead_cluster_smem(P)) == cudaSuccess &&
                   cudaFuncSetAttribute(stream_update_pipe_tma_kernel<LPX_PIPE_K>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_pass_smem()) == cudaSuccess &&
-                  cudaStreamCreateWithFlags(&s->streamL, cudaStreamNonBlocking) == cudaSuccess;
+                  create_priority_stream(&s->streamL);
         for (int k = 0; k < 2 && ok; k++)
             ok = cudaEventCreateWithFlags(&s->evL[k], cudaEventDisableTiming) == cudaSuccess &&
                  cudaEventCreateWithFlags(&s->evP[k], cudaEventDisableTiming) == cudaSuccess;
@@ -909,11 +940,7 @@ int lpx_session_step_async(lpx_session* s, int max_pivots) {
         // the look-ahead stream starts after whatever the caller has queued on the main stream
         LPX_CUDA(cudaEventRecord(s->evStart, s->stream));
         LPX_CUDA(cudaStreamWaitEvent(s->streamL, s->evStart, 0));
-        for (int left = max_pivots; left > 0; left -= s->P.kblock) {
-            int rc = launch_pipe_block(s, std::min(left, s->P.kblock), false);
-            if (rc != LPX_OK) return rc;
-        }
-        return LPX_OK;
+        return launch_pipe_blocks(s, max_pivots, false);
     }
     if (s->P.kblock > 0) {
         for (int left = max_pivots; left > 0; left -= s->P.kblock) {
