@@ -397,7 +397,7 @@ def run_ours(args):
                 "note": "C++ restatement (oracle/) of the C# loops, not the C# binary (no .NET toolchain here)"}
 
     if args.workload == "large":
-        per_step = 32
+        per_step = 128
         L = bench_large(args.steps, args.warmup, per_step)
         line = {"metric": "simplex pivots/sec", "value": L["value"], "unit": "pivots/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": L["ms_per_step"], "higher_is_better": True,
@@ -413,7 +413,7 @@ def run_ours(args):
         host = Bm.pop("host")
         if not args.no_extras:
             try:
-                Lg = bench_large(3, 3, 32)
+                Lg = bench_large(3, 3, 128)
                 extras["large_tableau"] = {"metric": "simplex pivots/sec, one 4096x8192 LP (tableau 4097x12289)",
                                            "value": Lg["value"], "unit": "pivots/s", "ms_per_pivot":
                                            Lg["ms_per_step"] / Lg["pivots_per_step"], "roofline": Lg["roofline"],

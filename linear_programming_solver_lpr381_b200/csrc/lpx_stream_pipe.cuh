@@ -77,6 +77,7 @@ __global__ void __cluster_dims__(LPX_LA_CLUSTER, 1, 1) __launch_bounds__(LPX_LA_
             st = LPX_S_ITER_LIMIT;
             break;
         }
+        if (P.dbg && rank == 0 && tid == 0 && cnt == 2) P.dbg[0] = lpx_gtime();
         // ---- ChooseEntering: slice argmin, exchanged through distributed shared memory -----------
         {
             ArgMin a;
@@ -105,6 +106,7 @@ __global__ void __cluster_dims__(LPX_LA_CLUSTER, 1, 1) __launch_bounds__(LPX_LA_
             }
         }
         cluster.sync();  // (1)
+        if (P.dbg && rank == 0 && tid == 0 && cnt == 2) P.dbg[1] = lpx_gtime();
         ArgMin g = s_part[0];
 #pragma unroll
         for (int r = 1; r < CL; r++) g = argmin_pick(g, s_part[r]);
@@ -114,10 +116,10 @@ __global__ void __cluster_dims__(LPX_LA_CLUSTER, 1, 1) __launch_bounds__(LPX_LA_
             break;
         }
         // ---- column e, rows of this CTA: gather, bring up to date, all-gather -------------------
+        // One global round trip for the whole phase: the p_s[e] scalars, the gathered column entries
+        // and the factor entries are all requested before anything waits (the loads inside a
+        // dependent chain cost ~1 us each under the memory load of the concurrent pass).
         if (tid < pc + cnt) s_pe[tid] = P.Pbuf[(size_t)PIPE_ROW(tid) * ld + e];
-        __syncthreads();
-        // All factor entries a thread needs are loaded BEFORE the dependent multiply/subtract chain:
-        // with the load inside the chain each decided pivot cost one L2 round trip (~0.7 us).
         for (int base = i_lo; base < i_hi; base += 2 * TH) {
             double c[2];
             double f[2][LPX_BLOCK_KMAX];
@@ -134,6 +136,7 @@ __global__ void __cluster_dims__(LPX_LA_CLUSTER, 1, 1) __launch_bounds__(LPX_LA_
                     f[u][s] = (s < pc + cnt && i < i_hi) ? P.Fbuf[(size_t)PIPE_ROW(s) * cs + i] : 0.0;
                 }
             }
+            __syncthreads();  // s_pe is in shared memory (first trip only matters; later trips are rare)
 #pragma unroll
             for (int s = 0; s < LPX_BLOCK_KMAX; s++) {
                 if (s < pc + cnt) {
@@ -150,25 +153,23 @@ __global__ void __cluster_dims__(LPX_LA_CLUSTER, 1, 1) __launch_bounds__(LPX_LA_
             for (int u = 0; u < 2; u++) {
                 const int i = base + u * TH + tid;
                 if (i < i_hi) {
+                    // the ratio of the row travels with the column entry (one division per thread here
+                    // instead of eight per thread after the all-gather)
+                    double r = __longlong_as_double(0x7ff8000000000000LL);
+                    if (i < m && c[u] > LPX_EPS) r = __ddiv_rn(rhs[i], c[u]);
+                    const int slot = (i % Q) * TH + i / Q;  // permuted position of row i
 #pragma unroll
-                    for (int r = 0; r < CL; r++) cluster.map_shared_rank(col, r)[i] = c[u];
+                    for (int rk = 0; rk < CL; rk++) {
+                        cluster.map_shared_rank(col, rk)[i] = c[u];
+                        if (i < m) cluster.map_shared_rank(ratio, rk)[slot] = r;
+                    }
                 }
             }
         }
         cluster.sync();  // (2) every CTA holds the whole up-to-date column
-        for (int i = tid; i < Q * TH; i += TH) {
-            // permuted slot (u, t) <-> row t*Q + u
-            const int t = i % TH, u = i / TH;
-            const int row_i = t * Q + u;
-            double r = __longlong_as_double(0x7ff8000000000000LL);
-            if (row_i < m) {
-                const double a = col[row_i];
-                if (a > LPX_EPS) r = __ddiv_rn(rhs[row_i], a);
-            }
-            ratio[i] = r;
-        }
-        __syncthreads();
+        if (P.dbg && rank == 0 && tid == 0 && cnt == 2) P.dbg[2] = lpx_gtime();
         const int l = la_leaving_scan(ratio, m, Q, s_wmin, s_wcnt, s_rec, &s_out, s_ired);
+        if (P.dbg && rank == 0 && tid == 0 && cnt == 2) P.dbg[3] = lpx_gtime();
         if (l < 0) {
             st = LPX_UNBOUNDED;
             break;
@@ -177,7 +178,6 @@ __global__ void __cluster_dims__(LPX_LA_CLUSTER, 1, 1) __launch_bounds__(LPX_LA_
         const double piv = col[l], fz = col[m];
         // ---- row l, columns of this CTA: gather, bring up to date, normalise, advance z ----------
         if (tid < pc + cnt) s_fl[tid] = P.Fbuf[(size_t)PIPE_ROW(tid) * cs + l];
-        __syncthreads();
         double* pout = P.Pbuf + (size_t)(par * LPX_PIPE_K + cnt) * ld;
         const double* Tl = Tin + (size_t)l * ld;
         for (int base = j_lo; base < j_hi; base += 2 * TH) {
@@ -196,6 +196,7 @@ __global__ void __cluster_dims__(LPX_LA_CLUSTER, 1, 1) __launch_bounds__(LPX_LA_
                     pp[u][s] = (s < pc + cnt && j < j_hi) ? P.Pbuf[(size_t)PIPE_ROW(s) * ld + j] : 0.0;
                 }
             }
+            __syncthreads();  // s_fl is in shared memory
 #pragma unroll
             for (int s = 0; s < LPX_BLOCK_KMAX; s++) {
                 if (s < pc + cnt) {
@@ -216,6 +217,7 @@ __global__ void __cluster_dims__(LPX_LA_CLUSTER, 1, 1) __launch_bounds__(LPX_LA_
             }
         }
         // ---- RHS (every CTA keeps the full vector), factor column slice, bookkeeping ------------
+        if (P.dbg && rank == 0 && tid == 0 && cnt == 2) P.dbg[4] = lpx_gtime();
         const double prhs = __ddiv_rn(rhs[l], piv);
         __syncthreads();
         double* fout = P.Fbuf + (size_t)(par * LPX_PIPE_K + cnt) * cs;
@@ -238,6 +240,7 @@ __global__ void __cluster_dims__(LPX_LA_CLUSTER, 1, 1) __launch_bounds__(LPX_LA_
         cnt++;
         __threadfence();
         cluster.sync();  // (3) Pbuf / Fbuf slices of this pivot are visible to the whole cluster
+        if (P.dbg && rank == 0 && tid == 0 && cnt == 3) P.dbg[5] = lpx_gtime();
     }
     if (!probe) {
         for (int j = j_lo + tid; j < j_hi; j += TH) P.zbuf[j] = zloc[j - j_lo];

@@ -96,7 +96,7 @@ if __name__ == "__main__":
             ss = torch.cuda.ExternalStream(s.stream)
             s.step(32)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            npv = 192
+            npv = 256
             e0.record(ss)
             s.step_async(npv)
             e1.record(ss)
