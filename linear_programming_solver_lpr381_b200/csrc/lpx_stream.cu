@@ -937,9 +937,9 @@ int lpx_session_step_async(lpx_session* s, int max_pivots) {
         return LPX_E_BAD_ARGS;
     }
     if (s->pipe) {
-        // the look-ahead stream starts after whatever the caller has queued on the main stream
-        LPX_CUDA(cudaEventRecord(s->evStart, s->stream));
-        LPX_CUDA(cudaStreamWaitEvent(s->streamL, s->evStart, 0));
+        // No fence against the main stream here: the look-ahead only depends on the session's own
+        // kernels (event chain below), so the first look-ahead of this call overlaps the last pass
+        // of the previous call and the pipeline never drains between calls.
         return launch_pipe_blocks(s, max_pivots, false);
     }
     if (s->P.kblock > 0) {

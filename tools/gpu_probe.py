@@ -156,3 +156,52 @@ if __name__ == "__main__":
             print(json.dumps(dict(spec_nodes=sn, spec_depth=sd, nodes=int(r["n_evals"].sum()), seconds=dt,
                                   nodes_s=int(r["n_evals"].sum()) / dt, launches=F.lib().lpx_kernel_launches() - l0)),
                   flush=True)
+    if what == "blockwin":
+        A, b, c = workloads.large_c3()
+        for warm, calls, per in ((32, 1, 256), (384, 1, 640), (384, 5, 128), (32, 8, 32), (1024, 1, 256)):
+            s = api.Session(A, b, c, max_iterations=1 << 30)
+            ss = torch.cuda.ExternalStream(s.stream)
+            s.step(warm)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(ss)
+            for _ in range(calls):
+                s.step_async(per)
+            e1.record(ss)
+            st, tot = s.sync()
+            us = e0.elapsed_time(e1) * 1e3 / (calls * per)
+            print(json.dumps(dict(warm=warm, calls=calls, per=per, us_per_pivot=us, pivots_s=1e6 / us, status=st)), flush=True)
+            s.close()
+    if what == "benchlike":
+        A, b, c = workloads.large_c3()
+        for mode in ("host", "devptr", "devptr_events"):
+            if mode == "host":
+                s = api.Session(A, b, c, max_iterations=1 << 30)
+            else:
+                dA, db, dc = (torch.from_numpy(v).to(dev) for v in (A, b, c))
+                torch.cuda.synchronize()
+                s = api.Session(dA.data_ptr(), db.data_ptr(), dc.data_ptr(), device_ptrs=True, m=4096, n=8192,
+                                max_iterations=1 << 30)
+                del dA
+            ss = torch.cuda.ExternalStream(s.stream)
+            for _ in range(3):
+                s.step_async(128)
+            s.sync()
+            torch.cuda.synchronize()
+            if mode == "devptr_events":
+                ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+                for k in range(5):
+                    ev[k][0].record(ss)
+                    s.step_async(128)
+                    ev[k][1].record(ss)
+                st, tot = s.sync()
+                ms = sum(a.elapsed_time(bb) for a, bb in ev)
+            else:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(ss)
+                for k in range(5):
+                    s.step_async(128)
+                e1.record(ss)
+                st, tot = s.sync()
+                ms = e0.elapsed_time(e1)
+            print(json.dumps(dict(mode=mode, us_per_pivot=ms * 1e3 / 640, status=st)), flush=True)
+            s.close()
