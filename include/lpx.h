@@ -68,7 +68,9 @@ typedef struct lpx_options {
     int stream_block;     /* streaming kernels: pivots applied per HBM pass (0 = default, max 16) */
     int stream_pass_variant; /* blocked pass: 0 auto, 1 two doubles per thread, 2 one double per thread,
                                 3 TMA-staged (cp.async.bulk + mbarrier pipeline) */
-    int reserved[7];
+    int knap_ordered_sums; /* knapsack: 1 = always sum in the reference's order, even for exactly summable
+                              integer data (which otherwise take the warp-parallel exact path) */
+    int reserved[6];
 } lpx_options;
 
 #define LPX_KERNEL_AUTO        0
@@ -245,6 +247,12 @@ int lpx_comm_rank(void);
 /* Unfused FP64 rate (separate DMUL and DADD, the only arithmetic the bit-exactness contract
  * allows) in TFLOP/s: the roofline denominator of the on-chip batched kernels. */
 int lpx_measure_fp64_rate(double* tflops);
+/* Session kernels timed separately with CUDA events on the session stream, run back to back
+ * (no overlap): us[0] = mean look-ahead / select time, us[1] = mean HBM pass time, us[2] = mean time
+ * per block (blocked protocols) or per pivot (per-pivot protocols), over n blocks / pivots. */
+int lpx_session_profile(lpx_session* s, int n, double* us);
+/* Development aid: phase timestamps (ns, %globaltimer) of one look-ahead step. */
+int lpx_session_debug_stamps(lpx_session* s, unsigned long long* out8);
 
 /* ---- counters (for benchmarks: "how many of my kernels launched") --------------------------- */
 long long lpx_kernel_launches(void);   /* since lpx_init / last reset */

@@ -29,7 +29,7 @@ EXPORTS = [
     "lpx_session_close", "lpx_bnb_simplex_batched", "lpx_bnb_simplex", "lpx_bnb_instance", "lpx_bnb_knapsack",
     "lpx_bnb_knapsack_batched", "lpx_comm_unique_id", "lpx_comm_init", "lpx_comm_allreduce_max",
     "lpx_comm_allgather", "lpx_comm_destroy", "lpx_comm_world", "lpx_comm_rank", "lpx_kernel_launches",
-    "lpx_reset_counters", "lpx_measure_fp64_rate",
+    "lpx_reset_counters", "lpx_measure_fp64_rate", "lpx_session_profile", "lpx_session_debug_stamps",
 ]
 
 
@@ -42,7 +42,8 @@ class LpxError(RuntimeError):
 class Options(C.Structure):
     _fields_ = [("max_iterations", C.c_int), ("kernel", C.c_int), ("threads", C.c_int), ("knap_spec_nodes", C.c_int),
                 ("knap_spec_depth", C.c_int), ("stream_protocol", C.c_int), ("reg_variant", C.c_int),
-                ("stream_block", C.c_int), ("stream_pass_variant", C.c_int), ("reserved", C.c_int * 7)]
+                ("stream_block", C.c_int), ("stream_pass_variant", C.c_int), ("knap_ordered_sums", C.c_int),
+                ("reserved", C.c_int * 6)]
 
 
 class BnbNode(C.Structure):
@@ -150,7 +151,7 @@ def check(rc):
         raise LpxError(rc, last_error())
 
 
-def make_options(max_iterations=10000, kernel=KERNEL_AUTO, threads=0, spec_nodes=0, spec_depth=0, single_cta_select=0, reg_variant=0, kblock=0, pass_variant=0):
+def make_options(max_iterations=10000, kernel=KERNEL_AUTO, threads=0, spec_nodes=0, spec_depth=0, single_cta_select=0, reg_variant=0, kblock=0, pass_variant=0, ordered_sums=0):
     o = Options()
     lib().lpx_default_options(C.byref(o))
     o.max_iterations = max_iterations
@@ -162,6 +163,7 @@ def make_options(max_iterations=10000, kernel=KERNEL_AUTO, threads=0, spec_nodes
     o.reg_variant = reg_variant
     o.stream_block = kblock
     o.stream_pass_variant = pass_variant
+    o.knap_ordered_sums = ordered_sums
     return o
 
 

@@ -237,8 +237,7 @@ def bnb_knapsack(profit, weight, capacity, trace=False, spec_nodes=0, spec_depth
     w = np.ascontiguousarray(weight, dtype=np.float64)
     n = p.shape[0]
     # sequential=True forces the ordered-summation kernel path even for exactly summable integer data
-    opt = F.make_options(spec_nodes=spec_nodes, spec_depth=spec_depth,
-                         kernel=F.KERNEL_CTA_GLOBAL if sequential else F.KERNEL_AUTO)
+    opt = F.make_options(spec_nodes=spec_nodes, spec_depth=spec_depth, ordered_sums=1 if sequential else 0)
     found = C.c_int()
     best = C.c_double()
     bx = np.zeros(n, dtype=np.int32)

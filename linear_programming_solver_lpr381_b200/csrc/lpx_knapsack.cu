@@ -852,7 +852,7 @@ static int knapsack_entry(int count, int n, const double* profit, const double* 
     if (opt) d.opt = *opt;
     if (d.opt.knap_spec_nodes > 0) d.spec_nodes = d.opt.knap_spec_nodes;
     if (d.opt.knap_spec_depth > 0) d.spec_depth = d.opt.knap_spec_depth;
-    d.force_sequential = d.opt.kernel == LPX_KERNEL_CTA_GLOBAL;  // reuse of the kernel selector for tests
+    d.force_sequential = d.opt.knap_ordered_sums != 0;
     d.on_pop = on_pop;
     d.user = user;
     rc = d.run();

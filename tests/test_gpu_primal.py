@@ -243,3 +243,42 @@ def test_register_resident_kernel(lpx, orc, reg_variant):
     # shapes it does not serve are refused, not silently rerouted
     with pytest.raises(F.LpxError):
         lpx.primal_solve_batched(np.ones((2, 70, 10)), np.ones((2, 70)), np.ones((2, 10)), kernel=F.KERNEL_CTA_REG)
+
+
+BEALE_A = np.array([[0.25, -8.0, -1.0, 9.0], [0.5, -12.0, -0.5, 3.0], [0.0, 0.0, 1.0, 0.0]])
+BEALE_B = np.array([0.0, 0.0, 1.0])
+BEALE_C = np.array([0.75, -20.0, 0.5, -6.0])
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_cycling_lp_hits_the_iteration_limit(lpx, orc, kernel):
+    """Beale's example cycles under Dantzig + lowest-index ties: the reference throws "Iteration
+    limit exceeded." after exactly 10000 pivots (PrimalSimplex.cs:95-96); so must the engine, with
+    the same 10000 (entering, leaving) pairs."""
+    want = orc.primal_solve(BEALE_A, BEALE_B, BEALE_C, max_iterations=10000)
+    assert want["status"] == F.S_ITER_LIMIT and want["n_pivots"] == 10000
+    got = lpx.primal_solve(BEALE_A, BEALE_B, BEALE_C, max_iterations=10000, kernel=kernel)
+    assert got["status"] == F.S_ITER_LIMIT and got["n_pivots"] == 10000
+    assert got["pivots"].tolist() == want["pivots"].tolist()
+    assert F.status_message(got["status"]) == "Iteration limit exceeded."
+
+
+def test_cycling_lp_batched_register_kernel(lpx, orc):
+    A = np.repeat(BEALE_A[None], 5, axis=0)
+    b = np.repeat(BEALE_B[None], 5, axis=0)
+    c = np.repeat(BEALE_C[None], 5, axis=0)
+    c[3] = [1.0, 1.0, 1.0, 1.0]  # one well-behaved instance among the cycling ones
+    for kernel in (F.KERNEL_CTA_REG, F.KERNEL_CTA_SMEM):
+        got = lpx.primal_solve_batched(A, b, c, max_iterations=10000, kernel=kernel)
+        for k in range(5):
+            want = orc.primal_solve(A[k], b[k], c[k], max_iterations=10000)
+            assert got["status"][k] == want["status"] and got["n_pivots"][k] == want["n_pivots"], (kernel, k)
+
+
+def test_extreme_aspect_ratios(lpx, orc):
+    """Tall-thin and short-wide tableaux through the automatic kernel choice."""
+    for (m, n, seed) in [(2500, 4, 1), (4, 12000, 2), (700, 900, 3)]:
+        A, b, c = workloads.lp_integer(m, n, seed)
+        want = orc.primal_solve(A, b, c)
+        got = lpx.primal_solve(A, b, c)
+        compare_primal(got, want, f"{m}x{n}")

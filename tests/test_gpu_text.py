@@ -127,3 +127,19 @@ def test_cli_example_input(lpx, orc, tmp_path):
     assert out.stdout == open(os.path.join(ROOT, "tests", "golden", "example_output.txt")).read()
     bad = subprocess.run([exe, "Primal Simplex"], input="Max: 1x1\n1x1 >= 2\n", capture_output=True, text=True, timeout=120)
     assert bad.returncode == 1 and "Constraint contains '>=' sign." in bad.stderr
+
+
+def test_ragged_rows_fail_like_build_tableau(lpx, orc):
+    """A constraint with fewer coefficients than the objective parses, then BuildTableau indexes past
+    the row (IndexOutOfRangeException, PrimalSimplex.cs:190)."""
+    text = "Max: 3x1 + 5x2 + 1x3\n1x1 + 2x2 <= 4\n1x1 + 1x2 + 1x3 <= 5\n"
+    for algo in ("Primal Simplex", "Dual Simplex", "Branch and Bound", "knapsack"):
+        got = H.solve_text(text, algo)
+        assert got["code"] != 0 and got["error"] != "", algo
+    assert H.solve_text(text, "Primal Simplex")["error"] == "Index was outside the bounds of the array."
+
+
+def test_empty_and_blank_inputs(lpx, orc):
+    for text in ("", "\n\n", "Max: 3x1\n"):
+        want, got = orc.solve_text(text, "Primal Simplex"), H.solve_text(text, "Primal Simplex")
+        assert got["error"] == want["error"] == "Input must contain an objective and at least one constraint."
