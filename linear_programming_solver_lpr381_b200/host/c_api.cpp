@@ -10,6 +10,8 @@ using namespace lpr381;
 struct lpr_text {
     int code = 0, chunks = 0, highlighted = 0;
     std::string error, log, report, summary;
+    SimplexResult result;
+    std::vector<Constraint> cuts;
 };
 
 static thread_local std::string t_buf;
@@ -18,7 +20,8 @@ extern "C" {
 
 void lpr_set_newline(const char* nl) { NewLine() = nl; }
 
-// algorithm: any LPSolver key; "knapsack" constructs BranchAndBoundKnapsack directly (it has no
+// algorithm: any LPSolver key; "cutting plane" constructs CuttingPlane directly (Form1.cs:249-254);
+// "knapsack" constructs BranchAndBoundKnapsack directly (it has no
 // LPSolver key upstream); "controller" goes through LPController.SolvePrimalSimplex (no callback).
 lpr_text* lpr_solve_text(const char* input, const char* algorithm) {
     lpr_text* t = new lpr_text();
@@ -33,9 +36,15 @@ lpr_text* lpr_solve_text(const char* input, const char* algorithm) {
         const std::string algo = algorithm;
         if (algo == "knapsack") r = BranchAndBoundKnapsack().Solve(p, cb);
         else if (algo == "controller") r = LPController::SolvePrimalSimplex(p);
+        else if (algo == "cutting plane") {
+            CuttingPlane cp;
+            r = cp.Solve(p, cb);
+            t->cuts = cp.Cuts;
+        }
         else r = LPSolver().Solve(p, algo, cb);
         t->report = r.Report;
         t->summary = r.Summary;
+        t->result = r;
     } catch (const LpException& e) {
         t->code = e.code ? e.code : -1;
         t->error = e.what();
@@ -49,6 +58,25 @@ const char* lpr_text_error(const lpr_text* t) { return t->error.c_str(); }
 const char* lpr_text_log(const lpr_text* t) { return t->log.c_str(); }
 const char* lpr_text_report(const lpr_text* t) { return t->report.c_str(); }
 const char* lpr_text_summary(const lpr_text* t) { return t->summary.c_str(); }
+// numeric part of the SimplexResult; returns 1 when Tableau != null
+int lpr_text_result_dims(const lpr_text* t, int* rows, int* cols, int* nx, int* nbasis) {
+    *rows = t->result.Tableau.rows;
+    *cols = t->result.Tableau.cols;
+    *nx = t->result.HasSolution ? (int)t->result.Solution.size() : 0;
+    *nbasis = (int)t->result.Basis.size();
+    return t->result.Tableau.is_null() ? 0 : 1;
+}
+const double* lpr_text_tableau(const lpr_text* t) { return t->result.Tableau.v.data(); }
+const double* lpr_text_solution(const lpr_text* t) { return t->result.Solution.data(); }
+const int* lpr_text_basis(const lpr_text* t) { return t->result.Basis.data(); }
+double lpr_text_z(const lpr_text* t) { return t->result.OptimalValue; }
+int lpr_text_cut_count(const lpr_text* t) { return (int)t->cuts.size(); }
+int lpr_text_cut(const lpr_text* t, int k, double* a, double* b) {
+    if (k < 0 || k >= (int)t->cuts.size()) return -1;
+    *b = t->cuts[k].B;
+    for (size_t j = 0; j < t->cuts[k].A.size(); j++) a[j] = t->cuts[k].A[j];
+    return (int)t->cuts[k].A.size();
+}
 void lpr_text_free(lpr_text* t) { delete t; }
 
 // two-phase like the oracle's: A == NULL -> sizes only

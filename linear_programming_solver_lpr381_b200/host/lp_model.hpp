@@ -8,6 +8,7 @@
 //   LPParser.ParseFromText                             R/Models/LPParser.cs:9-59
 //   LPSolver.Solve / NormalizeAlgorithmKey             R/Models/LPSolver.cs:16-76
 //   LPController.SolvePrimalSimplex                    R/Controllers/LPController.cs:13-17
+//   CuttingPlane.Solve                                 R/Models/CuttingPlane.cs:13-164
 #pragma once
 #include <functional>
 #include <memory>
@@ -90,6 +91,12 @@ struct BranchAndBound : ILPAlgorithm {
     SimplexResult Solve(const LPProblem& problem, UpdatePivot updatePivot = nullptr) override;
 };
 struct BranchAndBoundKnapsack : ILPAlgorithm {
+    SimplexResult Solve(const LPProblem& problem, UpdatePivot updatePivot = nullptr) override;
+};
+
+// R/Models/CuttingPlane.cs:9-165 — constructed directly by the GUI (Form1.cs:249-254), no LPSolver key
+struct CuttingPlane : ILPAlgorithm {
+    std::vector<Constraint> Cuts;  // the Gomory cuts added, in order (not kept upstream; for inspection)
     SimplexResult Solve(const LPProblem& problem, UpdatePivot updatePivot = nullptr) override;
 };
 

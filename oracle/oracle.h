@@ -65,7 +65,8 @@ int orc_knapsack(int n, const double* profit, const double* weight, double capac
                  int* ev_var, double* ev_bound, double* ev_weight, int* ev_frac, int* ev_decision);
 
 /* Full text of a headless solve: the updatePivot stream, Report and Summary.
- * algorithm: any LPSolver key, or "knapsack" for BranchAndBoundKnapsack. */
+ * algorithm: any LPSolver key, "knapsack" for BranchAndBoundKnapsack, "cutting plane" for
+ * CuttingPlane (both constructed directly by Form1.btnSolve_Click, not through LPSolver). */
 typedef struct orc_text orc_text;
 orc_text* orc_solve_text(const char* input, const char* algorithm);
 int orc_text_code(const orc_text* t);           /* 0 or the negative error code */
@@ -74,6 +75,16 @@ const char* orc_text_log(const orc_text* t);
 const char* orc_text_report(const orc_text* t);
 const char* orc_text_summary(const orc_text* t);
 int orc_text_masks(const orc_text* t);          /* number of callback chunks */
+/* numeric part of the returned SimplexResult; returns 1 when Tableau != null */
+int orc_text_result_dims(const orc_text* t, int* rows, int* cols, int* nx, int* nbasis);
+const double* orc_text_tableau(const orc_text* t);
+const double* orc_text_solution(const orc_text* t);
+const int* orc_text_basis(const orc_text* t);
+double orc_text_z(const orc_text* t);
+/* Gomory cuts added by "cutting plane", in order */
+int orc_text_cut_count(const orc_text* t);
+int orc_text_cut(const orc_text* t, int k, int* frac_var, int* row, double* a, double* b);
+int orc_text_cut_end(const orc_text* t);        /* 0 integer, 1 incomplete (50 rounds), 2 LP error, 3 non-basic */
 void orc_text_free(orc_text* t);
 
 /* .NET formatting restatements, exposed for unit tests.  Return pointers valid until the next call

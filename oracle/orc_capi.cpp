@@ -291,6 +291,8 @@ struct orc_text {
     int code = 0;
     int chunks = 0;
     std::string error, log, report, summary;
+    Outcome result;   // numeric part of the SimplexResult (Tableau / Solution / Basis may be null)
+    CutTrace cuts;
 };
 
 orc_text* orc_solve_text(const char* input, const char* algorithm) {
@@ -304,9 +306,11 @@ orc_text* orc_solve_text(const char* input, const char* algorithm) {
         Outcome o;
         std::string algo = algorithm;
         if (algo == "knapsack") o = knapsack_bnb(p, sink, nullptr, true);
+        else if (algo == "cutting plane") o = cutting_plane(p, sink, &t->cuts);   // Form1.cs:249-254
         else o = lp_solver_solve(p, algo, sink, nullptr, true);
         t->report = o.report;
         t->summary = o.summary;
+        t->result = o;
     } catch (const SolveError& e) {
         t->code = e.code;
         t->error = e.what();
@@ -319,6 +323,27 @@ const char* orc_text_log(const orc_text* t) { return t->log.c_str(); }
 const char* orc_text_report(const orc_text* t) { return t->report.c_str(); }
 const char* orc_text_summary(const orc_text* t) { return t->summary.c_str(); }
 int orc_text_masks(const orc_text* t) { return t->chunks; }
+int orc_text_result_dims(const orc_text* t, int* rows, int* cols, int* nx, int* nbasis) {
+    *rows = t->result.has_tableau ? t->result.rows : 0;
+    *cols = t->result.has_tableau ? t->result.cols : 0;
+    *nx = t->result.has_x ? (int)t->result.x.size() : 0;
+    *nbasis = (int)t->result.basis.size();
+    return t->result.has_tableau ? 1 : 0;
+}
+const double* orc_text_tableau(const orc_text* t) { return t->result.T.data(); }
+const double* orc_text_solution(const orc_text* t) { return t->result.x.data(); }
+const int* orc_text_basis(const orc_text* t) { return t->result.basis.data(); }
+double orc_text_z(const orc_text* t) { return t->result.z; }
+int orc_text_cut_count(const orc_text* t) { return (int)t->cuts.cut_b.size(); }
+int orc_text_cut(const orc_text* t, int k, int* frac_var, int* row, double* a, double* b) {
+    if (k < 0 || k >= (int)t->cuts.cut_b.size()) return -1;
+    *frac_var = t->cuts.frac_var[k];
+    *row = t->cuts.cut_row[k];
+    *b = t->cuts.cut_b[k];
+    for (size_t j = 0; j < t->cuts.cut_a[k].size(); j++) a[j] = t->cuts.cut_a[k][j];
+    return (int)t->cuts.cut_a[k].size();
+}
+int orc_text_cut_end(const orc_text* t) { return t->cuts.end; }
 void orc_text_free(orc_text* t) { delete t; }
 
 const char* orc_fmt_custom(double v, int decimals) { t_fmt = fmt_custom(v, decimals); return t_fmt.c_str(); }

@@ -37,6 +37,16 @@ def lib():
         L.orc_text_code.argtypes = [C.c_void_p]
         L.orc_text_masks.argtypes = [C.c_void_p]
         L.orc_text_free.argtypes = [C.c_void_p]
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+        L.orc_text_result_dims.argtypes = [C.c_void_p, ip, ip, ip, ip]
+        L.orc_text_tableau.restype = dp
+        L.orc_text_solution.restype = dp
+        L.orc_text_basis.restype = ip
+        L.orc_text_z.restype = C.c_double
+        for f in ("orc_text_tableau", "orc_text_solution", "orc_text_basis", "orc_text_z", "orc_text_cut_count",
+                  "orc_text_cut_end"):
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.orc_text_cut.argtypes = [C.c_void_p, C.c_int, ip, ip, dp, dp]
         for f in ("orc_fmt_custom", "orc_fmt_fixed"):
             getattr(L, f).restype = C.c_char_p
             getattr(L, f).argtypes = [C.c_double, C.c_int]
@@ -238,8 +248,25 @@ def solve_text(text, algorithm):
     L = lib()
     h = L.orc_solve_text(text.encode("utf-8"), algorithm.encode("utf-8"))
     try:
-        return dict(code=L.orc_text_code(h), error=L.orc_text_error(h).decode("utf-8"),
-                    log=L.orc_text_log(h).decode("utf-8"), report=L.orc_text_report(h).decode("utf-8"),
-                    summary=L.orc_text_summary(h).decode("utf-8"), chunks=L.orc_text_masks(h))
+        out = dict(code=L.orc_text_code(h), error=L.orc_text_error(h).decode("utf-8"),
+                   log=L.orc_text_log(h).decode("utf-8"), report=L.orc_text_report(h).decode("utf-8"),
+                   summary=L.orc_text_summary(h).decode("utf-8"), chunks=L.orc_text_masks(h))
+        rows, cols, nx, nb = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        L.orc_text_result_dims(h, C.byref(rows), C.byref(cols), C.byref(nx), C.byref(nb))
+        out["tableau"] = (np.ctypeslib.as_array(L.orc_text_tableau(h), (rows.value, cols.value)).copy()
+                          if rows.value else None)
+        out["x"] = np.ctypeslib.as_array(L.orc_text_solution(h), (nx.value,)).copy() if nx.value else None
+        out["basis"] = np.ctypeslib.as_array(L.orc_text_basis(h), (nb.value,)).copy() if nb.value else None
+        out["z"] = L.orc_text_z(h)
+        cuts = []
+        n = max(nx.value, 1024)
+        for k in range(L.orc_text_cut_count(h)):
+            fv, row, b = C.c_int(), C.c_int(), C.c_double()
+            a = np.zeros(n)
+            na = L.orc_text_cut(h, k, C.byref(fv), C.byref(row), _d(a), C.byref(b))
+            cuts.append(dict(frac_var=fv.value, row=row.value, a=a[:na].copy(), b=b.value))
+        out["cuts"] = cuts
+        out["cut_end"] = L.orc_text_cut_end(h)
+        return out
     finally:
         L.orc_text_free(h)

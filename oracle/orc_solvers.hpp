@@ -70,4 +70,16 @@ struct KnapTrace {
 // R/Models/BranchAndBoundKnapsack.cs:58-407
 Outcome knapsack_bnb(const Problem& p, const Sink& sink, KnapTrace* trace, bool build_text = true);
 
+// One entry per round of CuttingPlane.Solve (one PrimalSimplex solve, then at most one cut).
+enum { CUT_INTEGER = 0, CUT_INCOMPLETE = 1, CUT_LP_ERROR = 2, CUT_NONBASIC = 3 };
+struct CutTrace {
+    std::vector<int> lp_pivots, lp_status;      // per round
+    std::vector<int> frac_var, cut_row;         // per cut: first fractional x_j, tableau row the cut was read from
+    std::vector<std::vector<double>> cut_a;     // per cut: coefficients over the decision variables
+    std::vector<double> cut_b;
+    int end = CUT_INTEGER;
+};
+// R/Models/CuttingPlane.cs:13-164
+Outcome cutting_plane(const Problem& p, const Sink& sink, CutTrace* trace);
+
 }  // namespace orc

@@ -58,13 +58,25 @@ KNAP_CASES = {
     "knap_nothing_fits": ([5, 6], [10, 12], 4),
 }
 
+CUT_CASES = {
+    # CuttingPlane: the reference's cut never removes the current vertex (it is read one row too low
+    # and bounds only decision-variable columns from above), so a fractional root runs all 50 rounds
+    "cut_classic_incomplete": (0, [5, 8], [([1, 1], LE, 6), ([5, 9], LE, 45)]),
+    "cut_integral_root": (0, [3, 5], [([1, 0], LE, 4), ([0, 2], LE, 12), ([3, 2], LE, 18)]),
+    "cut_from_z_row": (0, [1, 1], [([2, 2], LE, 3)]),
+    "cut_three_vars": (0, [7, 3, 4], [([3, 2, 5], LE, 17), ([4, 1, 2], LE, 11), ([1, 3, 1], LE, 9)]),
+    "cut_min_sense": (1, [-3, -2], [([2, 1], LE, 5), ([1, 3], LE, 7)]),
+    "cut_eq_row": (0, [2, 1], [([4, 2], EQ, 7), ([1, 0], LE, 3)]),
+    "cut_ge_error": (0, [1, 1], [([1, 1], LE, 4), ([1, 0], GE, 1)]),
+}
+
 
 def hx(v):
     return float(v).hex()
 
 
 def main():
-    out = {"lp": {}, "dual": {}, "ip": {}, "knap": {}}
+    out = {"lp": {}, "dual": {}, "ip": {}, "knap": {}, "cut": {}}
     for name, (sense, c, rows, mi) in LP_CASES.items():
         A = [[float(v) for v in r[0]] for r in rows]
         rel = [r[1] for r in rows]
@@ -101,6 +113,18 @@ def main():
         out["knap"][name] = dict(p=[hx(v) for v in p], w=[hx(v) for v in w], cap=hx(cap), found=found,
                                  best=hx(best) if found else None, best_x=bx, pops=pops, rank_order=order,
                                  evals=[[hx(e[0]), hx(e[1]), e[2], e[3]] for e in evals])
+    for name, (sense, c, rows) in CUT_CASES.items():
+        A = [[float(v) for v in r[0]] for r in rows]
+        rel = [r[1] for r in rows]
+        b = [float(r[2]) for r in rows]
+        r = pyref.cutting_plane(A, b, [float(v) for v in c], rel, sense)
+        case = dict(sense=sense, c=[hx(v) for v in c], A=[[hx(v) for v in r_] for r_ in A], rel=rel,
+                    b=[hx(v) for v in b], end=r["end"], rounds=[list(t) for t in r["rounds"]],
+                    cuts=[dict(frac_var=fv, row=row, a=[hx(v) for v in a], b=hx(f0)) for fv, row, a, f0 in r["cuts"]])
+        if r["end"] == 0:
+            case.update(x=[hx(v) for v in r["x"]], z=hx(r["z"]), basis=r["basis"],
+                        tableau=[[hx(v) for v in row] for row in r["tableau"]])
+        out["cut"][name] = case
     with open(os.path.join(HERE, "kat.json"), "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)
     print("wrote kat.json:", {k: len(v) for k, v in out.items()})

@@ -28,6 +28,15 @@ def lib():
         L.lpr_math_round.restype = C.c_double
         L.lpr_math_round.argtypes = [C.c_double, C.c_int]
         L.lpr_normalize_key.restype = C.c_char_p
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+        L.lpr_text_result_dims.argtypes = [C.c_void_p, ip, ip, ip, ip]
+        L.lpr_text_tableau.restype = dp
+        L.lpr_text_solution.restype = dp
+        L.lpr_text_basis.restype = ip
+        L.lpr_text_z.restype = C.c_double
+        for f in ("lpr_text_tableau", "lpr_text_solution", "lpr_text_basis", "lpr_text_z", "lpr_text_cut_count"):
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.lpr_text_cut.argtypes = [C.c_void_p, C.c_int, dp, dp]
         _lib = L
     return _lib
 
@@ -36,10 +45,24 @@ def solve_text(text, algorithm):
     L = lib()
     h = L.lpr_solve_text(text.encode("utf-8"), algorithm.encode("utf-8"))
     try:
-        return dict(code=L.lpr_text_code(h), error=L.lpr_text_error(h).decode("utf-8"),
-                    log=L.lpr_text_log(h).decode("utf-8"), report=L.lpr_text_report(h).decode("utf-8"),
-                    summary=L.lpr_text_summary(h).decode("utf-8"), chunks=L.lpr_text_chunks(h),
-                    highlighted=L.lpr_text_highlighted(h))
+        out = dict(code=L.lpr_text_code(h), error=L.lpr_text_error(h).decode("utf-8"),
+                   log=L.lpr_text_log(h).decode("utf-8"), report=L.lpr_text_report(h).decode("utf-8"),
+                   summary=L.lpr_text_summary(h).decode("utf-8"), chunks=L.lpr_text_chunks(h),
+                   highlighted=L.lpr_text_highlighted(h))
+        rows, cols, nx, nb = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        L.lpr_text_result_dims(h, C.byref(rows), C.byref(cols), C.byref(nx), C.byref(nb))
+        out["tableau"] = (np.ctypeslib.as_array(L.lpr_text_tableau(h), (rows.value, cols.value)).copy()
+                          if rows.value else None)
+        out["x"] = np.ctypeslib.as_array(L.lpr_text_solution(h), (nx.value,)).copy() if nx.value else None
+        out["basis"] = np.ctypeslib.as_array(L.lpr_text_basis(h), (nb.value,)).copy() if nb.value else None
+        out["z"] = L.lpr_text_z(h)
+        cuts = []
+        for k in range(L.lpr_text_cut_count(h)):
+            a, b = np.zeros(4096), C.c_double()
+            na = L.lpr_text_cut(h, k, a.ctypes.data_as(C.POINTER(C.c_double)), C.byref(b))
+            cuts.append(dict(a=a[:na].copy(), b=b.value))
+        out["cuts"] = cuts
+        return out
     finally:
         L.lpr_text_free(h)
 

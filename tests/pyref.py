@@ -387,3 +387,48 @@ def knapsack(p, w, cap):
                 dec = 4
             evals.append((pr, cw, fr, dec))
     return best > -math.inf, best, best_x, evals, pops, order
+
+
+def cutting_plane(A, b, c, rel=None, sense=0):
+    """CuttingPlane.Solve (R/Models/CuttingPlane.cs:13-164): <= 50 rounds of primal + one cut read
+    from tableau row `basis position + 1` (the reference's z-row-first assumption, :113)."""
+    import math
+    n = len(c)
+    A = [list(r) for r in A]
+    b = list(b)
+    rel = list(rel) if rel is not None else [LE] * len(A)
+    cuts, rounds = [], []
+    for _ in range(50):
+        try:
+            r = primal(A, b, c, rel, sense)
+        except SolveError as e:
+            return dict(end=2, code=e.code, cuts=cuts, rounds=rounds)
+        rounds.append((len(r["pivots"]), r["status"]))
+        x = r["x"][:n]
+        frac = -1
+        for i, v in enumerate(x):
+            f = v - math.floor(v)
+            if 1e-9 < f < 1 - 1e-9:
+                frac = i
+                break
+        if frac == -1:
+            return dict(end=0, cuts=cuts, rounds=rounds, x=x, z=r["z"], tableau=r["tableau"], basis=r["basis"])
+        row = -1
+        for i, bv in enumerate(r["basis"]):
+            if bv == frac:
+                row = i + 1
+                break
+        if row == -1:
+            return dict(end=3, cuts=cuts, rounds=rounds)
+        trow = r["tableau"][row]
+        a = [0.0] * n
+        for j in range(n):
+            fj = trow[j] - math.floor(trow[j])
+            if fj > 1e-9:
+                a[j] = fj
+        f0 = trow[-1] - math.floor(trow[-1])
+        cuts.append((frac, row, a, f0))
+        A.append(a)
+        b.append(f0)
+        rel.append(LE)
+    return dict(end=1, cuts=cuts, rounds=rounds)

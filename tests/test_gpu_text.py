@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import host_ffi as H
-from conftest import case_arrays
+from conftest import assert_bits_equal, case_arrays, unhex
 
 from linear_programming_solver_lpr381_b200 import workloads
 
@@ -109,6 +109,40 @@ def test_knapsack_requires_one_le_row(lpx, orc):
     for text in ("Max: 1x1 + 2x2\n1x1 + 1x2 <= 3\n1x1 + 0x2 <= 1\n", "Max: 1x1 + 2x2\n1x1 + 1x2 >= 3\n"):
         want, got = orc.solve_text(text, "knapsack"), H.solve_text(text, "knapsack")
         assert got["error"] == want["error"] != ""
+
+
+@pytest.mark.parametrize("name", ["cut_classic_incomplete", "cut_integral_root", "cut_from_z_row", "cut_three_vars",
+                                  "cut_min_sense", "cut_eq_row", "cut_ge_error"])
+def test_cutting_plane_text_and_cuts(lpx, orc, kat, name):
+    # CuttingPlane over the GPU primal solver: same text as the oracle, the golden cuts bit for bit
+    case = kat["cut"][name]
+    got = same_text(orc, kat_text(case), "cutting plane")
+    assert len(got["cuts"]) == len(case["cuts"])
+    for g, w in zip(got["cuts"], case["cuts"]):
+        assert_bits_equal(g["a"], unhex(w["a"]), "cut a")
+        assert_bits_equal([g["b"]], [unhex(w["b"])], "cut b")
+    if case["end"] == 0:
+        assert_bits_equal(got["tableau"], unhex(case["tableau"]), "tableau")
+        assert_bits_equal(got["x"], unhex(case["x"]), "x")
+        assert got["basis"].tolist() == case["basis"]
+    else:
+        assert got["tableau"] is None
+
+
+def test_cutting_plane_random_text(lpx, orc):
+    rng = np.random.default_rng(77)
+    for trial in range(4):
+        m, n = int(rng.integers(2, 6)), int(rng.integers(2, 6))
+        A = rng.integers(0, 9, size=(m, n)).astype(np.float64)
+        b = rng.integers(5, 40, size=m).astype(np.float64) + (0.5 if trial % 2 else 0.0)
+        c = rng.integers(1, 9, size=n).astype(np.float64)
+        text = workloads.lp_to_text(A, b, c, np.zeros(m, dtype=np.int32), 0)
+        got = same_text(orc, text, "cutting plane")
+        want = orc.solve_text(text, "cutting plane")
+        assert len(got["cuts"]) == len(want["cuts"])
+        for g, w in zip(got["cuts"], want["cuts"]):
+            assert_bits_equal(g["a"], w["a"], "cut a")
+            assert_bits_equal([g["b"]], [w["b"]], "cut b")
 
 
 def test_controller_entry_point(lpx, orc):

@@ -151,3 +151,37 @@ def test_oracle_bnb_matches_pyref_random(orc):
         if found:
             assert_bits_equal([r["best_z"]], [best], "best")
             assert_bits_equal(r["best_x"], bx, "best_x")
+
+
+CUT_NAMES = ["cut_classic_incomplete", "cut_integral_root", "cut_from_z_row", "cut_three_vars", "cut_min_sense",
+             "cut_eq_row", "cut_ge_error"]
+
+
+@pytest.mark.parametrize("name", CUT_NAMES)
+def test_cutting_plane_kat(orc, kat, name):
+    # CuttingPlane.cs:13-164: rounds, the row each cut is read from, and every cut coefficient
+    case = kat["cut"][name]
+    A, b, c, rel = case_arrays(case)
+    r = orc.solve_text(workloads.lp_to_text(A, b, c, rel, case["sense"]), "cutting plane")
+    assert r["code"] == 0 and r["cut_end"] == case["end"]
+    assert len(r["cuts"]) == len(case["cuts"])
+    for got, want in zip(r["cuts"], case["cuts"]):
+        assert (got["frac_var"], got["row"]) == (want["frac_var"], want["row"])
+        assert_bits_equal(got["a"], unhex(want["a"]), "cut a")
+        assert_bits_equal([got["b"]], [unhex(want["b"])], "cut b")
+    if case["end"] == 0:
+        assert_bits_equal(r["tableau"], unhex(case["tableau"]), "tableau")
+        assert_bits_equal(r["x"], unhex(case["x"]), "x")
+        assert r["summary"].startswith("Status: OPTIMAL INTEGER\nz* = ")
+    elif case["end"] == 1:
+        assert r["summary"] == "Status: INCOMPLETE" and r["tableau"] is None
+        assert r["report"].count("Added Gomory cut: ") == 50
+    else:
+        assert r["summary"].startswith("Error: Constraint contains '>=' sign.")
+
+
+def test_cutting_plane_reads_the_row_below(kat):
+    # the quirk: with one constraint the fractional variable sits in row 0, so the cut comes from
+    # tableau row 1 = the objective row, whose decision-variable entries are 0 -> the empty cut
+    case = kat["cut"]["cut_from_z_row"]
+    assert all(k["row"] == 1 and unhex(k["a"]) == [0.0, 0.0] and unhex(k["b"]) == 0.5 for k in case["cuts"])
