@@ -392,7 +392,7 @@ def run_ours(args):
     def bench_bnb(count):
         As, bs, cs = zip(*[workloads.ip_c4(seed=1000 * rank + 11 + k) for k in range(count)])
         A, b, c = np.stack(As), np.stack(bs), np.stack(cs)
-        api.bnb_simplex_batched(A[:1], b[:1], c[:1])
+        api.bnb_simplex_batched(A, b, c)  # warm-up at full size: the node pool and pinned staging grow once
         barrier()
         l0 = F.lib().lpx_kernel_launches()
         t0 = time.perf_counter()
@@ -408,7 +408,7 @@ def run_ours(args):
     def bench_knap(count):
         ps, ws, caps = zip(*[workloads.knapsack_c5(seed=1000 * rank + 13 + k) for k in range(count)])
         p, w, cap = np.stack(ps), np.stack(ws), np.array(caps)
-        api.bnb_knapsack_batched(p[:1], w[:1], cap[:1])
+        api.bnb_knapsack_batched(p, w, cap)  # warm-up at full size
         barrier()
         l0 = F.lib().lpx_kernel_launches()
         t0 = time.perf_counter()

@@ -205,3 +205,26 @@ if __name__ == "__main__":
                 ms = e0.elapsed_time(e1)
             print(json.dumps(dict(mode=mode, us_per_pivot=ms * 1e3 / 640, status=st)), flush=True)
             s.close()
+    if what == "bnbrep":
+        # repeat-call timing of the two B&B entry points: is the first full-size call paying for
+        # workspace growth?
+        import time
+        cnt = 256
+        As, bs, cs = zip(*[workloads.ip_c4(seed=11 + k) for k in range(cnt)])
+        A, b, c = np.stack(As), np.stack(bs), np.stack(cs)
+        api.bnb_simplex_batched(A[:1], b[:1], c[:1])
+        for rep in range(4):
+            t0 = time.perf_counter()
+            r = api.bnb_simplex_batched(A, b, c)
+            dt = time.perf_counter() - t0
+            print(json.dumps(dict(call="bnb_simplex_batched", rep=rep, s=dt, nodes=int(r["n_nodes"].sum()),
+                                  nodes_per_s=int(r["n_nodes"].sum()) / dt)), flush=True)
+        ps, ws, caps = zip(*[workloads.knapsack_c5(seed=13 + k) for k in range(16)])
+        p, w, cap = np.stack(ps), np.stack(ws), np.array(caps)
+        api.bnb_knapsack_batched(p[:1], w[:1], cap[:1])
+        for rep in range(4):
+            t0 = time.perf_counter()
+            r = api.bnb_knapsack_batched(p, w, cap)
+            dt = time.perf_counter() - t0
+            print(json.dumps(dict(call="bnb_knapsack_batched", rep=rep, s=dt, nodes=int(r["n_evals"].sum()),
+                                  nodes_per_s=int(r["n_evals"].sum()) / dt)), flush=True)
