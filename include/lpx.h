@@ -247,6 +247,10 @@ int lpx_comm_rank(void);
 /* Unfused FP64 rate (separate DMUL and DADD, the only arithmetic the bit-exactness contract
  * allows) in TFLOP/s: the roofline denominator of the on-chip batched kernels. */
 int lpx_measure_fp64_rate(double* tflops);
+/* Dependent-chain latencies in SM cycles, one warp alone: cycles8[0..7] = DADD, DMUL, DDIV, REDUX.MIN,
+ * SHFL, shared-memory store+load round trip, BAR.SYNC of 13 warps, DSETP+select.  These, not the
+ * FP64 rate, bound one pivot of a per-tableau kernel. */
+int lpx_measure_latencies(double* cycles8);
 /* Session kernels timed separately with CUDA events on the session stream, run back to back
  * (no overlap): us[0] = mean look-ahead / select time, us[1] = mean HBM pass time, us[2] = mean time
  * per block (blocked protocols) or per pivot (per-pivot protocols), over n blocks / pivots. */

@@ -153,6 +153,50 @@ __device__ __forceinline__ int warp_margin_scan(int count, double margin, Get ge
     return row;
 }
 
+// ---- 64-bit keys and REDUX-based warp minima ---------------------------------------------------
+// Order-preserving key of a double: a < b (as doubles)  =>  dkey(a) < dkey(b).  -0.0 sorts just
+// below +0.0 and NaN above +inf; callers that care about -0.0 == +0.0 re-check with a real compare.
+__device__ __forceinline__ unsigned long long dkey(double x) {
+    const long long b = __double_as_longlong(x);
+    return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ULL));
+}
+__device__ __forceinline__ double dkey_inv(unsigned long long k) {
+    const long long b = (long long)k;
+    return __longlong_as_double(b < 0 ? (b ^ (long long)0x8000000000000000ULL) : ~b);
+}
+// Warp minimum of a 64-bit key with two 32-bit REDUX instructions (no shuffle ladder).
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long k) {
+    const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+    const unsigned hmin = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned lmin = __reduce_min_sync(0xffffffffu, hi == hmin ? lo : 0xffffffffu);
+    return ((unsigned long long)hmin << 32) | lmin;
+}
+
+// ChooseLeaving for up to 64 rows held two per lane (r0 = row lane, r1 = row lane + 32; NaN = not
+// eligible).  Fast path: the plain minimum (lowest index) IS the sequential margin scan's answer
+// whenever every other eligible ratio r_j satisfies  min < r_j - margin  — then whatever record
+// precedes the minimum, the minimum is accepted after it, and nothing after it can be.  One REDUX
+// min + one ballot certify that; anything closer than the margin (ties, near-ties, -0.0 vs +0.0)
+// falls back to the exact replay.
+__device__ __forceinline__ int warp_margin_scan64(int count, double margin, double r0, double r1) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long k0 = dkey(r0), k1 = dkey(r1);
+    const unsigned long long K = warp_min_u64(k1 < k0 ? k1 : k0);
+    const double vmin = dkey_inv(K);
+    if (vmin != vmin) return -1;  // no eligible row
+    const unsigned b0 = __ballot_sync(0xffffffffu, k0 == K);
+    const unsigned b1 = __ballot_sync(0xffffffffu, k1 == K);
+    const int imin = b0 ? __ffs(b0) - 1 : 32 + __ffs(b1) - 1;
+    // other eligible rows that are NOT more than the margin above the minimum
+    const bool close0 = (r0 == r0) && lane != imin && !(vmin < __dsub_rn(r0, margin));
+    const bool close1 = (r1 == r1) && lane + 32 != imin && !(vmin < __dsub_rn(r1, margin));
+    if (!__any_sync(0xffffffffu, close0 || close1) && vmin < __longlong_as_double(0x7ff0000000000000LL)) return imin;
+    return warp_margin_scan(count, margin, [&](int i, double& ratio) {
+        ratio = i < 32 ? r0 : r1;
+        return ratio == ratio;
+    });
+}
+
 __device__ __forceinline__ double neg_if(double v, bool flip) {
     // "v *= -1" of the reference (PrimalSimplex.cs:170-171, DualSimplex.cs:135,144-152)
     return flip ? __dmul_rn(v, -1.0) : v;

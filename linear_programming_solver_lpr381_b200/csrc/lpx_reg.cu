@@ -12,6 +12,9 @@
 // entering = warp-shuffle argmin with lowest index on ties, leaving = exact sequential margin
 // scan (every warp repeats it on the staged vectors instead of waiting for a broadcast), pivot =
 // true division then separate multiply and subtract, zero-factor rows included.
+#include <cstdio>
+#include <cstdlib>
+
 #include "lpx_cta.cuh"
 #include "lpx_stream.hpp"
 
@@ -29,31 +32,53 @@ struct RegBatch {
     double* z;
     double* tableau;
     unsigned long long* total_pivots;
+    long long* dbg;  // LPX_REG_STAMPS=1: per-phase clock64() sums of block 0 (8 slots)
 };
 
-template <int NW, int R, int C, int OCC>
-__global__ void __launch_bounds__(NW * 32, OCC) reg_simplex_kernel(const RegBatch B) {
-    constexpr int ROWS = NW * R;   // padded rows (>= m + 1)
+// NW row warps + 1 control warp.  Row warp w owns constraint rows w*R .. w*R+R-1, lane l the columns
+// l, l+32, .. of those rows.  The control warp (warp NW) owns what every decision needs: the
+// objective row (C entries per lane), the RHS column (rows lane and lane+32) and the objective value.
+// Column slots 0..CR-1 of every thread are registers, slots CR..CR+CS-1 live in shared memory
+// (lane-interleaved, conflict-free): CS = 0 is the all-register build (one CTA per SM), CS = 2 leaves
+// room for two CTAs per SM without spilling, so one CTA's narrow phases hide behind the other's update.
+template <int NW, int R, int CR, int CS, int OCC, bool DBG = false>
+__global__ void __launch_bounds__((NW + 1) * 32, OCC) reg_simplex_kernel(const RegBatch B) {
+    constexpr int C = CR + CS;
+    constexpr int ROWS = NW * R;   // padded constraint rows (>= m)
     constexpr int COLS = 32 * C;   // padded non-RHS columns (>= n + m)
-    __shared__ double s_f[ROWS];   // entering column = update factors
-    __shared__ double s_rhs[ROWS];
-    __shared__ double s_p[COLS + 1];    // normalised pivot row, [COLS] = its RHS
-    __shared__ double s_raw[COLS + 1];  // the leaving row before normalisation
-    __shared__ double s_ratio[ROWS];
+    __shared__ double s_t[(CS ? CS : 1) * (ROWS + 1) * 32];  // [slot][row][lane]; row ROWS = objective row
+    constexpr int NT = (NW + 1) * 32;
+    static_assert(ROWS >= 64 && ROWS <= 96, "the control warp holds the RHS of rows lane and lane+32");
+    __shared__ double s_f[ROWS];     // entering column = update factors
+    __shared__ double s_rhs[ROWS + 1];
+    __shared__ double s_p[COLS];     // normalised pivot row
+    __shared__ double s_raw[COLS];   // the leaving row before normalisation
     __shared__ int s_basis[ROWS];
     __shared__ int s_ctl[4];
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const bool ctl = w == NW;
     const int p = blockIdx.x;
     const int m = B.m, n = B.n, width = n + m + 1;
     const double* Ap = B.A + (size_t)p * m * n;
     const double* bp = B.b + (size_t)p * m;
     const double* cp = B.c + (size_t)p * n;
-    const int wz = m / R, rz = m % R;  // owner of the z-row
 
     // ---- BuildTableau straight into registers (PrimalSimplex.cs:179-203) ---------------------
-    double t[R][C];
-    double rhsv = 0.0;
+    double t[R][CR];       // control warp: t[0][*] is the objective row
+    const int row0 = ctl ? ROWS : w * R;  // first padded row of this warp in s_t
+    // element (r, c) of this thread: a register for c < CR, shared memory otherwise
+#define T_GET(r, c) ((c) < CR ? t[r][(c) < CR ? (c) : 0] : s_t[(((c) - CR) * (ROWS + 1) + row0 + (r)) * 32 + lane])
+#define T_SET(r, c, v)                                                   \
+    do {                                                                 \
+        if ((c) < CR) t[r][(c) < CR ? (c) : 0] = (v);                    \
+        else s_t[(((c) - CR) * (ROWS + 1) + row0 + (r)) * 32 + lane] = (v); \
+    } while (0)
+    // control-warp state lives in the row slots it does not use (t[1..][*]), so that it costs the
+    // row warps no registers: RHS of rows lane / lane+32, objective value, and per-pivot scratch
+    static_assert(R >= 3 && CR >= 4, "control-warp aliases need t[1][0..3] and t[2][0..2]");
+    double &rhs0 = t[1][0], &rhs1 = t[1][1], &zrhs = t[1][2], &a0 = t[1][3], &a1 = t[2][0], &fz = t[2][1],
+           &prhs = t[2][2];
 #pragma unroll
     for (int r = 0; r < R; r++) {
         const int i = w * R + r;
@@ -61,57 +86,72 @@ __global__ void __launch_bounds__(NW * 32, OCC) reg_simplex_kernel(const RegBatc
         for (int c = 0; c < C; c++) {
             const int j = lane + 32 * c;
             double v = 0.0;
-            if (i < m) {
-                if (j < n) v = Ap[(size_t)i * n + j];
-                else if (j == n + i) v = 1.0;
-            } else if (i == m && j < n) {
+            if (!ctl) {
+                if (i < m) {
+                    if (j < n) v = Ap[(size_t)i * n + j];
+                    else if (j == n + i) v = 1.0;
+                }
+            } else if (r == 0 && j < n) {
                 double cj = cp[j];
                 if (B.sense == 1) cj = dneg(cj);
                 v = dneg(cj);
             }
-            t[r][c] = v;
+            if (!ctl || r == 0) T_SET(r, c, v);
+            else if (c < CR) t[r][c < CR ? c : 0] = 0.0;
         }
     }
-    if (lane < R && w * R + lane < m) rhsv = bp[w * R + lane];
+    if (ctl) {
+        if (lane < m) rhs0 = bp[lane];
+        if (lane + 32 < m) rhs1 = bp[lane + 32];
+    }
     // the reference's up-front check (PrimalSimplex.cs:73-76); '>=' rows cannot occur here
     if (tid == 0) s_ctl[1] = LPX_RUNNING;
-    for (int i = tid; i < m; i += NW * 32) s_basis[i] = n + i;
+    for (int i = tid; i < m; i += NT) s_basis[i] = n + i;
     __syncthreads();
-    if (lane < R && w * R + lane < m && rhsv < -1e-9) s_ctl[1] = LPX_S_NEG_RHS;
+    if (ctl && (rhs0 < -1e-9 || rhs1 < -1e-9)) s_ctl[1] = LPX_S_NEG_RHS;
     __syncthreads();
     int status = s_ctl[1];
     int n_piv = 0;
 
     if (status == LPX_RUNNING) {
-        // entering column of the first pivot (ChooseEntering on the initial z-row)
+        // ChooseEntering on the objective row (control warp): most negative entry below -1e-9,
+        // lowest column on ties, NaN never wins.  Two REDUX minima on the value key, one on the
+        // column index.
         auto choose_entering = [&]() {
-            ArgMin a;
-            a.v = -LPX_EPS;
-            a.i = INT_MAX;
+            unsigned long long kk[C], kl = ~0ULL;
 #pragma unroll
-            for (int r = 0; r < R; r++) {
-                if (r == rz) {
-#pragma unroll
-                    for (int c = 0; c < C; c++) {
-                        const double zv = t[r][c];
-                        if (zv < a.v) {
-                            a.v = zv;
-                            a.i = lane + 32 * c;
-                        }
-                    }
-                }
+            for (int c = 0; c < C; c++) {
+                const double zv = T_GET(0, c);
+                kk[c] = zv < -LPX_EPS ? dkey(zv) : ~0ULL;
+                kl = kk[c] < kl ? kk[c] : kl;
             }
-            a = warp_argmin(a);
-            if (lane == 0) s_ctl[0] = a.i == INT_MAX ? -1 : a.i;
+            const unsigned long long K = warp_min_u64(kl);
+            int jl = INT_MAX;
+#pragma unroll
+            for (int c = C - 1; c >= 0; c--)
+                if (kk[c] == K) jl = lane + 32 * c;
+            const int j = __reduce_min_sync(0xffffffffu, jl);
+            if (lane == 0) s_ctl[0] = K == ~0ULL ? -1 : j;
         };
-        if (w == wz) choose_entering();
+        if (ctl) choose_entering();
 
-        // Serial latency, not throughput, bounds a pivot: a double division is a ~40-instruction
-        // dependent chain, so every division below is done by a DIFFERENT thread (ratios: one per
-        // row, lanes 0..R-1 of each warp; pivot row: one per column), never several by one warp.
+        // One pivot = five short phases separated by block barriers.  Latency, not throughput,
+        // bounds it, so the narrow decisions (entering column, ratios, leaving row, RHS) run in the
+        // control warp only — the row warps neither repeat them nor compete for issue slots — and
+        // every division is done by a different thread.
         int iter = 1;
+        long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tk = 0;
+#define REG_STAMP(k)                          \
+    if (DBG) {                                \
+        const long long now_ = clock64();     \
+        ph[k] += now_ - tk;                   \
+        tk = now_;                            \
+    }
+#define REG_CASES(M) M(0) M(1) M(2) M(3) M(4) M(5) M(6) M(7)
+        if (DBG) tk = clock64();
         while (true) {
             __syncthreads();  // (A) s_ctl[0] holds the entering column; all updates are done
+            REG_STAMP(0)
             if (iter > B.max_iter) {
                 status = LPX_S_ITER_LIMIT;
                 break;
@@ -121,131 +161,170 @@ __global__ void __launch_bounds__(NW * 32, OCC) reg_simplex_kernel(const RegBatc
                 status = LPX_OPTIMAL;
                 break;
             }
-            // ---- entering column -> factors and ratios, inside each warp by shuffle -------------
+            // ---- P2: the lanes that own the entering column publish it -----------------------------
             const int ce = e >> 5, le = e & 31;
-            double my_a = 0.0;
-#pragma unroll
-            for (int r = 0; r < R; r++) {
+            if (!ctl) {
+                if (lane == le) {
+#define REG_PUT(K)                                                                                     \
+    case K:                                                                                            \
+        if (K < C) {                                                                                   \
+            _Pragma("unroll") for (int r = 0; r < R; r++) s_f[w * R + r] = T_GET(r, K);                \
+        }                                                                                              \
+        break;
+                    switch (ce) { REG_CASES(REG_PUT) }
+#undef REG_PUT
+                }
+            } else {
                 double v = 0.0;
-#pragma unroll
-                for (int c = 0; c < C; c++)
-                    if (c == ce) v = t[r][c];
-                v = __shfl_sync(0xffffffffu, v, le);
-                if (lane == r) my_a = v;
+#define REG_GET(K)                       \
+    case K:                              \
+        if (K < C) v = T_GET(0, K);      \
+        break;
+                switch (ce) { REG_CASES(REG_GET) }
+#undef REG_GET
+                fz = __shfl_sync(0xffffffffu, v, le);
             }
-            if (lane < R) {
-                const int i = w * R + lane;
-                double ratio = __longlong_as_double(0x7ff8000000000000LL);  // NaN = not eligible
-                if (i < m && my_a > LPX_EPS) ratio = __ddiv_rn(rhsv, my_a);
-                s_f[i] = my_a;
-                s_ratio[i] = ratio;
-            }
+            REG_STAMP(1)
             __syncthreads();  // (B)
-            // ---- ChooseLeaving: every warp repeats the exact sequential scan on the ratios -------
-            const int lr = warp_margin_scan(m, LPX_MARGIN_PRIMAL, [&](int i, double& ratio) {
-                ratio = s_ratio[i];
-                return ratio == ratio;
-            });
+            REG_STAMP(2)
+            // ---- P3 (control warp): ratios, two rows per lane, and ChooseLeaving --------------------
+            if (ctl) {
+                a0 = s_f[lane];
+                a1 = s_f[lane + 32];
+                const double nan = __longlong_as_double(0x7ff8000000000000LL);  // = not eligible
+                const double r0 = (lane < m && a0 > LPX_EPS) ? __ddiv_rn(rhs0, a0) : nan;
+                const double r1 = (lane + 32 < m && a1 > LPX_EPS) ? __ddiv_rn(rhs1, a1) : nan;
+                const int row = warp_margin_scan64(m, LPX_MARGIN_PRIMAL, r0, r1);
+                if (lane == 0) s_ctl[2] = row;
+            }
+            REG_STAMP(3)
+            __syncthreads();  // (C)
+            const int lr = s_ctl[2];
             if (lr < 0) {
                 status = LPX_UNBOUNDED;
                 break;
             }
             const double piv = s_f[lr];
-            // ---- the owner of the leaving row publishes it; one division per thread -------------
+            // ---- P4: the owner of the leaving row publishes it; the control warp normalises its RHS ---
             const int wl = lr / R, rl = lr - wl * R;
             if (w == wl) {
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    if (r == rl) {
-#pragma unroll
-                        for (int c = 0; c < C; c++) s_raw[lane + 32 * c] = t[r][c];
-                    }
-                }
-                if (lane == rl) s_raw[COLS] = rhsv;
+#define REG_RAW(K)                                                                                \
+    case K:                                                                                       \
+        if (K < R) {                                                                              \
+            _Pragma("unroll") for (int c = 0; c < C; c++) s_raw[lane + 32 * c] = T_GET(K < R ? K : 0, c); \
+        }                                                                                         \
+        break;
+                switch (rl) { REG_CASES(REG_RAW) }
+#undef REG_RAW
+            }
+            if (ctl) {
+                const double rl_rhs = __shfl_sync(0xffffffffu, lr < 32 ? rhs0 : rhs1, lr & 31);
+                prhs = __ddiv_rn(rl_rhs, piv);
             }
             __syncthreads();  // (D)
-            for (int j = tid; j <= COLS; j += NW * 32) s_p[j] = __ddiv_rn(s_raw[j], piv);
+            REG_STAMP(4)
+            // ---- P5: one division per thread ------------------------------------------------------
+            if (tid < COLS) s_p[tid] = __ddiv_rn(s_raw[tid], piv);
+            REG_STAMP(5)
             __syncthreads();  // (E)
-            // ---- rank-1 update in registers.  The warp that owns the z-row updates that row
-            // first and picks the NEXT entering column while the other warps are still updating.
-            double f[R];
+            REG_STAMP(6)
+            // ---- P1: rank-1 update in registers; the control warp updates the objective row and the
+            // RHS column and picks the NEXT entering column meanwhile.  Only the warp that owns the
+            // leaving row pays for the "this row becomes the pivot row" select.
+            if (ctl) {
 #pragma unroll
-            for (int r = 0; r < R; r++) f[r] = s_f[w * R + r];
-            if (w == wz) {
-#pragma unroll
-                for (int c = 0; c < C; c++) {
-                    const double pc = s_p[lane + 32 * c];
-#pragma unroll
-                    for (int r = 0; r < R; r++)
-                        if (r == rz) t[r][c] = __dsub_rn(t[r][c], __dmul_rn(f[r], pc));
-                }
+                for (int c = 0; c < C; c++) T_SET(0, c, __dsub_rn(T_GET(0, c), __dmul_rn(fz, s_p[lane + 32 * c])));
                 choose_entering();
+                const double u0 = __dsub_rn(rhs0, __dmul_rn(a0, prhs)), u1 = __dsub_rn(rhs1, __dmul_rn(a1, prhs));
+                rhs0 = lane == lr ? prhs : u0;
+                rhs1 = lane + 32 == lr ? prhs : u1;
+                zrhs = __dsub_rn(zrhs, __dmul_rn(fz, prhs));
+                if (lane == 0) s_basis[lr] = e;
+            } else {
+                double f[R];
 #pragma unroll
-                for (int c = 0; c < C; c++) {
-                    const double pc = s_p[lane + 32 * c];
+                for (int r = 0; r < R; r++) f[r] = s_f[w * R + r];
+                if (w != wl) {
 #pragma unroll
-                    for (int r = 0; r < R; r++) {
-                        if (r != rz) {
-                            const double upd = __dsub_rn(t[r][c], __dmul_rn(f[r], pc));
-                            t[r][c] = (w * R + r == lr) ? pc : upd;
+                    for (int c = 0; c < C; c++) {
+                        const double pc = s_p[lane + 32 * c];
+#pragma unroll
+                        for (int r = 0; r < R; r++) T_SET(r, c, __dsub_rn(T_GET(r, c), __dmul_rn(f[r], pc)));
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < C; c++) {
+                        const double pc = s_p[lane + 32 * c];
+#pragma unroll
+                        for (int r = 0; r < R; r++) {
+                            const double upd = __dsub_rn(T_GET(r, c), __dmul_rn(f[r], pc));
+                            T_SET(r, c, (r == rl) ? pc : upd);
+                        }
+                    }
+                }
+            }
+            n_piv++;
+            iter++;
+            REG_STAMP(7)
+        }
+        __syncthreads();
+        if (DBG && B.dbg && p == 0 && (tid == 0 || tid == NW * 32)) {
+            const int slot = tid == 0 ? 0 : 1;  // row warp 0 and the control warp
+            for (int k = 0; k < 8; k++) B.dbg[slot * 10 + k] = ph[k];
+            B.dbg[slot * 10 + 8] = n_piv;
+        }
+#undef REG_STAMP
+#undef REG_CASES
+
+        // ---- results ----------------------------------------------------------------------------
+        if (ctl) {
+            s_rhs[lane] = rhs0;
+            s_rhs[lane + 32] = rhs1;
+            if (lane == 0) s_rhs[ROWS] = zrhs;
+        }
+        if (B.tableau) {
+            double* To = B.tableau + (size_t)p * (m + 1) * width;
+            if (!ctl) {
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const int i = w * R + r;
+                    if (i < m) {
+#pragma unroll
+                        for (int c = 0; c < C; c++) {
+                            const int j = lane + 32 * c;
+                            if (j < width - 1) To[(size_t)i * width + j] = T_GET(r, c);
                         }
                     }
                 }
             } else {
 #pragma unroll
                 for (int c = 0; c < C; c++) {
-                    const double pc = s_p[lane + 32 * c];
-#pragma unroll
-                    for (int r = 0; r < R; r++) {
-                        const double upd = __dsub_rn(t[r][c], __dmul_rn(f[r], pc));
-                        t[r][c] = (w * R + r == lr) ? pc : upd;
-                    }
+                    const int j = lane + 32 * c;
+                    if (j < width - 1) To[(size_t)m * width + j] = T_GET(0, c);
                 }
+                if (lane < m) To[(size_t)lane * width + width - 1] = rhs0;
+                if (lane + 32 < m) To[(size_t)(lane + 32) * width + width - 1] = rhs1;
+                if (lane == 0) To[(size_t)m * width + width - 1] = zrhs;
             }
-            if (lane < R) {
-                const double pr = s_p[COLS];
-                const double upd = __dsub_rn(rhsv, __dmul_rn(s_f[w * R + lane], pr));
-                rhsv = (w * R + lane == lr) ? pr : upd;
-            }
-            if (tid == 0) s_basis[lr] = e;
-            n_piv++;
-            iter++;
-        }
-        __syncthreads();
-
-        // ---- results ----------------------------------------------------------------------------
-        if (lane < R) s_rhs[w * R + lane] = rhsv;
-        if (B.tableau) {
-            double* To = B.tableau + (size_t)p * (m + 1) * width;
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                const int i = w * R + r;
-                if (i <= m) {
-#pragma unroll
-                    for (int c = 0; c < C; c++) {
-                        const int j = lane + 32 * c;
-                        if (j < width - 1) To[(size_t)i * width + j] = t[r][c];
-                    }
-                }
-            }
-            if (lane < R && w * R + lane <= m) To[(size_t)(w * R + lane) * width + width - 1] = rhsv;
         }
         if (B.x) {
             double* xo = B.x + (size_t)p * n;
-            for (int j = tid; j < n; j += NW * 32) xo[j] = 0.0;
+            for (int j = tid; j < n; j += NT) xo[j] = 0.0;
         }
         __syncthreads();
         if (B.basis)
-            for (int i = tid; i < m; i += NW * 32) B.basis[(size_t)p * m + i] = s_basis[i];
+            for (int i = tid; i < m; i += NT) B.basis[(size_t)p * m + i] = s_basis[i];
         if (tid == 0) {
             if (B.x) {
                 double* xo = B.x + (size_t)p * n;
                 for (int i = 0; i < m; i++)
                     if (s_basis[i] < n) xo[s_basis[i]] = s_rhs[i];
             }
-            if (B.z) B.z[p] = s_rhs[m];
+            if (B.z) B.z[p] = s_rhs[ROWS];
         }
     }
+#undef T_GET
+#undef T_SET
     if (tid == 0) {
         B.status[p] = status;
         if (B.n_pivots) B.n_pivots[p] = n_piv;
@@ -287,8 +366,33 @@ int reg_launch_batched(int count, int m, int n, int sense, const double* A, cons
     // with ~11 doubles per thread spilled to L1-resident local memory (72 registers).  The pivot is
     // bound by its serial latency chain, not by issue rate, so the second CTA per SM wins (measured
     // 2.2 ms vs 2.8 ms per 4096-LP batch); reg_variant = 1 forces the spill-free build.
-    if (opt.reg_variant == 1) reg_simplex_kernel<13, 5, 6, 1><<<count, 13 * 32, 0, stream>>>(B);
-    else reg_simplex_kernel<13, 5, 6, 2><<<count, 13 * 32, 0, stream>>>(B);
+    B.dbg = nullptr;
+    static const bool stamps = getenv("LPX_REG_STAMPS") != nullptr;  // measurement aid, prints to stderr
+    if (stamps) {
+        long long* d = nullptr;
+        LPX_CUDA(cudaMalloc(&d, 30 * sizeof(long long)));
+        LPX_CUDA(cudaMemsetAsync(d, 0, 30 * sizeof(long long), stream));
+        B.dbg = d;
+        if (opt.reg_variant == 1) reg_simplex_kernel<13, 5, 6, 0, 1, true><<<count, 14 * 32, 0, stream>>>(B);
+        else reg_simplex_kernel<13, 5, 4, 2, 2, true><<<count, 14 * 32, 0, stream>>>(B);
+        long long h[30];
+        LPX_CUDA(cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, stream));
+        LPX_CUDA(cudaStreamSynchronize(stream));
+        cudaFree(d);
+        static const char* names[8] = {"syncA", "column", "syncB", "ratio+scan", "raw+syncD", "rowdiv", "syncE",
+                                       "update+entering"};
+        for (int sl = 0; sl < 3; sl++) {
+            fprintf(stderr, "[reg stamps] %s pivots=%lld cycles/pivot:", sl == 0 ? "warp0" : sl == 1 ? "ctl  " : "-    ",
+                    h[sl * 10 + 8]);
+            for (int k = 0; k < 8; k++)
+                fprintf(stderr, " %s=%.0f", names[k], h[sl * 10 + 8] ? (double)h[sl * 10 + k] / h[sl * 10 + 8] : 0.0);
+            fprintf(stderr, "\n");
+        }
+        count_launch();
+        return LPX_OK;
+    }
+    if (opt.reg_variant == 1) reg_simplex_kernel<13, 5, 6, 0, 1><<<count, 14 * 32, 0, stream>>>(B);
+    else reg_simplex_kernel<13, 5, 4, 2, 2><<<count, 14 * 32, 0, stream>>>(B);
     LPX_CUDA(cudaGetLastError());
     count_launch();
     return LPX_OK;

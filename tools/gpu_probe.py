@@ -228,3 +228,9 @@ if __name__ == "__main__":
             dt = time.perf_counter() - t0
             print(json.dumps(dict(call="bnb_knapsack_batched", rep=rep, s=dt, nodes=int(r["n_evals"].sum()),
                                   nodes_per_s=int(r["n_evals"].sum()) / dt)), flush=True)
+    if what == "lat":
+        import ctypes as C
+        out = (C.c_double * 8)()
+        F.check(F.lib().lpx_measure_latencies(out))
+        names = ["DADD", "DMUL", "DDIV", "REDUX", "SHFL", "LDS_roundtrip", "BAR13", "DSETP_SEL"]
+        print(json.dumps({k: round(v, 1) for k, v in zip(names, out)}), flush=True)
