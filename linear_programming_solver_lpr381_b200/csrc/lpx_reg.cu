@@ -117,7 +117,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, OCC) reg_simplex_kernel(const R
         // ChooseEntering on the objective row (control warp): most negative entry below -1e-9,
         // lowest column on ties, NaN never wins.  Two REDUX minima on the value key, one on the
         // column index.
-        auto choose_entering = [&]() {
+        auto choose_entering = [&](int next_iter) {
             unsigned long long kk[C], kl = ~0ULL;
 #pragma unroll
             for (int c = 0; c < C; c++) {
@@ -131,62 +131,53 @@ __global__ void __launch_bounds__((NW + 1) * 32, OCC) reg_simplex_kernel(const R
             for (int c = C - 1; c >= 0; c--)
                 if (kk[c] == K) jl = lane + 32 * c;
             const int j = __reduce_min_sync(0xffffffffu, jl);
-            if (lane == 0) s_ctl[0] = K == ~0ULL ? -1 : j;
+            // one word tells every warp how the next pass starts: the column, -1 = optimal, -2 = the
+            // reference's iteration limit, which it tests BEFORE looking for an entering column
+            if (lane == 0) s_ctl[0] = next_iter > B.max_iter ? -2 : (K == ~0ULL ? -1 : j);
         };
-        if (ctl) choose_entering();
+        if (ctl) choose_entering(1);
 
         // One pivot = five short phases separated by block barriers.  Latency, not throughput,
         // bounds it, so the narrow decisions (entering column, ratios, leaving row, RHS) run in the
         // control warp only — the row warps neither repeat them nor compete for issue slots — and
         // every division is done by a different thread.
         int iter = 1;
-        long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tk = 0;
-#define REG_STAMP(k)                          \
-    if (DBG) {                                \
-        const long long now_ = clock64();     \
-        ph[k] += now_ - tk;                   \
-        tk = now_;                            \
-    }
-#define REG_CASES(M) M(0) M(1) M(2) M(3) M(4) M(5) M(6) M(7)
-        if (DBG) tk = clock64();
+        // DBG build: lane 0 of four warps records its ARRIVAL time at each barrier of pivots 4..7
+        const int dslot = w == 0 ? 0 : w == 5 ? 1 : w == NW - 1 ? 2 : ctl ? 3 : -1;
+#define REG_STAMP(k)                                                                                  \
+    if (DBG && B.dbg && p == 0 && lane == 0 && dslot >= 0 && iter >= 4 && iter < 8)                    \
+        B.dbg[((iter - 4) * 4 + dslot) * 8 + (k)] = clock64();
         while (true) {
             __syncthreads();  // (A) s_ctl[0] holds the entering column; all updates are done
-            REG_STAMP(0)
-            if (iter > B.max_iter) {
-                status = LPX_S_ITER_LIMIT;
-                break;
-            }
             const int e = s_ctl[0];
             if (e < 0) {
-                status = LPX_OPTIMAL;
+                status = e == -2 ? LPX_S_ITER_LIMIT : LPX_OPTIMAL;
                 break;
             }
             // ---- P2: the lanes that own the entering column publish it -----------------------------
             const int ce = e >> 5, le = e & 31;
+            // A chain of warp-uniform branches: predicated-off stores still queue in the memory pipe
+            // (30 slots per warp) and a jump table costs an indirect branch; the empty asm keeps the
+            // compiler from if-converting the bodies.
             if (!ctl) {
-                if (lane == le) {
-#define REG_PUT(K)                                                                                     \
-    case K:                                                                                            \
-        if (K < C) {                                                                                   \
-            _Pragma("unroll") for (int r = 0; r < R; r++) s_f[w * R + r] = T_GET(r, K);                \
-        }                                                                                              \
-        break;
-                    switch (ce) { REG_CASES(REG_PUT) }
+#define REG_PUT(K)                                                                        \
+    if (K < C && ce == K) {                                                               \
+        asm volatile("" ::: "memory");                                                    \
+        if (lane == le) {                                                                 \
+            _Pragma("unroll") for (int r = 0; r < R; r++) s_f[w * R + r] = T_GET(r, K);   \
+        }                                                                                 \
+    }
+                REG_PUT(0) else REG_PUT(1) else REG_PUT(2) else REG_PUT(3) else REG_PUT(4) else REG_PUT(5) else REG_PUT(6) else REG_PUT(7)
 #undef REG_PUT
-                }
             } else {
                 double v = 0.0;
-#define REG_GET(K)                       \
-    case K:                              \
-        if (K < C) v = T_GET(0, K);      \
-        break;
-                switch (ce) { REG_CASES(REG_GET) }
-#undef REG_GET
+#pragma unroll
+                for (int c = 0; c < C; c++)
+                    if (c == ce) v = T_GET(0, c);
                 fz = __shfl_sync(0xffffffffu, v, le);
             }
-            REG_STAMP(1)
+            REG_STAMP(0)
             __syncthreads();  // (B)
-            REG_STAMP(2)
             // ---- P3 (control warp): ratios, two rows per lane, and ChooseLeaving --------------------
             if (ctl) {
                 a0 = s_f[lane];
@@ -197,7 +188,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, OCC) reg_simplex_kernel(const R
                 const int row = warp_margin_scan64(m, LPX_MARGIN_PRIMAL, r0, r1);
                 if (lane == 0) s_ctl[2] = row;
             }
-            REG_STAMP(3)
+            REG_STAMP(1)
             __syncthreads();  // (C)
             const int lr = s_ctl[2];
             if (lr < 0) {
@@ -207,74 +198,80 @@ __global__ void __launch_bounds__((NW + 1) * 32, OCC) reg_simplex_kernel(const R
             const double piv = s_f[lr];
             // ---- P4: the owner of the leaving row publishes it; the control warp normalises its RHS ---
             const int wl = lr / R, rl = lr - wl * R;
+            double f[R];  // this warp's update factors; the all-register build has room to fetch them
+                          // while the pivot row is still being prepared
+            if (CS == 0 && !ctl) {
+#pragma unroll
+                for (int r = 0; r < R; r++) f[r] = s_f[w * R + r];
+            }
             if (w == wl) {
-#define REG_RAW(K)                                                                                \
-    case K:                                                                                       \
-        if (K < R) {                                                                              \
-            _Pragma("unroll") for (int c = 0; c < C; c++) s_raw[lane + 32 * c] = T_GET(K < R ? K : 0, c); \
-        }                                                                                         \
-        break;
-                switch (rl) { REG_CASES(REG_RAW) }
-#undef REG_RAW
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    if (r == rl) {
+#pragma unroll
+                        for (int c = 0; c < C; c++) s_raw[lane + 32 * c] = T_GET(r, c);
+                    }
+                }
             }
-            if (ctl) {
-                const double rl_rhs = __shfl_sync(0xffffffffu, lr < 32 ? rhs0 : rhs1, lr & 31);
-                prhs = __ddiv_rn(rl_rhs, piv);
-            }
+            REG_STAMP(2)
             __syncthreads();  // (D)
-            REG_STAMP(4)
             // ---- P5: one division per thread ------------------------------------------------------
-            if (tid < COLS) s_p[tid] = __ddiv_rn(s_raw[tid], piv);
-            REG_STAMP(5)
+            // (a zero numerator sends the whole warp down the division's slow path, and tableau rows are
+            // full of zeros; 0 / piv with piv > 1e-9 is that same signed zero, so zeros divide a stand-in)
+            if (tid < COLS) {
+                const double raw = s_raw[tid];
+                double num = raw != 0.0 ? raw : 1.0;
+                asm volatile("" : "+d"(num));  // keep the stand-in: the compiler would divide raw again
+                const double q = __ddiv_rn(num, piv);
+                s_p[tid] = raw != 0.0 ? q : raw;
+            } else if (ctl) {
+                const double rl_rhs = __shfl_sync(0xffffffffu, lr < 32 ? rhs0 : rhs1, lr & 31);
+                double num = rl_rhs != 0.0 ? rl_rhs : 1.0;
+                asm volatile("" : "+d"(num));
+                const double q = __ddiv_rn(num, piv);
+                prhs = rl_rhs != 0.0 ? q : rl_rhs;
+            }
+            REG_STAMP(3)
             __syncthreads();  // (E)
-            REG_STAMP(6)
             // ---- P1: rank-1 update in registers; the control warp updates the objective row and the
             // RHS column and picks the NEXT entering column meanwhile.  Only the warp that owns the
             // leaving row pays for the "this row becomes the pivot row" select.
             if (ctl) {
 #pragma unroll
                 for (int c = 0; c < C; c++) T_SET(0, c, __dsub_rn(T_GET(0, c), __dmul_rn(fz, s_p[lane + 32 * c])));
-                choose_entering();
+                choose_entering(iter + 1);
                 const double u0 = __dsub_rn(rhs0, __dmul_rn(a0, prhs)), u1 = __dsub_rn(rhs1, __dmul_rn(a1, prhs));
                 rhs0 = lane == lr ? prhs : u0;
                 rhs1 = lane + 32 == lr ? prhs : u1;
                 zrhs = __dsub_rn(zrhs, __dmul_rn(fz, prhs));
                 if (lane == 0) s_basis[lr] = e;
             } else {
-                double f[R];
+                if (CS != 0) {
 #pragma unroll
-                for (int r = 0; r < R; r++) f[r] = s_f[w * R + r];
-                if (w != wl) {
+                    for (int r = 0; r < R; r++) f[r] = s_f[w * R + r];
+                }
+#pragma unroll
+                for (int c = 0; c < C; c++) {
+                    const double pc = s_p[lane + 32 * c];
+#pragma unroll
+                    for (int r = 0; r < R; r++) T_SET(r, c, __dsub_rn(T_GET(r, c), __dmul_rn(f[r], pc)));
+                }
+                if (w == wl) {  // the leaving row becomes the normalised pivot row
 #pragma unroll
                     for (int c = 0; c < C; c++) {
                         const double pc = s_p[lane + 32 * c];
 #pragma unroll
-                        for (int r = 0; r < R; r++) T_SET(r, c, __dsub_rn(T_GET(r, c), __dmul_rn(f[r], pc)));
-                    }
-                } else {
-#pragma unroll
-                    for (int c = 0; c < C; c++) {
-                        const double pc = s_p[lane + 32 * c];
-#pragma unroll
-                        for (int r = 0; r < R; r++) {
-                            const double upd = __dsub_rn(T_GET(r, c), __dmul_rn(f[r], pc));
-                            T_SET(r, c, (r == rl) ? pc : upd);
-                        }
+                        for (int r = 0; r < R; r++)
+                            if (r == rl) T_SET(r, c, pc);
                     }
                 }
             }
+            REG_STAMP(4)
             n_piv++;
             iter++;
-            REG_STAMP(7)
         }
         __syncthreads();
-        if (DBG && B.dbg && p == 0 && (tid == 0 || tid == NW * 32)) {
-            const int slot = tid == 0 ? 0 : 1;  // row warp 0 and the control warp
-            for (int k = 0; k < 8; k++) B.dbg[slot * 10 + k] = ph[k];
-            B.dbg[slot * 10 + 8] = n_piv;
-        }
 #undef REG_STAMP
-#undef REG_CASES
 
         // ---- results ----------------------------------------------------------------------------
         if (ctl) {
@@ -370,23 +367,25 @@ int reg_launch_batched(int count, int m, int n, int sense, const double* A, cons
     static const bool stamps = getenv("LPX_REG_STAMPS") != nullptr;  // measurement aid, prints to stderr
     if (stamps) {
         long long* d = nullptr;
-        LPX_CUDA(cudaMalloc(&d, 30 * sizeof(long long)));
-        LPX_CUDA(cudaMemsetAsync(d, 0, 30 * sizeof(long long), stream));
+        const int nslots = 4 * 4 * 8;
+        LPX_CUDA(cudaMalloc(&d, nslots * sizeof(long long)));
+        LPX_CUDA(cudaMemsetAsync(d, 0, nslots * sizeof(long long), stream));
         B.dbg = d;
         if (opt.reg_variant == 1) reg_simplex_kernel<13, 5, 6, 0, 1, true><<<count, 14 * 32, 0, stream>>>(B);
         else reg_simplex_kernel<13, 5, 4, 2, 2, true><<<count, 14 * 32, 0, stream>>>(B);
-        long long h[30];
+        long long h[nslots];
         LPX_CUDA(cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, stream));
         LPX_CUDA(cudaStreamSynchronize(stream));
         cudaFree(d);
-        static const char* names[8] = {"syncA", "column", "syncB", "ratio+scan", "raw+syncD", "rowdiv", "syncE",
-                                       "update+entering"};
-        for (int sl = 0; sl < 3; sl++) {
-            fprintf(stderr, "[reg stamps] %s pivots=%lld cycles/pivot:", sl == 0 ? "warp0" : sl == 1 ? "ctl  " : "-    ",
-                    h[sl * 10 + 8]);
-            for (int k = 0; k < 8; k++)
-                fprintf(stderr, " %s=%.0f", names[k], h[sl * 10 + 8] ? (double)h[sl * 10 + k] / h[sl * 10 + 8] : 0.0);
-            fprintf(stderr, "\n");
+        // arrival times at barriers B, C, D, E, A(next), relative to the control warp's arrival at B
+        static const char* wn[4] = {"warp0", "warp5", "warp12", "ctl"};
+        for (int it = 0; it < 4; it++) {
+            const long long t0 = h[(it * 4 + 3) * 8 + 0];
+            for (int sl = 0; sl < 4; sl++) {
+                fprintf(stderr, "[reg arrivals] pivot %d %-6s:", it + 4, wn[sl]);
+                for (int k = 0; k < 5; k++) fprintf(stderr, " %c=%lld", "BCDEA"[k], h[(it * 4 + sl) * 8 + k] - t0);
+                fprintf(stderr, "\n");
+            }
         }
         count_launch();
         return LPX_OK;

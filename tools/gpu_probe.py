@@ -234,3 +234,9 @@ if __name__ == "__main__":
         F.check(F.lib().lpx_measure_latencies(out))
         names = ["DADD", "DMUL", "DDIV", "REDUX", "SHFL", "LDS_roundtrip", "BAR13", "DSETP_SEL"]
         print(json.dumps({k: round(v, 1) for k, v in zip(names, out)}), flush=True)
+    if what == "regcounts":
+        for rv in (1, 2):
+            for cnt in (148, 296, 592, 1184, 4096):
+                print(json.dumps(time_batched(kernel=F.KERNEL_CTA_REG, reg_variant=rv, count=cnt, reps=5)), flush=True)
+    if what == "prof_reg2":
+        print(json.dumps(time_batched(kernel=F.KERNEL_CTA_REG, reg_variant=2, count=1184, reps=1)), flush=True)
