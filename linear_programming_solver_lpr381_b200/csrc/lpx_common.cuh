@@ -153,6 +153,26 @@ __device__ __forceinline__ int warp_margin_scan(int count, double margin, Get ge
     return row;
 }
 
+// num / den for a divisor that is a pivot element or an eligible ratio denominator (|den| > 1e-9,
+// never NaN or zero).  Bit-identical to __ddiv_rn, but a ZERO numerator — tableau rows are full of
+// them — no longer drags its whole warp through the division's slow path (a subroutine call that
+// costs several times the inline sequence): zeros divide a stand-in and return the signed zero that
+// IEEE division gives, sign(num) xor sign(den).
+// Same for a divisor known to be positive (primal pivot elements and ratio denominators).
+__device__ __forceinline__ double ddiv_by_pos(double num, double den) {
+    double n = num != 0.0 ? num : 1.0;
+    asm volatile("" : "+d"(n));
+    const double q = __ddiv_rn(n, den);
+    return num != 0.0 ? q : num;
+}
+__device__ __forceinline__ double ddiv_by_pivot(double num, double den) {
+    double n = num != 0.0 ? num : 1.0;
+    asm volatile("" : "+d"(n));  // opaque, or the compiler folds the stand-in away again
+    const double q = __ddiv_rn(n, den);
+    const double z = den < 0.0 ? __longlong_as_double(__double_as_longlong(num) ^ (long long)0x8000000000000000ULL) : num;
+    return num != 0.0 ? q : z;
+}
+
 // ---- 64-bit keys and REDUX-based warp minima ---------------------------------------------------
 // Order-preserving key of a double: a < b (as doubles)  =>  dkey(a) < dkey(b).  -0.0 sorts just
 // below +0.0 and NaN above +inf; callers that care about -0.0 == +0.0 re-check with a real compare.

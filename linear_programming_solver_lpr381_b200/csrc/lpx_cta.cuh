@@ -97,7 +97,7 @@ __device__ __forceinline__ void cta_pivot(double* T, int ld, int rows, int width
                                           double* fcol) {
     const int tid = threadIdx.x;
     const double piv = T[(size_t)l * ld + e];
-    for (int j = tid; j < width; j += THREADS) prow[j] = __ddiv_rn(T[(size_t)l * ld + j], piv);
+    for (int j = tid; j < width; j += THREADS) prow[j] = ddiv_by_pivot(T[(size_t)l * ld + j], piv);
     for (int i = tid; i < rows; i += THREADS) fcol[i] = T[(size_t)i * ld + e];
     __syncthreads();
     const int cw = (width + 31) & ~31;
@@ -136,7 +136,7 @@ __device__ __forceinline__ void cta_stage_ratios(const double* T, int ld, int m,
     for (int i = threadIdx.x; i < m; i += THREADS) {
         const double a = T[(size_t)i * ld + e];
         double r = __longlong_as_double(0x7ff8000000000000LL);
-        if (a > LPX_EPS) r = __ddiv_rn(T[(size_t)i * ld + rhs], a);
+        if (a > LPX_EPS) r = ddiv_by_pivot(T[(size_t)i * ld + rhs], a);
         prow[i] = r;
     }
     __syncthreads();
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) 
                     for (int j = tid; j < width - 1; j += THREADS) {
                         const double a = lrow[j];
                         double r = __longlong_as_double(0x7ff8000000000000LL);
-                        if (a < -LPX_EPS) r = __ddiv_rn(zrow[j], dneg(a));
+                        if (a < -LPX_EPS) r = ddiv_by_pivot(zrow[j], dneg(a));
                         prow[j] = r;
                     }
                     __syncthreads();

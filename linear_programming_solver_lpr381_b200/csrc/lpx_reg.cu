@@ -216,20 +216,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, OCC) reg_simplex_kernel(const R
             REG_STAMP(2)
             __syncthreads();  // (D)
             // ---- P5: one division per thread ------------------------------------------------------
-            // (a zero numerator sends the whole warp down the division's slow path, and tableau rows are
-            // full of zeros; 0 / piv with piv > 1e-9 is that same signed zero, so zeros divide a stand-in)
             if (tid < COLS) {
-                const double raw = s_raw[tid];
-                double num = raw != 0.0 ? raw : 1.0;
-                asm volatile("" : "+d"(num));  // keep the stand-in: the compiler would divide raw again
-                const double q = __ddiv_rn(num, piv);
-                s_p[tid] = raw != 0.0 ? q : raw;
+                s_p[tid] = ddiv_by_pos(s_raw[tid], piv);
             } else if (ctl) {
                 const double rl_rhs = __shfl_sync(0xffffffffu, lr < 32 ? rhs0 : rhs1, lr & 31);
-                double num = rl_rhs != 0.0 ? rl_rhs : 1.0;
-                asm volatile("" : "+d"(num));
-                const double q = __ddiv_rn(num, piv);
-                prhs = rl_rhs != 0.0 ? q : rl_rhs;
+                prhs = ddiv_by_pos(rl_rhs, piv);
             }
             REG_STAMP(3)
             __syncthreads();  // (E)
@@ -311,14 +302,12 @@ __global__ void __launch_bounds__((NW + 1) * 32, OCC) reg_simplex_kernel(const R
         __syncthreads();
         if (B.basis)
             for (int i = tid; i < m; i += NT) B.basis[(size_t)p * m + i] = s_basis[i];
-        if (tid == 0) {
-            if (B.x) {
-                double* xo = B.x + (size_t)p * n;
-                for (int i = 0; i < m; i++)
-                    if (s_basis[i] < n) xo[s_basis[i]] = s_rhs[i];
-            }
-            if (B.z) B.z[p] = s_rhs[ROWS];
+        if (B.x) {  // basic decision variables take their row's RHS (distinct rows, distinct targets)
+            double* xo = B.x + (size_t)p * n;
+            for (int i = tid; i < m; i += NT)
+                if (s_basis[i] < n) xo[s_basis[i]] = s_rhs[i];
         }
+        if (tid == 0 && B.z) B.z[p] = s_rhs[ROWS];
     }
 #undef T_GET
 #undef T_SET

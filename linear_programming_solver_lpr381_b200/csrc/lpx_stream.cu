@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(1024) stream_select_kernel(StreamParams P, int
     for (int i = tid; i < m; i += 1024) {
         const double a = col[i];
         double r = __longlong_as_double(0x7ff8000000000000LL);
-        if (a > LPX_EPS) r = __ddiv_rn(P.rhsbuf[i], a);
+        if (a > LPX_EPS) r = ddiv_by_pos(P.rhsbuf[i], a);
         P.ratio[i] = r;
     }
     __syncthreads();
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(1024) stream_select_kernel(StreamParams P, int
     a.i = INT_MAX;
     const int ncand = P.width - 1;
     for (int j = tid; j < P.ld; j += 1024) {
-        const double pj = __ddiv_rn(Tl[j], piv);
+        const double pj = ddiv_by_pos(Tl[j], piv);
         P.prow[j] = pj;
         Tl[j] = pj;
         if (j < ncand) {
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(LPX_PREP_THREADS) stream_prep_kernel(StreamPar
         for (int u = 0; u < 4; u++) {
             const int i = base + u * TH + tid;
             double r = __longlong_as_double(0x7ff8000000000000LL);  // NaN: never eligible
-            if (a[u] > LPX_EPS) r = __ddiv_rn(bb[u], a[u]);
+            if (a[u] > LPX_EPS) r = ddiv_by_pos(bb[u], a[u]);
             if (i < m) s_ratio[i] = r;
         }
     }
@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(LPX_PREP_THREADS) stream_prep_kernel(StreamPar
     a.i = INT_MAX;
     if (j < P.ld) {
         double* Tl = P.T + (size_t)l * P.ld;
-        const double pj = __ddiv_rn(Tl[j], piv);
+        const double pj = ddiv_by_pos(Tl[j], piv);
         if (j < P.width - 1) {
             const double zn = __dsub_rn(P.T[(size_t)m * P.ld + j], __dmul_rn(fz, pj));
             if (zn < a.v) {

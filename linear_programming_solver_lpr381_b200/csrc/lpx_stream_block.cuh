@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(1024) stream_lookahead_kernel(StreamParams P, 
                     col[i] = v;
                     if (i < m) {
                         double r = __longlong_as_double(0x7ff8000000000000LL);
-                        if (v > LPX_EPS) r = __ddiv_rn(rhs[i], v);
+                        if (v > LPX_EPS) r = ddiv_by_pos(rhs[i], v);
                         ratio[i] = r;
                     }
                 }
@@ -172,14 +172,14 @@ __global__ void __launch_bounds__(1024) stream_lookahead_kernel(StreamParams P, 
             for (int u = 0; u < 8; u++) {
                 const int j = base + u * TH + tid;
                 if (j < ld) {
-                    const double pj = __ddiv_rn(r8[u], piv);
+                    const double pj = ddiv_by_pos(r8[u], piv);
                     pout[j] = pj;
                     if (j < width - 1) z[j] = __dsub_rn(z[j], __dmul_rn(fz, pj));
                 }
             }
         }
         // ---- RHS column and bookkeeping ----------------------------------------------------------
-        const double prhs = __ddiv_rn(rhs[l], piv);
+        const double prhs = ddiv_by_pos(rhs[l], piv);
         __syncthreads();  // every thread has read rhs[l]; z is complete for the next argmin
         LPX_STAMP(4);
         double* fout = P.Fbuf + (size_t)cnt * cs;
@@ -473,7 +473,7 @@ __global__ void __cluster_dims__(LPX_LA_CLUSTER, 1, 1) __launch_bounds__(LPX_LA_
             double r = __longlong_as_double(0x7ff8000000000000LL);
             if (row_i < m) {
                 const double a = col[row_i];
-                if (a > LPX_EPS) r = __ddiv_rn(rhs[row_i], a);
+                if (a > LPX_EPS) r = ddiv_by_pos(rhs[row_i], a);
             }
             ratio[i] = r;
         }
@@ -520,7 +520,7 @@ __global__ void __cluster_dims__(LPX_LA_CLUSTER, 1, 1) __launch_bounds__(LPX_LA_
             for (int u = 0; u < 2; u++) {
                 const int j = base + u * TH + tid;
                 if (j < j_hi) {
-                    const double pj = __ddiv_rn(r2[u], piv);
+                    const double pj = ddiv_by_pos(r2[u], piv);
                     pout[j] = pj;
                     if (j < width - 1) zloc[j - j_lo] = __dsub_rn(zloc[j - j_lo], __dmul_rn(fz, pj));
                 }
@@ -528,7 +528,7 @@ __global__ void __cluster_dims__(LPX_LA_CLUSTER, 1, 1) __launch_bounds__(LPX_LA_
         }
         // ---- RHS (every CTA keeps the full vector), factor column slice, bookkeeping ------------
         if (P.dbg && rank == 0 && tid == 0 && cnt == 2) P.dbg[4] = lpx_gtime();
-        const double prhs = __ddiv_rn(rhs[l], piv);
+        const double prhs = ddiv_by_pos(rhs[l], piv);
         __syncthreads();
         double* fout = P.Fbuf + (size_t)cnt * cs;
         for (int i = tid; i < rows; i += TH) {

@@ -156,7 +156,7 @@ __global__ void __cluster_dims__(LPX_LA_CLUSTER, 1, 1) __launch_bounds__(LPX_LA_
                     // the ratio of the row travels with the column entry (one division per thread here
                     // instead of eight per thread after the all-gather)
                     double r = __longlong_as_double(0x7ff8000000000000LL);
-                    if (i < m && c[u] > LPX_EPS) r = __ddiv_rn(rhs[i], c[u]);
+                    if (i < m && c[u] > LPX_EPS) r = ddiv_by_pos(rhs[i], c[u]);
                     const int slot = (i % Q) * TH + i / Q;  // permuted position of row i
 #pragma unroll
                     for (int rk = 0; rk < CL; rk++) {
@@ -210,7 +210,7 @@ __global__ void __cluster_dims__(LPX_LA_CLUSTER, 1, 1) __launch_bounds__(LPX_LA_
             for (int u = 0; u < 2; u++) {
                 const int j = base + u * TH + tid;
                 if (j < j_hi) {
-                    const double pj = __ddiv_rn(r2[u], piv);
+                    const double pj = ddiv_by_pos(r2[u], piv);
                     pout[j] = pj;
                     if (j < width - 1) zloc[j - j_lo] = __dsub_rn(zloc[j - j_lo], __dmul_rn(fz, pj));
                 }
@@ -218,7 +218,7 @@ __global__ void __cluster_dims__(LPX_LA_CLUSTER, 1, 1) __launch_bounds__(LPX_LA_
         }
         // ---- RHS (every CTA keeps the full vector), factor column slice, bookkeeping ------------
         if (P.dbg && rank == 0 && tid == 0 && cnt == 2) P.dbg[4] = lpx_gtime();
-        const double prhs = __ddiv_rn(rhs[l], piv);
+        const double prhs = ddiv_by_pos(rhs[l], piv);
         __syncthreads();
         double* fout = P.Fbuf + (size_t)(par * LPX_PIPE_K + cnt) * cs;
         for (int i = tid; i < rows; i += TH) {
