@@ -1,17 +1,27 @@
 // lpx_reg.cu — register-resident batched Primal Simplex (BASELINE config 2: 64 x 128).
 //
-// One CTA per tableau, the tableau lives in REGISTERS for the whole solve: warp w owns rows
-// w*R .. w*R+R-1, lane l owns columns l, l+32, .., l+32(C-1) of those rows (R*C doubles per
-// thread); the RHS column is spread over lanes 0..R-1 of each warp.  Per pivot only three small
-// vectors cross shared memory — the entering column (factors), the RHS and the normalised pivot
-// row — so shared-memory traffic drops from 2 x 100 KB per pivot (lpx_cta.cuh) to ~3 KB and the
-// rank-1 update issues at the FP64 rate: R*C unfused DMUL + DSUB per thread, 97 % of them useful
-// at 65 x 193 with NW = 13, R = 5, C = 6.
+// One CTA per tableau, the tableau lives in REGISTERS for the whole solve.  13 row warps: warp w
+// owns constraint rows w*5 .. w*5+4, lane l the columns l, l+32, .. of those rows (30 doubles per
+// thread).  One control warp owns what every decision needs — the objective row, the RHS column
+// and the objective value — and makes the two decisions alone, so that the row warps neither
+// repeat them nor compete with them for issue slots.  Per pivot only three small vectors cross
+// shared memory: the entering column (= update factors), the raw leaving row and its quotients.
+//
+// A pivot is five short phases between block barriers (measured with ncu's PC sampling, cycles at
+// one CTA per SM): row warps publish the entering column (~460) | control warp: ratios, two rows
+// per lane, and the leaving row (~700) | the owner warp publishes the leaving row (~300) | 192
+// threads divide it, one division each (~300) | rank-1 update, R*C unfused DMUL + DSUB per thread,
+// while the control warp updates the objective row / RHS and picks the NEXT entering column (~840).
+// The chain is latency, not throughput: FP64 pipe < 20 % busy, so two CTAs per SM are kept
+// resident (CS = 2 of the 6 column slots move to shared memory to fit 72 registers, no spills)
+// and one CTA's narrow phases hide behind the other's update.
 //
 // Same rules, same order, same rounding as the reference (R/Models/PrimalSimplex.cs:205-257):
-// entering = warp-shuffle argmin with lowest index on ties, leaving = exact sequential margin
-// scan (every warp repeats it on the staged vectors instead of waiting for a broadcast), pivot =
-// true division then separate multiply and subtract, zero-factor rows included.
+// entering = most negative objective entry below -1e-9, lowest index on ties, as two REDUX minima
+// over an order-preserving key plus one over the index; leaving = the sequential margin scan,
+// answered by one REDUX min + one ballot when no other ratio lies within the margin of the minimum
+// (warp_margin_scan64) and replayed exactly otherwise; pivot = true division then separate multiply
+// and subtract, zero-factor rows included.
 #include <cstdio>
 #include <cstdlib>
 
@@ -348,10 +358,9 @@ int reg_launch_batched(int count, int m, int n, int sense, const double* A, cons
     B.z = z;
     B.tableau = tableau;
     B.total_pivots = total_pivots;
-    // Two builds: one CTA per SM with everything in registers (122 registers), or two CTAs per SM
-    // with ~11 doubles per thread spilled to L1-resident local memory (72 registers).  The pivot is
-    // bound by its serial latency chain, not by issue rate, so the second CTA per SM wins (measured
-    // 2.2 ms vs 2.8 ms per 4096-LP batch); reg_variant = 1 forces the spill-free build.
+    // Two builds: all six column slots in registers, one CTA per SM (reg_variant = 1), or four in
+    // registers + two in shared memory at 72 registers without spills, two CTAs per SM (default:
+    // 1.08 ms vs 1.34 ms per 4096-LP batch).
     B.dbg = nullptr;
     static const bool stamps = getenv("LPX_REG_STAMPS") != nullptr;  // measurement aid, prints to stderr
     if (stamps) {
