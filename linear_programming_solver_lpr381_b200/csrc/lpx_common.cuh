@@ -59,69 +59,72 @@ __device__ __forceinline__ ArgMin warp_argmin(ArgMin a) {
     return a;
 }
 
-// Block-wide "most negative entry below thresh, lowest index on ties" over v[0..n).
-// Returns -1 when no entry is < thresh.  NaN entries never win (comparison is false).
-// red: shared scratch of at least 33 ArgMin.  Ends with a barrier: red may be reused at once.
-template <int THREADS>
-__device__ __forceinline__ int block_argmin_below(const double* v, int n, double thresh, ArgMin* red) {
-    ArgMin a;
-    a.v = thresh;
-    a.i = INT_MAX;
-    for (int j = threadIdx.x; j < n; j += THREADS) {
-        double z = v[j];
-        if (z < a.v) {
-            a.v = z;
-            a.i = j;
-        }
-    }
-    a = warp_argmin(a);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) red[warp] = a;
-    __syncthreads();
-    if (warp == 0) {
-        ArgMin b;
-        b.v = thresh;
-        b.i = INT_MAX;
-        if (lane < THREADS / 32) b = red[lane];
-        b = warp_argmin(b);
-        if (lane == 0) red[32] = b;
-    }
-    __syncthreads();
-    int idx = red[32].i;
-    __syncthreads();
-    return idx == INT_MAX ? -1 : idx;
+// ---- 64-bit keys and REDUX-based warp minima ---------------------------------------------------
+// Order-preserving key of a double: a < b (as doubles)  =>  dkey(a) < dkey(b).  -0.0 sorts just
+// below +0.0 and NaN above +inf; callers that care about -0.0 == +0.0 re-check with a real compare.
+__device__ __forceinline__ unsigned long long dkey(double x) {
+    const long long b = __double_as_longlong(x);
+    return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ULL));
+}
+__device__ __forceinline__ double dkey_inv(unsigned long long k) {
+    const long long b = (long long)k;
+    return __longlong_as_double(b < 0 ? (b ^ (long long)0x8000000000000000ULL) : ~b);
+}
+// Warp minimum of a 64-bit key with two 32-bit REDUX instructions (no shuffle ladder).
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long k) {
+    const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+    const unsigned hmin = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned lmin = __reduce_min_sync(0xffffffffu, hi == hmin ? lo : 0xffffffffu);
+    return ((unsigned long long)hmin << 32) | lmin;
 }
 
+// Block-wide "most negative entry below thresh, lowest index on ties" over load(0..n).
+// Returns -1 when no entry is < thresh.  NaN entries never win (comparison is false).
+// Per warp: REDUX minimum of the value keys, then of the indices that hold it; the per-warp partials
+// meet in shared memory and EVERY warp reduces them itself, so one barrier publishes the answer
+// (the second one only frees `red`, >= 33 ArgMin, for immediate reuse).
+template <int THREADS, class Load>
+__device__ __forceinline__ int block_argmin_core(int n, double thresh, ArgMin* red, Load load) {
+    unsigned long long kl = ~0ULL;
+    int il = INT_MAX;
+    for (int j = threadIdx.x; j < n; j += THREADS) {
+        const double z = load(j);
+        if (z < thresh) {
+            const unsigned long long k = dkey(z);
+            if (k < kl) {
+                kl = k;
+                il = j;
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long K = warp_min_u64(kl);
+    const int iw = __reduce_min_sync(0xffffffffu, kl == K ? il : INT_MAX);
+    if (lane == 0) {
+        red[warp].v = __longlong_as_double((long long)K);
+        red[warp].i = iw;
+    }
+    __syncthreads();
+    unsigned long long k2 = ~0ULL;
+    int i2 = INT_MAX;
+    if (lane < THREADS / 32) {
+        k2 = (unsigned long long)__double_as_longlong(red[lane].v);
+        i2 = red[lane].i;
+    }
+    const unsigned long long K2 = warp_min_u64(k2);
+    const int idx = __reduce_min_sync(0xffffffffu, k2 == K2 ? i2 : INT_MAX);
+    __syncthreads();
+    return K2 == ~0ULL ? -1 : idx;
+}
+template <int THREADS>
+__device__ __forceinline__ int block_argmin_below(const double* v, int n, double thresh, ArgMin* red) {
+    return block_argmin_core<THREADS>(n, thresh, red, [&](int j) { return v[j]; });
+}
 // Same with a stride between consecutive entries (column scans of a row-major tableau).
 template <int THREADS>
 __device__ __forceinline__ int block_argmin_below_strided(const double* v, size_t stride, int n, double thresh,
                                                           ArgMin* red) {
-    ArgMin a;
-    a.v = thresh;
-    a.i = INT_MAX;
-    for (int j = threadIdx.x; j < n; j += THREADS) {
-        double z = v[(size_t)j * stride];
-        if (z < a.v) {
-            a.v = z;
-            a.i = j;
-        }
-    }
-    a = warp_argmin(a);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) red[warp] = a;
-    __syncthreads();
-    if (warp == 0) {
-        ArgMin b;
-        b.v = thresh;
-        b.i = INT_MAX;
-        if (lane < THREADS / 32) b = red[lane];
-        b = warp_argmin(b);
-        if (lane == 0) red[32] = b;
-    }
-    __syncthreads();
-    int idx = red[32].i;
-    __syncthreads();
-    return idx == INT_MAX ? -1 : idx;
+    return block_argmin_core<THREADS>(n, thresh, red, [&](int j) { return v[(size_t)j * stride]; });
 }
 
 // The reference's ratio test is NOT an argmin:
@@ -173,48 +176,60 @@ __device__ __forceinline__ double ddiv_by_pivot(double num, double den) {
     return num != 0.0 ? q : z;
 }
 
-// ---- 64-bit keys and REDUX-based warp minima ---------------------------------------------------
-// Order-preserving key of a double: a < b (as doubles)  =>  dkey(a) < dkey(b).  -0.0 sorts just
-// below +0.0 and NaN above +inf; callers that care about -0.0 == +0.0 re-check with a real compare.
-__device__ __forceinline__ unsigned long long dkey(double x) {
-    const long long b = __double_as_longlong(x);
-    return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ULL));
-}
-__device__ __forceinline__ double dkey_inv(unsigned long long k) {
-    const long long b = (long long)k;
-    return __longlong_as_double(b < 0 ? (b ^ (long long)0x8000000000000000ULL) : ~b);
-}
-// Warp minimum of a 64-bit key with two 32-bit REDUX instructions (no shuffle ladder).
-__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long k) {
-    const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
-    const unsigned hmin = __reduce_min_sync(0xffffffffu, hi);
-    const unsigned lmin = __reduce_min_sync(0xffffffffu, hi == hmin ? lo : 0xffffffffu);
-    return ((unsigned long long)hmin << 32) | lmin;
-}
-
-// ChooseLeaving for up to 64 rows held two per lane (r0 = row lane, r1 = row lane + 32; NaN = not
-// eligible).  Fast path: the plain minimum (lowest index) IS the sequential margin scan's answer
-// whenever every other eligible ratio r_j satisfies  min < r_j - margin  — then whatever record
-// precedes the minimum, the minimum is accepted after it, and nothing after it can be.  One REDUX
-// min + one ballot certify that; anything closer than the margin (ties, near-ties, -0.0 vs +0.0)
-// falls back to the exact replay.
+// Certified shortcut of the margin scan.  Let v be the minimum eligible ratio and i* its lowest row.
+// If v is the ONLY eligible ratio with  !(v < r_j - margin)  (v itself always is one), then whatever
+// record b precedes i*,  v < b - margin  (monotone in b), so i* is accepted, and nothing after it can
+// be (r_k < v - margin <= v is impossible): the sequential answer is i*.  One REDUX minimum and a
+// count decide that; ties, near-ties inside the margin and -0.0 / +0.0 pairs fail the certificate and
+// take the exact replay.
+//
+// Up to 64 rows held two per lane (r0 = row lane, r1 = row lane + 32; NaN = not eligible).
 __device__ __forceinline__ int warp_margin_scan64(int count, double margin, double r0, double r1) {
-    const int lane = threadIdx.x & 31;
     const unsigned long long k0 = dkey(r0), k1 = dkey(r1);
+    const double d0 = __dsub_rn(r0, margin), d1 = __dsub_rn(r1, margin);  // off the critical path
     const unsigned long long K = warp_min_u64(k1 < k0 ? k1 : k0);
     const double vmin = dkey_inv(K);
     if (vmin != vmin) return -1;  // no eligible row
     const unsigned b0 = __ballot_sync(0xffffffffu, k0 == K);
     const unsigned b1 = __ballot_sync(0xffffffffu, k1 == K);
-    const int imin = b0 ? __ffs(b0) - 1 : 32 + __ffs(b1) - 1;
-    // other eligible rows that are NOT more than the margin above the minimum
-    const bool close0 = (r0 == r0) && lane != imin && !(vmin < __dsub_rn(r0, margin));
-    const bool close1 = (r1 == r1) && lane + 32 != imin && !(vmin < __dsub_rn(r1, margin));
-    if (!__any_sync(0xffffffffu, close0 || close1) && vmin < __longlong_as_double(0x7ff0000000000000LL)) return imin;
+    const unsigned c0 = __ballot_sync(0xffffffffu, (r0 == r0) && !(vmin < d0));
+    const unsigned c1 = __ballot_sync(0xffffffffu, (r1 == r1) && !(vmin < d1));
+    if (__popc(c0) + __popc(c1) == 1 && vmin < __longlong_as_double(0x7ff0000000000000LL))
+        return b0 ? __ffs(b0) - 1 : 32 + __ffs(b1) - 1;
     return warp_margin_scan(count, margin, [&](int i, double& ratio) {
         ratio = i < 32 ? r0 : r1;
         return ratio == ratio;
     });
+}
+
+// Any number of candidates, read through get(i, r) -> eligible (cheap, called up to three times per
+// candidate).  Must be called by all 32 lanes of the warp.
+template <class Get>
+__device__ __forceinline__ int warp_margin_scan_cert(int count, double margin, Get get) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long kl = ~0ULL;
+    for (int i = lane; i < count; i += 32) {
+        double r;
+        if (get(i, r)) {
+            const unsigned long long k = dkey(r);
+            kl = k < kl ? k : kl;
+        }
+    }
+    const unsigned long long K = warp_min_u64(kl);
+    if (K == ~0ULL) return -1;
+    const double vmin = dkey_inv(K);
+    int il = INT_MAX, close = 0;
+    for (int i = lane; i < count; i += 32) {
+        double r;
+        if (get(i, r)) {
+            if (dkey(r) == K && i < il) il = i;
+            if (!(vmin < __dsub_rn(r, margin))) close++;
+        }
+    }
+    const int imin = __reduce_min_sync(0xffffffffu, il);
+    const int nclose = __reduce_add_sync(0xffffffffu, close);
+    if (nclose == 1 && vmin < __longlong_as_double(0x7ff0000000000000LL)) return imin;
+    return warp_margin_scan(count, margin, get);
 }
 
 __device__ __forceinline__ double neg_if(double v, bool flip) {

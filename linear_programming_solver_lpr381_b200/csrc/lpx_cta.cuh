@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) 
                 if (e < 0) break;
                 cta_stage_ratios<THREADS>(T, ld, m, e, rhs, prow);
                 if (warp == 0) {
-                    const int l = warp_margin_scan(m, LPX_MARGIN_DUAL, [&](int i, double& r) {
+                    const int l = warp_margin_scan_cert(m, LPX_MARGIN_DUAL, [&](int i, double& r) {
                         r = prow[i];
                         return r == r;
                     });
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) 
                 // ChooseLeaving: sequential margin scan over rows with T[i,e] > 1e-9
                 cta_stage_ratios<THREADS>(T, ld, m, e, rhs, prow);
                 if (warp == 0) {
-                    const int lv = warp_margin_scan(m, LPX_MARGIN_PRIMAL, [&](int i, double& r) {
+                    const int lv = warp_margin_scan_cert(m, LPX_MARGIN_PRIMAL, [&](int i, double& r) {
                         r = prow[i];
                         return r == r;
                     });
@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) 
                     __syncthreads();
                 }
                 if (warp == 0) {
-                    const int ev = warp_margin_scan(width - 1, LPX_MARGIN_DUAL, [&](int j, double& r) {
+                    const int ev = warp_margin_scan_cert(width - 1, LPX_MARGIN_DUAL, [&](int j, double& r) {
                         r = prow[j];
                         return r == r;
                     });
@@ -403,9 +403,8 @@ __global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) 
             double* xo = B.x + (size_t)p * n;
             for (int j = tid; j < n; j += THREADS) xo[j] = 0.0;
             __syncthreads();
-            if (tid == 0)
-                for (int i = 0; i < m; i++)
-                    if (sbasis[i] < n) xo[sbasis[i]] = T[(size_t)i * ld + rhs];
+            for (int i = tid; i < m; i += THREADS)  // distinct rows, distinct basic variables
+                if (sbasis[i] < n) xo[sbasis[i]] = T[(size_t)i * ld + rhs];
         }
         if (B.z && tid == 0) B.z[p] = T[(size_t)m * ld + rhs];
         if (B.tableau && (SMEM_T || T != B.tableau + (size_t)p * B.tableau_stride))

@@ -250,6 +250,48 @@ BEALE_B = np.array([0.0, 0.0, 1.0])
 BEALE_C = np.array([0.75, -20.0, 0.5, -6.0])
 
 
+@pytest.mark.parametrize("reg_variant", [1, 2])
+def test_register_kernel_near_ties_and_signed_zeros(lpx, orc, reg_variant):
+    """The certified shortcut of the leaving-row scan must hand ties, near-ties inside the 1e-9
+    margin, zero ratios and -0.0 / +0.0 pairs to the exact replay (PrimalSimplex.cs:222-243)."""
+    rng = np.random.default_rng(5)
+    count, m, n = 96, 16, 6
+    A = rng.integers(1, 6, size=(count, m, n)).astype(np.float64)
+    b = np.empty((count, m))
+    c = rng.integers(1, 9, size=(count, n)).astype(np.float64)
+    for k in range(count):
+        base = float(rng.integers(2, 9))
+        # ratios of column j are b_i / A_ij: make whole groups of rows tie, or differ by less /
+        # slightly more than the margin, in shuffled order
+        eps = rng.choice([0.0, 2e-10, 6e-10, 9.9e-10, 1.1e-9, 3e-9], size=m)
+        b[k] = (base + eps) * A[k, :, 0]
+        if k % 3 == 0:
+            b[k, rng.integers(0, m, size=3)] = 0.0          # degenerate rows: zero ratios, signed zeros later
+        if k % 4 == 0:
+            A[k, rng.integers(0, m), :] *= -1.0             # rows that are never eligible in some columns
+        rng.shuffle(b[k])
+    b = np.abs(b)
+    want = orc.primal_batch(A, b, c, threads=8, want_tableau=True)
+    got = lpx.primal_solve_batched(A, b, c, kernel=F.KERNEL_CTA_REG, reg_variant=reg_variant)
+    assert np.array_equal(got["status"], want["status"])
+    assert np.array_equal(got["n_pivots"], want["n_pivots"])
+    assert np.array_equal(got["basis"], want["basis"])
+    assert_bits_equal(got["tableau"], want["tableau"], "tableau")
+    assert_bits_equal(got["x"], want["x"], "x")
+    # the cases are only worth something if the margin rule really differs from a plain argmin on them
+    plain = 0
+    for k in range(count):
+        T0 = np.zeros((m + 1, n + m + 1))
+        T0[:m, :n], T0[:m, n:n + m], T0[:m, -1], T0[m, :n] = A[k], np.eye(m), b[k], -c[k]
+        e = int(np.argmin(T0[m, :-1]))
+        col = T0[:m, e]
+        ratios = np.where(col > 1e-9, T0[:m, -1] / np.where(col > 1e-9, col, 1.0), np.inf)
+        first = orc.primal_solve(A[k], b[k], c[k], None, 0)["pivots"]
+        if len(first) and int(np.argmin(ratios)) != int(first[0][1]):
+            plain += 1
+    assert plain > 0
+
+
 @pytest.mark.parametrize("kernel", KERNELS)
 def test_cycling_lp_hits_the_iteration_limit(lpx, orc, kernel):
     """Beale's example cycles under Dantzig + lowest-index ties: the reference throws "Iteration
