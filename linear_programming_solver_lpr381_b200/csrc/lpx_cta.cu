@@ -322,8 +322,12 @@ int lpx_primal_solve_batched(int count, int m, int n, int sense, const double* A
     LPX_CUDA(cudaMemsetAsync(dtot, 0, 8, r.h2d));
 
     // Three-stage pipeline over chunks of the batch: H2D | solve | D2H on three streams, so that
-    // PCIe traffic in both directions overlaps the kernels.
+    // PCIe traffic in both directions overlaps the kernels.  The result copy is the long pole (the
+    // tableaux are 1.5x the inputs), so large batches ramp the chunk size up — 1, 2, 4, 5, 5, ... 32nds —
+    // and the first results start down the link after a 32nd of the upload instead of an 8th.
     const int chunks = count >= 1024 ? 8 : (count >= 64 ? 4 : 1);
+    static const int ramp[9] = {0, 1, 3, 7, 12, 17, 22, 27, 32};
+    auto bound = [&](int k) -> size_t { return chunks == 8 ? cnt * ramp[k] / 32 : cnt * k / chunks; };
     std::vector<cudaEvent_t> up(chunks), done(chunks);
     for (int k = 0; k < chunks; k++) {
         LPX_CUDA(cudaEventCreateWithFlags(&up[k], cudaEventDisableTiming));
@@ -331,7 +335,7 @@ int lpx_primal_solve_batched(int count, int m, int n, int sense, const double* A
     }
     int result = LPX_OK;
     for (int k = 0; k < chunks && result == LPX_OK; k++) {
-        const size_t lo = cnt * k / chunks, hi = cnt * (k + 1) / chunks, len = hi - lo;
+        const size_t lo = bound(k), hi = bound(k + 1), len = hi - lo;
         if (len == 0) continue;
         LPX_CUDA(cudaMemcpyAsync(dA + lo * m * n, A + lo * m * n, len * m * n * 8, cudaMemcpyHostToDevice, r.h2d));
         LPX_CUDA(cudaMemcpyAsync(db + lo * m, b + lo * m, len * m * 8, cudaMemcpyHostToDevice, r.h2d));

@@ -240,3 +240,23 @@ if __name__ == "__main__":
                 print(json.dumps(time_batched(kernel=F.KERNEL_CTA_REG, reg_variant=rv, count=cnt, reps=5)), flush=True)
     if what == "prof_reg2":
         print(json.dumps(time_batched(kernel=F.KERNEL_CTA_REG, reg_variant=2, count=1184, reps=1)), flush=True)
+    if what == "kblock":
+        # pipelined C3 session at several look-ahead block sizes
+        A, b, c = workloads.large_c3()
+        for kb in (8, 10, 12, 16):
+            s = api.Session(A, b, c, max_iterations=1 << 30, kblock=kb)
+            ss = torch.cuda.ExternalStream(s.stream)
+            per = 240  # multiple of 8, 10, 12, 16
+            for _ in range(2):
+                s.step_async(per)
+            s.sync()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(ss)
+            for k in range(3):
+                s.step_async(per)
+            e1.record(ss)
+            st, tot = s.sync()
+            us = e0.elapsed_time(e1) * 1e3 / (3 * per)
+            s.close()
+            print(json.dumps(dict(kblock=kb, us_per_pivot=us, pivots_per_s=1e6 / us, status=int(st))), flush=True)
