@@ -241,6 +241,54 @@ __device__ __forceinline__ int la_leaving_scan(const double* ratio, int m, int Q
     constexpr int TH = LPX_LA_THREADS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    // ---- certified shortcut (see warp_margin_scan64 in lpx_common.cuh): the minimum ratio at its
+    // lowest row is the sequential answer when it is the only eligible ratio r with !(min < r - margin).
+    // Two block reductions, each published by one barrier and finished by every warp on its own.
+    {
+        unsigned long long kl = ~0ULL;
+        for (int u = 0; u < Q; u++) {
+            const int i = tid * Q + u;
+            if (i < m) {
+                const double r = ratio[u * TH + tid];
+                if (r == r) {
+                    const unsigned long long k = dkey(r);
+                    kl = k < kl ? k : kl;
+                }
+            }
+        }
+        const unsigned long long Kw = warp_min_u64(kl);
+        if (lane == 0) s_wmin[warp] = __longlong_as_double((long long)Kw);
+        __syncthreads();
+        const unsigned long long k2 = lane < TH / 32 ? (unsigned long long)__double_as_longlong(s_wmin[lane]) : ~0ULL;
+        const unsigned long long K = warp_min_u64(k2);
+        if (K == ~0ULL) {
+            __syncthreads();  // s_wmin is free again
+            return -1;        // no eligible row
+        }
+        const double vmin = dkey_inv(K);
+        int il = INT_MAX, close = 0;
+        for (int u = 0; u < Q; u++) {
+            const int i = tid * Q + u;
+            if (i < m) {
+                const double r = ratio[u * TH + tid];
+                if (r == r) {
+                    if (dkey(r) == K && i < il) il = i;
+                    if (!(vmin < __dsub_rn(r, LPX_MARGIN_PRIMAL))) close++;
+                }
+            }
+        }
+        const int iw = __reduce_min_sync(0xffffffffu, il);
+        const int cw = __reduce_add_sync(0xffffffffu, close);
+        if (lane == 0) {
+            s_ired[warp] = iw;
+            s_wcnt[warp] = cw;
+        }
+        __syncthreads();
+        const int imin = __reduce_min_sync(0xffffffffu, lane < TH / 32 ? s_ired[lane] : INT_MAX);
+        const int nclose = __reduce_add_sync(0xffffffffu, lane < TH / 32 ? s_wcnt[lane] : 0);
+        __syncthreads();  // the scratch arrays are free again
+        if (nclose == 1 && vmin < INF) return imin;
+    }
     double lmin = INF;
     for (int u = 0; u < Q; u++) {
         const int i = tid * Q + u;

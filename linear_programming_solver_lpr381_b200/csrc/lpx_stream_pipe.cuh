@@ -70,42 +70,60 @@ __global__ void __cluster_dims__(LPX_LA_CLUSTER, 1, 1) __launch_bounds__(LPX_LA_
     if (tid < pc) s_L[tid] = P.Lbuf[q * LPX_PIPE_K + tid];
     __syncthreads();
 
+    // ChooseEntering, first half: this CTA's z-slice argmin (REDUX minima on the value key, then on the
+    // index), pushed into every CTA's s_part through distributed shared memory.  The cluster barrier
+    // that follows — (3) of the previous pivot, or the one before the loop — publishes it, so a pivot
+    // costs two cluster barriers plus this one, not three plus one.
+    auto push_entering_candidates = [&]() {
+        unsigned long long kl = ~0ULL;
+        int il = INT_MAX;
+        for (int j = j_lo + tid; j < j_hi && j < width - 1; j += TH) {
+            const double zv = zloc[j - j_lo];
+            if (zv < -LPX_EPS) {
+                const unsigned long long kk = dkey(zv);
+                if (kk < kl) {
+                    kl = kk;
+                    il = j;
+                }
+            }
+        }
+        const unsigned long long K = warp_min_u64(kl);
+        const int iw = __reduce_min_sync(0xffffffffu, kl == K ? il : INT_MAX);
+        if (lane == 0) {
+            red[warp].v = __longlong_as_double((long long)K);
+            red[warp].i = iw;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long k2 = ~0ULL;
+            int i2 = INT_MAX;
+            if (lane < TH / 32) {
+                k2 = (unsigned long long)__double_as_longlong(red[lane].v);
+                i2 = red[lane].i;
+            }
+            const unsigned long long K2 = warp_min_u64(k2);
+            const int idx = __reduce_min_sync(0xffffffffu, k2 == K2 ? i2 : INT_MAX);
+            if (lane < CL) {
+                ArgMin b2;
+                b2.v = K2 == ~0ULL ? -LPX_EPS : dkey_inv(K2);
+                b2.i = idx;
+                ArgMin* dst = cluster.map_shared_rank(s_part, lane);
+                dst[rank] = b2;
+            }
+        }
+    };
+
     const int steps = probe ? 1 : min(min(budget, P.kblock), LPX_PIPE_K);
     int cnt = 0, st = LPX_RUNNING;
+    push_entering_candidates();
+    cluster.sync();
     for (int k = 0; k < steps; k++) {
         if (done + cnt >= P.max_iter) {
             st = LPX_S_ITER_LIMIT;
             break;
         }
         if (P.dbg && rank == 0 && tid == 0 && cnt == 2) P.dbg[0] = lpx_gtime();
-        // ---- ChooseEntering: slice argmin, exchanged through distributed shared memory -----------
-        {
-            ArgMin a;
-            a.v = -LPX_EPS;
-            a.i = INT_MAX;
-            for (int j = j_lo + tid; j < j_hi && j < width - 1; j += TH) {
-                const double zv = zloc[j - j_lo];
-                if (zv < a.v) {
-                    a.v = zv;
-                    a.i = j;
-                }
-            }
-            a = warp_argmin(a);
-            if (lane == 0) red[warp] = a;
-            __syncthreads();
-            if (warp == 0) {
-                ArgMin b2;
-                b2.v = -LPX_EPS;
-                b2.i = INT_MAX;
-                if (lane < TH / 32) b2 = red[lane];
-                b2 = warp_argmin(b2);
-                if (lane < CL) {
-                    ArgMin* dst = cluster.map_shared_rank(s_part, lane);
-                    dst[rank] = b2;
-                }
-            }
-        }
-        cluster.sync();  // (1)
+        // ---- ChooseEntering, second half: combine the CL slice candidates -------------------------
         if (P.dbg && rank == 0 && tid == 0 && cnt == 2) P.dbg[1] = lpx_gtime();
         ArgMin g = s_part[0];
 #pragma unroll
@@ -238,6 +256,8 @@ __global__ void __cluster_dims__(LPX_LA_CLUSTER, 1, 1) __launch_bounds__(LPX_LA_
             }
         }
         cnt++;
+        __syncthreads();              // zloc is complete
+        push_entering_candidates();   // for the NEXT pivot, published by the barrier below
         __threadfence();
         cluster.sync();  // (3) Pbuf / Fbuf slices of this pivot are visible to the whole cluster
         if (P.dbg && rank == 0 && tid == 0 && cnt == 3) P.dbg[5] = lpx_gtime();
