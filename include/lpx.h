@@ -78,6 +78,7 @@ typedef struct lpx_options {
 #define LPX_KERNEL_CTA_GLOBAL  2   /* one CTA per tableau, tableau in global memory (L2/HBM) */
 #define LPX_KERNEL_STREAM      3   /* one tableau over the whole GPU, HBM-streamed rank-1 pivots */
 #define LPX_KERNEL_CTA_REG     4   /* one CTA per tableau, tableau resident in registers */
+#define LPX_KERNEL_CTA_CLUSTER 5   /* one 2- or 4-CTA cluster per tableau, rows split over their shared memories */
 
 void lpx_default_options(lpx_options* opt);
 

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "liblpx.so")
 OPTIMAL, UNBOUNDED, INFEASIBLE, RUNNING = 0, 1, 2, 3
 S_GE_ROW, S_NEG_RHS, S_ITER_LIMIT = -1, -2, -3
 E_BAD_ARGS, E_CUDA, E_CAPACITY, E_NCCL = -4, -5, -8, -9
-KERNEL_AUTO, KERNEL_CTA_SMEM, KERNEL_CTA_GLOBAL, KERNEL_STREAM, KERNEL_CTA_REG = 0, 1, 2, 3, 4
+KERNEL_AUTO, KERNEL_CTA_SMEM, KERNEL_CTA_GLOBAL, KERNEL_STREAM, KERNEL_CTA_REG, KERNEL_CTA_CLUSTER = 0, 1, 2, 3, 4, 5
 BNB_WANT_HISTORY = 1
 
 # every symbol include/lpx.h declares; tests check that the library exports all of them

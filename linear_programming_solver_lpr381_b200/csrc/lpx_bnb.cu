@@ -13,6 +13,9 @@
 // Simplex, whose result has no Solution/Tableau, so SolveNode rejects it ("Invalid Simplex
 // result").  It is still solved (it is a _solver.Solve call and its tableaux are part of the
 // iteration log) but never branches.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -185,8 +188,13 @@ struct Driver {
         return LPX_OK;
     }
 
+    // LPX_BNB_TRACE=1: wall time, launches, nodes and pivots per kernel kind, printed by run()
+    double tr_time[2] = {0, 0};
+    long tr_launch[2] = {0, 0}, tr_nodes[2] = {0, 0}, tr_piv[2] = {0, 0};
+
     int launch_group(std::vector<Node*>& G, size_t lo, size_t hi, int pivots_cap, int history_cap) {
         Runtime& r = rt();
+        const auto tr_t0 = std::chrono::steady_clock::now();
         const int cnt = (int)(hi - lo);
         int max_extra = 0;
         size_t total_extra = 0;
@@ -295,6 +303,13 @@ struct Driver {
         LPX_CUDA(cudaMemcpyAsync(h_x, d_x, (size_t)cnt * n * 8, cudaMemcpyDeviceToHost, s));
         LPX_CUDA(cudaMemcpyAsync(h_z, d_z, (size_t)cnt * 8, cudaMemcpyDeviceToHost, s));
         LPX_CUDA(cudaStreamSynchronize(s));
+        {
+            const int kind = fits ? 0 : 1;
+            tr_time[kind] += std::chrono::duration<double>(std::chrono::steady_clock::now() - tr_t0).count();
+            tr_launch[kind]++;
+            tr_nodes[kind] += cnt;
+            for (int k = 0; k < cnt; k++) tr_piv[kind] += h_stat[cnt + k];
+        }
         for (int k = 0; k < cnt; k++) {
             Node* nd = G[lo + k];
             nd->evaluated = true;
@@ -497,7 +512,14 @@ struct Driver {
                 if (!I.finished)
                     for (auto& nd : I.stack)
                         if (!nd->evaluated) todo.push_back(nd.get());
-            if (todo.empty()) break;
+            if (todo.empty()) {
+                if (getenv("LPX_BNB_TRACE"))
+                    for (int kind = 0; kind < 2; kind++)
+                        fprintf(stderr, "[bnb trace] %s kernel: %.3f s, %ld launches, %ld nodes, %ld pivots\n",
+                                kind ? "cluster / global-memory" : "shared-memory", tr_time[kind], tr_launch[kind], tr_nodes[kind],
+                                tr_piv[kind]);
+                break;
+            }
             int rc = evaluate(todo, want_history);
             if (rc != LPX_OK) return rc;
             for (Instance& I : inst) {

@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "lpx_cta.cuh"
+#include "lpx_cta_cluster.cuh"
 #include "lpx_runtime.hpp"
 #include "lpx_stream.hpp"
 
@@ -24,11 +25,58 @@ static int launch_variant(const CtaBatch& B, int count, size_t smem, cudaStream_
     return LPX_OK;
 }
 
+bool cta_cluster_fits(int max_rows, int max_width, int cl) {
+    return cta_cluster_carve(max_rows, max_width, cl).total <= (size_t)max_smem_optin();
+}
+
+// smallest cluster (2 or 4 CTAs) whose combined shared memory holds the tableau; 0 = none
+int cta_cluster_size_for(int max_rows, int max_width) {
+    if (cta_cluster_fits(max_rows, max_width, 2)) return 2;
+    if (cta_cluster_fits(max_rows, max_width, 4)) return 4;
+    return 0;
+}
+
+template <int CL>
+static int launch_cluster_variant(const CtaBatch& B, int count, cudaStream_t stream) {
+    auto kfn = cta_cluster_simplex_kernel<512, CL>;
+    const size_t smem = cta_cluster_carve(B.max_rows, B.max_width, CL).total;
+    LPX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)count * CL, 1, 1);
+    cfg.blockDim = dim3(512, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    LPX_CUDA(cudaLaunchKernelEx(&cfg, kfn, B));
+    count_launch();
+    return LPX_OK;
+}
+
 int cta_launch(const CtaBatch& B, int count, int kernel_pref, int threads_pref, cudaStream_t stream,
                bool* used_smem) {
     if (count <= 0) return LPX_OK;
     bool smem_T = cta_fits_smem(B.max_rows, B.max_width);
     if (kernel_pref == LPX_KERNEL_CTA_GLOBAL) smem_T = false;
+    // Too large for one SM's shared memory: a cluster of 2 or 4 CTAs keeps it on chip
+    // (lpx_cta_cluster.cuh); only beyond that does the tableau go to global memory.
+    if (kernel_pref == LPX_KERNEL_CTA_CLUSTER || (kernel_pref == LPX_KERNEL_AUTO && !smem_T)) {
+        const int cl = cta_cluster_size_for(B.max_rows, B.max_width);
+        if (cl == 0 && kernel_pref == LPX_KERNEL_CTA_CLUSTER) {
+            set_error("tableau does not fit the shared memory of a 4-CTA cluster (LPX_KERNEL_CTA_CLUSTER forced)");
+            return LPX_E_CAPACITY;
+        }
+        if (cl) {
+            if (used_smem) *used_smem = true;
+            return cl == 2 ? launch_cluster_variant<2>(B, count, stream) : launch_cluster_variant<4>(B, count, stream);
+        }
+    }
     if (kernel_pref == LPX_KERNEL_CTA_SMEM && !smem_T) {
         set_error("tableau does not fit in shared memory (LPX_KERNEL_CTA_SMEM forced)");
         return LPX_E_CAPACITY;
@@ -205,7 +253,8 @@ int lpx_primal_solve(int m, int n, int sense, const double* A, const int* rel, c
         const size_t elems = (size_t)(mm + 1) * (n + mm + 1);
         kernel = (cta_fits_smem(mm + 1, n + mm + 1) || elems <= (size_t)96 * 1024) ? LPX_KERNEL_CTA_SMEM
                                                                                     : LPX_KERNEL_STREAM;
-        if (kernel == LPX_KERNEL_CTA_SMEM && !cta_fits_smem(mm + 1, n + mm + 1)) kernel = LPX_KERNEL_CTA_GLOBAL;
+        if (kernel == LPX_KERNEL_CTA_SMEM && !cta_fits_smem(mm + 1, n + mm + 1))
+            kernel = cta_cluster_size_for(mm + 1, n + mm + 1) ? LPX_KERNEL_CTA_CLUSTER : LPX_KERNEL_CTA_GLOBAL;
         if (history && history_cap > 0 && kernel == LPX_KERNEL_STREAM) kernel = LPX_KERNEL_CTA_GLOBAL;
     }
     if (kernel == LPX_KERNEL_STREAM)

@@ -10,7 +10,7 @@ from linear_programming_solver_lpr381_b200 import workloads
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = [F.KERNEL_AUTO, F.KERNEL_CTA_SMEM, F.KERNEL_CTA_GLOBAL, F.KERNEL_STREAM]
+KERNELS = [F.KERNEL_AUTO, F.KERNEL_CTA_SMEM, F.KERNEL_CTA_GLOBAL, F.KERNEL_STREAM, F.KERNEL_CTA_CLUSTER]
 LP_NAMES = ["wyndor", "unbounded", "degenerate_tie", "near_tie_margin", "near_tie_margin_rev", "eq_expansion",
             "min_trivial", "min_negative_costs", "ge_row", "neg_rhs", "neg_rhs_tolerated", "iter_limit_hit",
             "iter_limit_ok", "zero_cost_negzero", "klee_minty3"]
@@ -46,7 +46,7 @@ def test_primal_kat(lpx, kat, name, kernel):
     assert_bits_equal(r["tableau"], unhex(case["tableau"]), "tableau")
 
 
-@pytest.mark.parametrize("kernel", [F.KERNEL_CTA_SMEM, F.KERNEL_CTA_GLOBAL])
+@pytest.mark.parametrize("kernel", [F.KERNEL_CTA_SMEM, F.KERNEL_CTA_GLOBAL, F.KERNEL_CTA_CLUSTER])
 def test_history_matches_oracle(lpx, orc, kernel):
     p = orc.parse_text(workloads.WYNDOR_TEXT)
     want = orc.primal_solve(p["A"], p["b"], p["c"], p["rel"], p["sense"], history=True)
@@ -59,7 +59,7 @@ def test_history_matches_oracle(lpx, orc, kernel):
 
 
 @pytest.mark.parametrize("name", ["dual_ge", "dual_mixed", "dual_eq", "dual_infeasible", "dual_ge_child_becomes_le"])
-@pytest.mark.parametrize("kernel", [F.KERNEL_CTA_SMEM, F.KERNEL_CTA_GLOBAL])
+@pytest.mark.parametrize("kernel", [F.KERNEL_CTA_SMEM, F.KERNEL_CTA_GLOBAL, F.KERNEL_CTA_CLUSTER])
 def test_dual_kat(lpx, kat, name, kernel):
     case = kat["dual"][name]
     A, b, c, rel = case_arrays(case)
@@ -103,8 +103,34 @@ def test_random_dual_vs_oracle(lpx, orc):
         assert_bits_equal(got["x"], want["x"], f"dual x {t}")
 
 
+@pytest.mark.parametrize("shape", [(100, 130), (150, 150), (180, 220), (60, 300)])
+def test_cluster_kernel_mid_size_primal_and_dual(lpx, orc, shape):
+    """Tableaux too large for one SM's shared memory: AUTO takes the 2- or 4-CTA cluster kernel
+    (rows split over the cluster, exchanges through distributed shared memory); same bits as the
+    global-memory kernel and the oracle, primal and dual, with and without the iteration history."""
+    m, n = shape
+    A, b, c = workloads.lp_integer(m, n, 5 + m)
+    want = orc.primal_solve(A, b, c, history=False)
+    for kernel in (F.KERNEL_CTA_CLUSTER, F.KERNEL_AUTO):
+        got = lpx.primal_solve(A, b, c, kernel=kernel)
+        compare_primal(got, want, f"{m}x{n} kernel={kernel}")
+    rng = np.random.default_rng(m + n)
+    rel = rng.choice([0, 0, 1, 2], size=m).astype(np.int32)
+    want = orc.dual_solve(A, b, c, rel, 1)
+    got = lpx.dual_solve(A, b, c, rel, 1, kernel=F.KERNEL_CTA_CLUSTER)
+    assert got["status"] == want["status"] and got["silent"] == want["silent"]
+    assert got["pivots"].tolist() == want["pivots"].tolist()
+    assert got["basis"].tolist() == want["basis"].tolist()
+    assert_bits_equal(got["tableau"], want["tableau"], "dual tableau")
+    assert_bits_equal(got["x"], want["x"], "dual x")
+    if m <= 100:
+        w = orc.primal_solve(A[:, :40], b, c[:40], history=True)
+        g = lpx.primal_solve(A[:, :40], b, c[:40], history=w["n_pivots"] + 1, kernel=F.KERNEL_CTA_CLUSTER)
+        assert_bits_equal(g["history"], w["history"], "history")
+
+
 def test_tie_free_decimal_mid_size(lpx, orc):
-    for kernel in (F.KERNEL_CTA_SMEM, F.KERNEL_CTA_GLOBAL, F.KERNEL_STREAM):
+    for kernel in (F.KERNEL_CTA_SMEM, F.KERNEL_CTA_GLOBAL, F.KERNEL_STREAM, F.KERNEL_CTA_CLUSTER):
         A, b, c = workloads.lp_decimal(40, 70, 12)
         want = orc.primal_solve(A, b, c)
         got = lpx.primal_solve(A, b, c, kernel=kernel)
