@@ -13,7 +13,9 @@
 // Simplex, whose result has no Solution/Tableau, so SolveNode rejects it ("Invalid Simplex
 // result").  It is still solved (it is a _solver.Solve call and its tableaux are part of the
 // iteration log) but never branches.
+#include <atomic>
 #include <chrono>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
@@ -122,6 +124,16 @@ int expanded_rows(int m, const int* rel) {
     int mm = 0;
     for (int i = 0; i < m; i++) mm += (rel && rel[i] == 2) ? 2 : 1;
     return mm;
+}
+
+// host threads for the per-instance commit: LPX_HOST_THREADS, else min(8, half the cores)
+inline int host_threads() {
+    static const int n = [] {
+        if (const char* e = getenv("LPX_HOST_THREADS")) return std::max(1, atoi(e));
+        const unsigned hw = std::thread::hardware_concurrency();
+        return (int)std::max(1u, std::min(8u, hw / 2));
+    }();
+    return n;
 }
 
 struct Driver {
@@ -522,7 +534,10 @@ struct Driver {
             }
             int rc = evaluate(todo, want_history);
             if (rc != LPX_OK) return rc;
-            for (Instance& I : inst) {
+            // SolveNode bodies of the evaluated nodes.  Instances are independent trees, so without a
+            // callback (whose records must arrive in order on the calling thread) they commit on a few
+            // host threads: IsFeasible alone is m x n multiplies per node.
+            auto commit_instance = [&](Instance& I) {
                 while (!I.finished && !I.stack.empty() && I.stack.back()->evaluated) {
                     std::unique_ptr<Node> nd = std::move(I.stack.back());
                     I.stack.pop_back();
@@ -530,6 +545,23 @@ struct Driver {
                     else commit_node(I, std::move(nd));
                 }
                 if (I.stack.empty()) I.finished = true;
+            };
+            const int nthreads = (on_node || count < 32) ? 1 : host_threads();
+            if (nthreads <= 1) {
+                for (Instance& I : inst) commit_instance(I);
+            } else {
+                std::atomic<int> next(0);
+                auto worker = [&]() {
+                    for (;;) {
+                        const int lo = next.fetch_add(8);
+                        if (lo >= count) break;
+                        for (int k = lo; k < std::min(count, lo + 8); k++) commit_instance(inst[k]);
+                    }
+                };
+                std::vector<std::thread> pool;
+                for (int t = 1; t < nthreads; t++) pool.emplace_back(worker);
+                worker();
+                for (std::thread& th : pool) th.join();
             }
         }
         return LPX_OK;
