@@ -41,6 +41,15 @@ def load_peaks():
     return 6650.0, "fallback"
 
 
+def measured_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            return json.load(f)[kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """SM clock and throttle reasons while the timed region runs: NVML polled every 2 ms from a
     thread (the timed region of the default workload is ~10-50 ms, too short for `nvidia-smi -lms`),
@@ -290,7 +299,8 @@ def run_ours(args):
         return dict(value=pivots_s, ms_per_step=total_ms / steps, launches=launches, rows=rows, cols=cols,
                     pivots_per_step=per_step, clocks=clocks,
                     roofline={"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                              "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_kind,
+                              "frac": ach / hbm_peak, "traffic": measured_traffic("stream_update_pipe_tma_kernel"),
+                              "peak_source": peak_kind,
                               "kernel": "stream_update_pipe_tma_kernel (one TMA-staged HBM pass applying a block of pivots; "
                                         "timed alone, the look-ahead of the next block normally runs beside it)",
                               "algorithmic_bytes_per_launch": bytes_per_pass, "launch_us": pass_us,
@@ -376,7 +386,8 @@ def run_ours(args):
         ach_tf = flops_per_pivot * pivots / (sum(ms) * 1e-3) / 1e12
         hbm_bytes = (A.nbytes + b.nbytes + c.nbytes) + T.numel() * 8 + x.numel() * 8 + basis.numel() * 4
         roof = {"bound": "fp64", "achieved": ach_tf, "peak": rate.value, "unit": "TFLOP/s",
-                "frac": ach_tf / rate.value if rate.value else None, "traffic": None,
+                "frac": ach_tf / rate.value if rate.value else None,
+                "traffic": measured_traffic("reg_simplex_kernel"),
                 "peak_source": "measured in this run: unfused DMUL+DADD issue rate (lpx_measure_fp64_rate); FMA is "
                                "excluded by the bit-exactness contract",
                 "flops_per_pivot": flops_per_pivot,

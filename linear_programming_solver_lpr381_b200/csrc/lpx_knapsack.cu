@@ -14,6 +14,9 @@
 // its own max-heap with the reference's sift rules (:494-547), left child before right child,
 // incumbent updates exactly where the C# code makes them.  Speculative results that were not
 // consumed stay cached under their heap node.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -773,7 +776,14 @@ struct KnDriver {
         }
 
         int stalled = 0;
+        double tr[3] = {0, 0, 0};  // LPX_KNAP_TRACE=1: seconds in plan / device rounds / commit
+        long tr_rounds = 0;
+        auto now = [] { return std::chrono::steady_clock::now(); };
+        auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+            return std::chrono::duration<double>(b - a).count();
+        };
         while (true) {
+            const auto t0 = now();
             Plan pl;
             bool any = false;
             for (int k = 0; k < count; k++) {
@@ -799,9 +809,17 @@ struct KnDriver {
                     taken++;
                 }
             }
-            if (!any) break;
+            if (!any) {
+                if (getenv("LPX_KNAP_TRACE"))
+                    fprintf(stderr, "[knap trace] %ld rounds: plan %.3f s, device %.3f s, commit %.3f s\n", tr_rounds, tr[0],
+                            tr[1], tr[2]);
+                break;
+            }
+            const auto t1 = now();
             int rc = run_plan(pl);
             if (rc != LPX_OK) return rc;
+            const auto t2 = now();
+            tr_rounds++;
             bool progressed = false;
             // unlink evaluations the device skipped, so they can be planned again later
             for (int id : pl.roots) prune_skipped(id);
@@ -813,6 +831,9 @@ struct KnDriver {
                 if (rc != LPX_OK) return rc;
                 if (I.pops != before || I.done) progressed = true;
             }
+            tr[0] += secs(t0, t1);
+            tr[1] += secs(t1, t2);
+            tr[2] += secs(t2, now());
             stalled = progressed ? 0 : stalled + 1;
             if (stalled > 2 || (!progressed && pl.in.empty())) {
                 set_error("knapsack: no progress possible (node pool exhausted?)");

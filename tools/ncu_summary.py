@@ -54,19 +54,36 @@ def main():
                     except ValueError:
                         pass
         src = page(rep, "source")
-        if len(src) > 2 and "Source" in src[1]:
-            hdr = src[1]
+        # one section per launch: a "Kernel Name" line, the column header, then one row per instruction
+        sections, cur = [], None
+        for r in src:
+            if r and r[0] == "Kernel Name":
+                cur = {"name": r[1] if len(r) > 1 else "", "hdr": None, "rows": []}
+                sections.append(cur)
+            elif cur is not None and cur["hdr"] is None and "Source" in r:
+                cur["hdr"] = r
+            elif cur is not None and cur["hdr"] is not None and len(r) == len(cur["hdr"]):
+                cur["rows"].append(r)
+        for si, sec in enumerate(sections[:1]):
+            hdr, data = sec["hdr"], sec["rows"]
+            if not hdr or "# Samples" not in hdr:
+                continue
             ix = {h: i for i, h in enumerate(hdr)}
-            data = [r for r in src[2:] if len(r) == len(hdr)]
+
+            def num(r, k):
+                try:
+                    return int(r[ix[k]] or 0)
+                except ValueError:
+                    return 0
             bars = [i for i, r in enumerate(data) if "BAR.SYNC" in r[ix["Source"]] or "BARRIER.SYNC" in r[ix["Source"]]]
             if bars:
                 lines.append([f"## {label}: PC samples per barrier interval (SASS index range, samples, instructions, top stalls)"])
                 prev = 0
                 for b in bars + [len(data)]:
                     hi = min(b + 1, len(data))
-                    n = sum(int(r[ix["# Samples"]] or 0) for r in data[prev:hi])
-                    ins = sum(int(r[ix["Instructions Executed"]] or 0) for r in data[prev:hi])
-                    st = {k[6:]: sum(int(r[ix[k]] or 0) for r in data[prev:hi]) for k in STALLS if k in ix}
+                    n = sum(num(r, "# Samples") for r in data[prev:hi])
+                    ins = sum(num(r, "Instructions Executed") for r in data[prev:hi])
+                    st = {k[6:]: sum(num(r, k) for r in data[prev:hi]) for k in STALLS if k in ix}
                     top = " ".join(f"{k}={v}" for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:5] if v)
                     lines.append([f"[{prev},{b}]", n, ins, top])
                     prev = b + 1
