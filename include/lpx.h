@@ -45,7 +45,9 @@ extern "C" {
 #define LPX_RUNNING            3   /* session not finished yet */
 #define LPX_S_GE_ROW          -1   /* exception, R/Models/PrimalSimplex.cs:68-71 */
 #define LPX_S_NEG_RHS         -2   /* exception, R/Models/PrimalSimplex.cs:73-76 */
-#define LPX_S_ITER_LIMIT      -3   /* exception, R/Models/PrimalSimplex.cs:95-96, DualSimplex.cs:39 */
+#define LPX_S_ITER_LIMIT      -3   /* exception, R/Models/PrimalSimplex.cs:95-96, DualSimplex.cs:39, RevisedPrimalSimplex.cs:144 */
+#define LPX_S_REV_UNSUPPORTED -10  /* exception, R/Models/RevisedPrimalSimplex.cs:19-21 (needs all <= rows, b >= -1e-9) */
+#define LPX_S_SINGULAR        -11  /* exception, R/Models/RevisedPrimalSimplex.cs:433 "Singular basis encountered." */
 
 /* ---- call-level error codes ----------------------------------------------------------------- */
 #define LPX_OK                 0
@@ -243,6 +245,22 @@ int lpx_comm_allgather(const void* send, void* recv, size_t bytes_per_rank);  /*
 void lpx_comm_destroy(void);
 int lpx_comm_world(void);
 int lpx_comm_rank(void);
+
+/* ---- Revised Primal Simplex ------------------------------------------------------------------- */
+/* RevisedPrimalSimplex.Solve (R/Models/RevisedPrimalSimplex.cs:17-145): price-out with the basis
+ * inverse recomputed by Gauss-Jordan (partial pivoting) every iteration, left-to-right dot products,
+ * ratio margin 1e-12.  status: LPX_OPTIMAL / LPX_UNBOUNDED / LPX_S_ITER_LIMIT / LPX_S_REV_UNSUPPORTED /
+ * LPX_S_SINGULAR.  pivots: 2 ints per iteration (entering column, leaving ROW = basis position),
+ * theta: the chosen ratio.  basis (m) = Bidx, nonbasic (n) = Nidx in the reference's list order,
+ * xB (m), Binv (m x m, row-major), x (n) = basic decision variables mapped back.
+ * history (nullable): history_cap records of lpx_revised_history_stride(m, n) doubles, one per
+ * BuildIterationBlock call (:62, :134): [Binv m*m][x_B m][z][r_N n][d m][theta][Bidx m][Nidx n][entering],
+ * integers stored as doubles; record 0 is the initial basis (r_N, d, theta unused, entering -1). */
+int lpx_revised_solve(int m, int n, int sense, const double* A, const int* rel, const double* b, const double* c,
+                      const lpx_options* opt, int* status, int* n_iters, int* pivots, double* theta, int pivots_cap,
+                      int* basis, int* nonbasic, double* xB, double* Binv, double* x, double* history,
+                      int history_cap);
+size_t lpx_revised_history_stride(int m, int n);
 
 /* ---- measurement helpers (bench.py) --------------------------------------------------------- */
 /* Unfused FP64 rate (separate DMUL and DADD, the only arithmetic the bit-exactness contract

@@ -74,6 +74,32 @@ def dual_solve(A, b, c, rel=None, sense=0, max_iterations=10000, kernel=F.KERNEL
     return out
 
 
+def revised_solve(A, b, c, rel=None, sense=0, max_iterations=10000, cap=16384, history=0):
+    """lpx_revised_solve: RevisedPrimalSimplex numerics (pivots, theta, final basis state)."""
+    A, b, c, rel = _prep(A, b, c, rel)
+    m, n = A.shape
+    opt = F.make_options(max_iterations)
+    status, n_iters = C.c_int(), C.c_int()
+    pivots = np.full((cap, 2), -1, dtype=np.int32)
+    theta = np.zeros(cap)
+    basis, nonbasic = np.zeros(m, dtype=np.int32), np.zeros(n, dtype=np.int32)
+    xB, Binv, x = np.zeros(m), np.zeros((m, m)), np.zeros(n)
+    L = F.lib()
+    L.lpx_revised_history_stride.restype = C.c_size_t
+    hs = L.lpx_revised_history_stride(m, n)
+    hist = np.zeros((history, hs)) if history else None
+    rc = L.lpx_revised_solve(m, n, sense, F.ptr(A), F.ptr(rel), F.ptr(b), F.ptr(c), C.byref(opt), C.byref(status),
+                             C.byref(n_iters), F.ptr(pivots), F.ptr(theta), cap, F.ptr(basis), F.ptr(nonbasic), F.ptr(xB),
+                             F.ptr(Binv), F.ptr(x), F.ptr(hist), history)
+    F.check(rc)
+    k = min(n_iters.value, cap)
+    out = dict(status=status.value, n_iters=n_iters.value, enter=pivots[:k, 0], leave=pivots[:k, 1], theta=theta[:k],
+               basis=basis, nonbasic=nonbasic, xB=xB, Binv=Binv, x=x)
+    if history:
+        out["history"] = hist[: min(n_iters.value + 1, history)]
+    return out
+
+
 def primal_solve_batched(A, b, c, rel=None, sense=0, max_iterations=10000, kernel=F.KERNEL_AUTO, threads=0,
                          want_tableau=True, out=None, reg_variant=0):
     """Host buffers in, host buffers out (the reference-facing call).  `out` may carry

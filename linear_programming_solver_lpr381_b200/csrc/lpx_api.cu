@@ -151,6 +151,10 @@ const char* lpx_status_message(int status) {
             return "Constraint has a negative RHS value. The Primal Simplex method cannot handle this. Please try the "
                    "Dual Simplex algorithm instead.";
         case LPX_S_ITER_LIMIT: return "Iteration limit exceeded.";
+        case LPX_S_REV_UNSUPPORTED:
+            return "Revised Primal Simplex currently supports only <= constraints with RHS >= 0. Use Dual Simplex for "
+                   "models with >= or =.";
+        case LPX_S_SINGULAR: return "Singular basis encountered.";
         case LPX_E_BAD_ARGS: return "bad arguments";
         case LPX_E_CUDA: return "CUDA error";
         case LPX_E_CAPACITY: return "problem exceeds kernel capacity";

@@ -1,7 +1,7 @@
 // lpr381 — headless front end of the host layer: what Form1.btnSolve_Click / BtnExport_Click do
 // (R/Form1.cs:231-279, 298-324) without the window.
 //
-//   lpr381 "<algorithm>" [input.txt]        algorithm: Primal Simplex | Dual Simplex |
+//   lpr381 "<algorithm>" [input.txt]        algorithm: Primal Simplex | Revised Primal Simplex | Dual Simplex |
 //                                           Branch and Bound | Cutting Plane | BranchAndBoundKnapsack | ...
 //   lpr381 --export "<algorithm>" [input]   the export file layout ("Linear Program:" / "Iterations:")
 #include <cstdio>

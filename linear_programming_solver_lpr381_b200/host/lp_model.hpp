@@ -81,6 +81,10 @@ struct LPParser {
 struct PrimalSimplex : ILPAlgorithm {
     SimplexResult Solve(const LPProblem& original, UpdatePivot updatePivot = nullptr) override;
 };
+// R/Models/RevisedPrimalSimplex.cs:13-145 (LPSolver keys "revised primal simplex", "revised primal")
+struct RevisedPrimalSimplex : ILPAlgorithm {
+    SimplexResult Solve(const LPProblem& original, UpdatePivot updatePivot = nullptr) override;
+};
 struct DualSimplex : ILPAlgorithm {
     SimplexResult Solve(const LPProblem& original, UpdatePivot updatePivot = nullptr) override;
 };

@@ -273,11 +273,10 @@ SimplexResult LPSolver::Solve(const LPProblem& problem, const std::string& algor
     const std::string key = NormalizeAlgorithmKey(algorithm);
     std::unique_ptr<ILPAlgorithm> algo;
     if (key == "primal simplex" || key == "primal") algo.reset(new PrimalSimplex());
+    else if (key == "revised primal simplex" || key == "revised primal") algo.reset(new RevisedPrimalSimplex());
     else if (key == "dual simplex" || key == "dual") algo.reset(new DualSimplex());
     else if (key == "branch and bound simplex" || key == "branch and bound" || key == "bnb") algo.reset(new BranchAndBound());
     else
-        // "revised primal simplex" / "revised primal" exist upstream (LPSolver.cs:27-28) but are not
-        // on the accelerated path; they get the reference's own rejection text.
         throw LpException("Algorithm not supported: '" + algorithm +
                           "'. Try one of: Primal Simplex, Revised Primal Simplex, Dual Simplex, Branch and Bound "
                           "Simplex.");

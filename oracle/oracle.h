@@ -64,6 +64,14 @@ int orc_knapsack(int n, const double* profit, const double* weight, double capac
                  int* best_x, long* n_evals, long* n_pops, long eval_cap, int* ev_parent, int* ev_child,
                  int* ev_var, double* ev_bound, double* ev_weight, int* ev_frac, int* ev_decision);
 
+/* RevisedPrimalSimplex.Solve numerics: per pivot the entering column, the leaving ROW and theta; the
+ * basis state after the last completed iteration (Bidx, x_B, B^-1 row-major m x m); x and the z*
+ * recomputed from the original objective.  status: 0 OPTIMAL, 1 UNBOUNDED, -3 iteration limit,
+ * -10 unsupported model (not all <= with b >= -1e-9), -11 singular basis. */
+int orc_revised_solve(int m, int n, int sense, const double* A, const int* rel, const double* b, const double* c,
+                      int max_iterations, int* status, int* n_iters, int* enter, int* leave, double* theta, int cap,
+                      int* basis, double* xB, double* Binv, double* x, double* z_original);
+
 /* Full text of a headless solve: the updatePivot stream, Report and Summary.
  * algorithm: any LPSolver key, "knapsack" for BranchAndBoundKnapsack, "cutting plane" for
  * CuttingPlane (both constructed directly by Form1.btnSolve_Click, not through LPSolver). */

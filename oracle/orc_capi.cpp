@@ -287,6 +287,51 @@ int orc_knapsack(int n, const double* profit, const double* weight, double capac
     return 0;
 }
 
+// RevisedPrimalSimplex numerics: pivots (entering column, leaving row, theta) and the final basis state.
+int orc_revised_solve(int m, int n, int sense, const double* A, const int* rel, const double* b, const double* c,
+                      int max_iterations, int* status, int* n_iters, int* enter, int* leave, double* theta, int cap,
+                      int* basis, double* xB, double* Binv, double* x, double* z_original) {
+    try {
+        Problem p = make_problem(m, n, sense, A, rel, b, c);
+        RevTrace t;
+        Outcome o;
+        int st = 0;
+        try {
+            o = revised_primal_simplex(p, Sink(), &t, max_iterations);
+            st = t.status;
+        } catch (const SolveError& e) {
+            if (e.code != ERR_ITER_LIMIT) {
+                *status = e.code;
+                *n_iters = 0;
+                return 0;
+            }
+            st = ERR_ITER_LIMIT;
+        }
+        *status = st;
+        *n_iters = (int)t.enter.size();
+        for (int k = 0; k < *n_iters && k < cap; k++) {
+            if (enter) enter[k] = t.enter[k];
+            if (leave) leave[k] = t.leave[k];
+            if (theta) theta[k] = t.theta[k];
+        }
+        for (int i = 0; i < m; i++) {
+            if (basis) basis[i] = t.basis[i];
+            if (xB) xB[i] = t.xB[i];
+        }
+        if (Binv)
+            for (size_t k = 0; k < t.Binv.size(); k++) Binv[k] = t.Binv[k];
+        if (st >= 0) {
+            if (x)
+                for (int j = 0; j < n; j++) x[j] = o.x[j];
+            if (z_original) *z_original = o.z;
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        t_err = e.what();
+        return -1;
+    }
+}
+
 struct orc_text {
     int code = 0;
     int chunks = 0;

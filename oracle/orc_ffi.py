@@ -244,6 +244,24 @@ def knapsack(profit, weight, capacity, eval_cap=1 << 22):
                 parent=par[:k], child=ch[:k], var=var[:k], bound=bd[:k], weight=wt[:k], frac=fr[:k], decision=dc[:k])
 
 
+def revised_solve(A, b, c, rel=None, sense=0, max_iterations=10000, cap=16384):
+    A, rel, b, c, m, n = _prep(A, rel, b, c)
+    L = lib()
+    status, n_iters, z = C.c_int(), C.c_int(), C.c_double()
+    enter, leave = np.zeros(cap, dtype=np.int32), np.zeros(cap, dtype=np.int32)
+    theta = np.zeros(cap)
+    basis = np.zeros(m, dtype=np.int32)
+    xB, Binv, x = np.zeros(m), np.zeros((m, m)), np.zeros(n)
+    rc = L.orc_revised_solve(m, n, sense, _d(A), _i(rel), _d(b), _d(c), max_iterations, C.byref(status),
+                             C.byref(n_iters), _i(enter), _i(leave), _d(theta), cap, _i(basis), _d(xB), _d(Binv), _d(x),
+                             C.byref(z))
+    if rc != 0:
+        raise RuntimeError(last_error())
+    k = min(n_iters.value, cap)
+    return dict(status=status.value, n_iters=n_iters.value, enter=enter[:k], leave=leave[:k], theta=theta[:k],
+                basis=basis, xB=xB, Binv=Binv, x=x, z=z.value)
+
+
 def solve_text(text, algorithm):
     L = lib()
     h = L.orc_solve_text(text.encode("utf-8"), algorithm.encode("utf-8"))

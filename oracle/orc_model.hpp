@@ -64,7 +64,7 @@ struct SolveError : std::runtime_error {
 };
 // negative status codes shared with include/lpx.h
 enum { ERR_GE_ROW = -1, ERR_NEG_RHS = -2, ERR_ITER_LIMIT = -3, ERR_BAD_ARGS = -4, ERR_PARSE = -6,
-       ERR_UNSUPPORTED_ALGO = -7 };
+       ERR_UNSUPPORTED_ALGO = -7, ERR_REV_UNSUPPORTED = -10, ERR_SINGULAR = -11 };
 
 extern std::string g_newline;  // Environment.NewLine ("\n" here; "\r\n" on the reference's Windows)
 

@@ -480,8 +480,7 @@ Outcome lp_solver_solve(const Problem& p, const std::string& algorithm, const Si
     if (key == "dual simplex" || key == "dual") return dual_simplex(p, sink, trace, format_every_iteration);
     if (key == "branch and bound simplex" || key == "branch and bound" || key == "bnb")
         return branch_and_bound(p, sink, nullptr, format_every_iteration);
-    // "revised primal simplex"/"revised primal" exist upstream (LPSolver.cs:27-28) but are outside
-    // the hot-path scope.
+    if (key == "revised primal simplex" || key == "revised primal") return revised_primal_simplex(p, sink, nullptr);
     throw SolveError(ERR_UNSUPPORTED_ALGO,
                      "Algorithm not supported: '" + algorithm +
                          "'. Try one of: Primal Simplex, Revised Primal Simplex, Dual Simplex, Branch and Bound "

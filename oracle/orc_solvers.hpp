@@ -70,6 +70,18 @@ struct KnapTrace {
 // R/Models/BranchAndBoundKnapsack.cs:58-407
 Outcome knapsack_bnb(const Problem& p, const Sink& sink, KnapTrace* trace, bool build_text = true);
 
+// RevisedPrimalSimplex: one entry per pivot; the basis state after the last completed iteration.
+struct RevTrace {
+    std::vector<int> enter, leave;   // entering column, leaving ROW (position in the basis)
+    std::vector<double> theta;
+    std::vector<int> basis;          // Bidx
+    std::vector<double> xB, Binv;    // m, m x m
+    double z = 0;                    // c_B . x_B of the standardized model
+    int status = 0;                  // 0 OPTIMAL, 1 UNBOUNDED
+};
+// R/Models/RevisedPrimalSimplex.cs:17-145
+Outcome revised_primal_simplex(const Problem& p, const Sink& sink, RevTrace* trace, int max_iterations = 10000);
+
 // One entry per round of CuttingPlane.Solve (one PrimalSimplex solve, then at most one cut).
 enum { CUT_INTEGER = 0, CUT_INCOMPLETE = 1, CUT_LP_ERROR = 2, CUT_NONBASIC = 3 };
 struct CutTrace {

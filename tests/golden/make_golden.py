@@ -70,13 +70,27 @@ CUT_CASES = {
     "cut_ge_error": (0, [1, 1], [([1, 1], LE, 4), ([1, 0], GE, 1)]),
 }
 
+REV_CASES = {
+    # RevisedPrimalSimplex: B^-1 recomputed by Gauss-Jordan each iteration, ratio margin 1e-12
+    "rev_wyndor": (0, [3, 5], [([1, 0], LE, 4), ([0, 2], LE, 12), ([3, 2], LE, 18)], 10000),
+    "rev_min_negative_costs": (1, [-2, -3], [([1, 1], LE, 4), ([1, 3], LE, 6)], 10000),
+    "rev_unbounded": (0, [1, 1], [([1, -1], LE, 1)], 10000),
+    "rev_degenerate_tie": (0, [2, 3], [([1, 1], LE, 4), ([1, 3], LE, 6), ([0, 1], LE, 2)], 10000),
+    "rev_three_vars": (0, [7, 3, 4], [([3, 2, 5], LE, 17), ([4, 1, 2], LE, 11), ([1, 3, 1], LE, 9)], 10000),
+    "rev_klee_minty3": (0, [100, 10, 1], [([1, 0, 0], LE, 1), ([20, 1, 0], LE, 100), ([200, 20, 1], LE, 10000)], 10000),
+    "rev_needs_row_swaps": (0, [2, 1, 3], [([0, 2, 1], LE, 10), ([3, 0, 1], LE, 12), ([1, 4, 0], LE, 8), ([1, 1, 1], LE, 7)], 10000),
+    "rev_ge_row": (0, [1, 1], [([1, 1], LE, 4), ([1, 0], GE, 1)], 10000),
+    "rev_neg_rhs": (0, [1, 1], [([1, 1], LE, -4)], 10000),
+    "rev_iter_limit": (0, [3, 5], [([1, 0], LE, 4), ([0, 2], LE, 12), ([3, 2], LE, 18)], 1),
+}
+
 
 def hx(v):
     return float(v).hex()
 
 
 def main():
-    out = {"lp": {}, "dual": {}, "ip": {}, "knap": {}, "cut": {}}
+    out = {"lp": {}, "dual": {}, "ip": {}, "knap": {}, "cut": {}, "rev": {}}
     for name, (sense, c, rows, mi) in LP_CASES.items():
         A = [[float(v) for v in r[0]] for r in rows]
         rel = [r[1] for r in rows]
@@ -125,6 +139,20 @@ def main():
             case.update(x=[hx(v) for v in r["x"]], z=hx(r["z"]), basis=r["basis"],
                         tableau=[[hx(v) for v in row] for row in r["tableau"]])
         out["cut"][name] = case
+    for name, (sense, c, rows, mi) in REV_CASES.items():
+        A = [[float(v) for v in r[0]] for r in rows]
+        rel = [r[1] for r in rows]
+        b = [float(r[2]) for r in rows]
+        case = dict(sense=sense, c=[hx(v) for v in c], A=[[hx(v) for v in r_] for r_ in A], rel=rel,
+                    b=[hx(v) for v in b], max_iterations=mi)
+        try:
+            r = pyref.revised(A, b, [float(v) for v in c], rel, sense, mi)
+            case.update(status=r["status"], pivots=[[e, l, hx(t)] for e, l, t in r["pivots"]], basis=r["basis"],
+                        xB=[hx(v) for v in r["xB"]], Binv=[[hx(v) for v in row] for row in r["Binv"]],
+                        x=[hx(v) for v in r["x"]], z=hx(r["z"]))
+        except pyref.SolveError as e:
+            case.update(status=e.code)
+        out["rev"][name] = case
     with open(os.path.join(HERE, "kat.json"), "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)
     print("wrote kat.json:", {k: len(v) for k, v in out.items()})

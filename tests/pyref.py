@@ -432,3 +432,89 @@ def cutting_plane(A, b, c, rel=None, sense=0):
         b.append(f0)
         rel.append(LE)
     return dict(end=1, cuts=cuts, rounds=rounds)
+
+
+def _invert(M):
+    """RevisedPrimalSimplex.Invert (R/Models/RevisedPrimalSimplex.cs:409-456)."""
+    n = len(M)
+    A = [list(M[i]) + [1.0 if j == i else 0.0 for j in range(n)] for i in range(n)]
+    for col in range(n):
+        piv_row, best = col, abs(A[col][col])
+        for r in range(col + 1, n):
+            if abs(A[r][col]) > best:
+                best, piv_row = abs(A[r][col]), r
+        if abs(A[piv_row][col]) < 1e-9:
+            raise SolveError(-11, "singular")
+        if piv_row != col:
+            A[col], A[piv_row] = A[piv_row], A[col]
+        piv = A[col][col]
+        A[col] = [v / piv for v in A[col]]
+        for r in range(n):
+            if r == col:
+                continue
+            f = A[r][col]
+            A[r] = [A[r][j] - f * A[col][j] for j in range(2 * n)]
+    return [row[n:] for row in A]
+
+
+def _seqdot(a, b):
+    s = 0.0
+    for u, v in zip(a, b):
+        s += u * v
+    return s
+
+
+def revised(A, b, c, rel=None, sense=0, max_iterations=10000):
+    """RevisedPrimalSimplex.Solve (R/Models/RevisedPrimalSimplex.cs:17-145): numerics only."""
+    m, n = len(A), len(c)
+    rel = rel if rel is not None else [LE] * m
+    if not all(rel[i] == LE and b[i] >= -1e-9 for i in range(m)):
+        raise SolveError(-10, "unsupported")
+    cc = [-v for v in c] if sense == 0 else list(c)   # Standardize negates C for MAX
+    ntot = n + m
+    Af = [list(A[i]) + [1.0 if j == i else 0.0 for j in range(m)] for i in range(m)]
+    cf = cc + [0.0] * m
+    Bidx, Nidx = list(range(n, ntot)), list(range(n))
+
+    def state():
+        Binv = _invert([[Af[i][k] for k in Bidx] for i in range(m)])
+        xB = [_seqdot(Binv[i], b) for i in range(m)]
+        cB = [cf[k] for k in Bidx]
+        return Binv, xB, cB
+    Binv, xB, cB = state()
+    pivots = []
+    status = None
+    for _ in range(max_iterations):
+        piT = [_seqdot(cB, [Binv[i][j] for i in range(m)]) for j in range(m)]
+        rN = [cf[k] - _seqdot(piT, [Af[i][k] for i in range(m)]) for k in Nidx]
+        pos, best = -1, -1e-9
+        for j, v in enumerate(rN):
+            if v < best:
+                best, pos = v, j
+        if pos == -1:
+            status = 0
+            break
+        e = Nidx[pos]
+        d = [_seqdot(Binv[i], [Af[j][e] for j in range(m)]) for i in range(m)]
+        row, theta_best = -1, float("inf")
+        for i in range(m):
+            if d[i] > 1e-9:
+                theta = xB[i] / d[i]
+                if theta < theta_best - 1e-12:
+                    theta_best, row = theta, i
+        if row == -1:
+            status = 1
+            break
+        leaving = Bidx[row]
+        Bidx[row] = e
+        Nidx.pop(pos)
+        Nidx.append(leaving)
+        Binv, xB, cB = state()
+        pivots.append((e, row, theta_best))
+    if status is None:
+        status = -3
+    x = [0.0] * n
+    for i, k in enumerate(Bidx):
+        if k < n:
+            x[k] = xB[i]
+    return dict(status=status, pivots=pivots, basis=Bidx, xB=xB, Binv=Binv, x=x, z=_seqdot(c, x))

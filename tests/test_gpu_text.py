@@ -52,7 +52,7 @@ def test_dual_text(lpx, orc, kat, name):
 
 
 def test_unsupported_and_empty_algorithm(lpx, orc):
-    for algo in ("Revised Primal Simplex", "Cutting Plane", "  "):
+    for algo in ("Revised Dual Simplex", "Cutting Plane", "  "):  # no such LPSolver keys (LPSolver.cs:24-33)
         want = orc.solve_text(workloads.WYNDOR_TEXT, algo)
         got = H.solve_text(workloads.WYNDOR_TEXT, algo)
         assert got["error"] == want["error"] != ""

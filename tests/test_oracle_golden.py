@@ -185,3 +185,47 @@ def test_cutting_plane_reads_the_row_below(kat):
     # tableau row 1 = the objective row, whose decision-variable entries are 0 -> the empty cut
     case = kat["cut"]["cut_from_z_row"]
     assert all(k["row"] == 1 and unhex(k["a"]) == [0.0, 0.0] and unhex(k["b"]) == 0.5 for k in case["cuts"])
+
+
+REV_NAMES = ["rev_wyndor", "rev_min_negative_costs", "rev_unbounded", "rev_degenerate_tie", "rev_three_vars",
+             "rev_klee_minty3", "rev_needs_row_swaps", "rev_ge_row", "rev_neg_rhs", "rev_iter_limit"]
+
+
+@pytest.mark.parametrize("name", REV_NAMES)
+def test_revised_kat(orc, kat, name):
+    # RevisedPrimalSimplex.cs:17-145: pivots (entering column, leaving row, theta), final Bidx, x_B, B^-1
+    case = kat["rev"][name]
+    A, b, c, rel = case_arrays(case)
+    r = orc.revised_solve(A, b, c, rel, case["sense"], max_iterations=case["max_iterations"])
+    assert r["status"] == case["status"]
+    if case["status"] in (-10, -11):
+        return
+    assert [[int(e), int(l)] for e, l in zip(r["enter"], r["leave"])] == [p[:2] for p in case["pivots"]]
+    assert_bits_equal(r["theta"], [unhex(p[2]) for p in case["pivots"]], "theta")
+    assert r["basis"].tolist() == case["basis"]
+    assert_bits_equal(r["xB"], unhex(case["xB"]), "xB")
+    assert_bits_equal(r["Binv"], unhex(case["Binv"]), "Binv")
+    if case["status"] >= 0:
+        assert_bits_equal(r["x"], unhex(case["x"]), "x")
+        assert_bits_equal([r["z"]], [unhex(case["z"])], "z")
+
+
+def test_revised_matches_pyref_on_random_small(orc):
+    import pyref
+    rng = np.random.default_rng(31)
+    for t in range(40):
+        m, n = int(rng.integers(1, 9)), int(rng.integers(1, 10))
+        A = rng.integers(-2, 9, size=(m, n)).astype(float)
+        b = rng.integers(0, 30, size=m).astype(float)
+        c = rng.integers(-3, 9, size=n).astype(float)
+        sense = int(rng.integers(0, 2))
+        try:
+            want = pyref.revised(A.tolist(), b.tolist(), c.tolist(), None, sense, 200)
+        except pyref.SolveError as e:
+            assert orc.revised_solve(A, b, c, None, sense, max_iterations=200)["status"] == e.code
+            continue
+        got = orc.revised_solve(A, b, c, None, sense, max_iterations=200)
+        assert got["status"] == want["status"], t
+        assert [[int(e), int(l)] for e, l in zip(got["enter"], got["leave"])] == [[e, l] for e, l, _ in want["pivots"]], t
+        assert_bits_equal(got["xB"], want["xB"], f"xB {t}")
+        assert_bits_equal(got["Binv"], want["Binv"], f"Binv {t}")
