@@ -52,6 +52,14 @@ namespace Linear_Programming_Solver.Models
             ref LpxOptions opt, out int status, out int n_pivots, out int silent_pivots, int[] pivots, int pivots_cap,
             int[] basis, double[] x, out double z, double[] tableau, double[] history, int history_cap);
 
+        // RevisedPrimalSimplex (R/Models/RevisedPrimalSimplex.cs:17-145): pivots = (entering column, leaving row)
+        // pairs; history = one record per BuildIterationBlock call, lpx_revised_history_stride doubles each
+        [DllImport(Lib)]
+        public static extern int lpx_revised_solve(int m, int n, int sense, double[] A, int[] rel, double[] b, double[] c,
+            ref LpxOptions opt, out int status, out int n_iters, int[] pivots, double[] theta, int pivots_cap,
+            int[] basis, int[] nonbasic, double[] xB, double[] Binv, double[] x, double[] history, int history_cap);
+        [DllImport(Lib)] public static extern UIntPtr lpx_revised_history_stride(int m, int n);
+
         [DllImport(Lib)]
         public static extern int lpx_primal_solve_batched(int count, int m, int n, int sense, double[] A, int[] rel,
             double[] b, double[] c, ref LpxOptions opt, int[] status, int[] n_pivots, int[] basis, double[] x,
