@@ -126,6 +126,53 @@ def main():
             if not ok:
                 bad += 1
                 print("MISMATCH revised", m, n, want["status"], got["status"], flush=True)
+        # 5. Branch & Bound: batches of small IPs (threaded host commit, cluster kernel for deep nodes)
+        if rd % 4 == 0:
+            m, n, cnt = int(rng.integers(3, 9)), int(rng.integers(3, 10)), 48
+            A = rng.integers(1, 12, size=(cnt, m, n)).astype(float)
+            b = rng.integers(3 * n, 12 * n, size=(cnt, m)).astype(float)
+            c = rng.integers(1, 15, size=(cnt, n)).astype(float)
+            got = api.bnb_simplex_batched(A, b, c)
+            for k in range(cnt):
+                want = orc.bnb_simplex(A[k], b[k], c[k], node_cap=1 << 16)
+                ok = (bool(got["found"][k]) == want["found"] and got["n_nodes"][k] == want["n_nodes"]
+                      and got["lp_pivots"][k] == want["total_pivots"])
+                if ok and want["found"]:
+                    ok = same([got["best_z"][k]], [want["best_z"]]) and same(got["best_x"][k], want["best_x"])
+                if not ok:
+                    bad += 1
+                    print("MISMATCH bnb", m, n, k, got["n_nodes"][k], want["n_nodes"], flush=True)
+            # one deeper instance so that nodes leave one SM's shared memory
+            A1 = rng.integers(1, 20, size=(40, 80)).astype(float)
+            b1 = rng.integers(5 * 80, 15 * 80, size=40).astype(float)
+            c1 = rng.integers(1, 30, size=80).astype(float)
+            want = orc.bnb_simplex(A1, b1, c1, node_cap=1 << 16)
+            g1 = api.bnb_simplex_batched(A1[None], b1[None], c1[None])
+            if not (bool(g1["found"][0]) == want["found"] and g1["n_nodes"][0] == want["n_nodes"]
+                    and g1["lp_pivots"][0] == want["total_pivots"]
+                    and (not want["found"] or same(g1["best_x"][0], want["best_x"]))):
+                bad += 1
+                print("MISMATCH bnb deep", g1["n_nodes"][0], want["n_nodes"], flush=True)
+        # 6. knapsack: integer (order-free sums) and fractional (ordered sums) data, several speculation settings
+        if rd % 4 == 1:
+            for t in range(6):
+                nk = int(rng.integers(5, 120))
+                w = rng.integers(1, 60, size=nk).astype(float)
+                pf = rng.integers(1, 90, size=nk).astype(float)
+                if t % 2:
+                    w = np.round(w / 7.0, 3)
+                    pf = np.round(pf / 3.0, 2)
+                cap = float(np.floor(w.sum() * rng.choice([0.3, 0.5, 0.7])))
+                want = orc.knapsack(pf, w, cap)
+                for spec in ((0, 0), (1, 1), (4, 2), (32, 5)):
+                    got = api.bnb_knapsack(pf, w, cap, spec_nodes=spec[0], spec_depth=spec[1])
+                    ok = (got["found"] == want["found"] and got["n_evals"] == want["n_evals"]
+                          and got["n_pops"] == want["n_pops"]
+                          and (not want["found"] or (same([got["best"]], [want["best"]])
+                                                     and list(got["best_x"]) == list(want["best_x"]))))
+                    if not ok:
+                        bad += 1
+                        print("MISMATCH knapsack", nk, spec, got["n_evals"], want["n_evals"], flush=True)
         print(f"round {rd} done, mismatches so far {bad}, {time.time() - t0:.0f} s", flush=True)
     print("FUZZ RESULT:", "OK" if bad == 0 else f"{bad} MISMATCHES")
     sys.exit(1 if bad else 0)
