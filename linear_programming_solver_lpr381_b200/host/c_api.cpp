@@ -36,7 +36,11 @@ lpr_text* lpr_solve_text(const char* input, const char* algorithm) {
         const std::string algo = algorithm;
         if (algo == "knapsack") r = BranchAndBoundKnapsack().Solve(p, cb);
         else if (algo == "controller") r = LPController::SolvePrimalSimplex(p);
-        else if (algo == "cutting plane") {
+        else if (algo == "revised cutting plane") {
+            CuttingPlaneRevised cp;
+            r = cp.Solve(p, cb);
+            t->cuts = cp.Cuts;
+        } else if (algo == "cutting plane") {
             CuttingPlane cp;
             r = cp.Solve(p, cb);
             t->cuts = cp.Cuts;

@@ -2,7 +2,7 @@
 // (R/Form1.cs:231-279, 298-324) without the window.
 //
 //   lpr381 "<algorithm>" [input.txt]        algorithm: Primal Simplex | Revised Primal Simplex | Dual Simplex |
-//                                           Branch and Bound | Cutting Plane | BranchAndBoundKnapsack | ...
+//                                           Branch and Bound | Cutting Plane | Revised Cutting Plane | BranchAndBoundKnapsack | ...
 //   lpr381 --export "<algorithm>" [input]   the export file layout ("Linear Program:" / "Iterations:")
 #include <cstdio>
 #include <fstream>
@@ -46,6 +46,8 @@ int main(int argc, char** argv) {
         // (Form1.cs:263-270); the knapsack solver itself is reachable here under its class name
         if (algorithm == "BranchAndBoundKnapsack" || algorithm == "knapsack")
             result = BranchAndBoundKnapsack().Solve(problem, append);
+        else if (algorithm == "Revised Cutting Plane")  // Form1.cs:256-261
+            result = CuttingPlaneRevised().Solve(problem, append);
         else if (algorithm == "Cutting Plane")  // Form1.cs:249-254
             result = CuttingPlane().Solve(problem, append);
         else if (algorithm == "Branch and Bound" || algorithm == "Revised Branch and Bound" ||

@@ -12,6 +12,7 @@
 #include <cmath>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "../../include/lpx.h"
 #include "dotnet_text.hpp"
@@ -133,6 +134,100 @@ SimplexResult CuttingPlane::Solve(const LPProblem& problem, UpdatePivot updatePi
     }
     report += "Iteration limit reached. Stopping." + nl;
     return failed("Status: INCOMPLETE");
+}
+
+// ---- CuttingPlaneRevised.Solve (R/Models/CuttingPlaneRevised.cs:14-111) -------------------------
+// Over the GPU revised simplex.  As upstream it reads x back from the Summary text (three-decimal
+// values), bounds the first fractional variable by its floor and re-solves, at most 50 rounds; the
+// LP solver's exceptions pass through.
+namespace {
+
+// ExtractSolution (:93-110); returns false when no "x* = [...]" line is found
+bool extract_solution(const std::string& summary, int nVars, std::vector<double>& x) {
+    size_t pos = 0;
+    while (pos <= summary.size()) {
+        size_t eol = summary.find('\n', pos);
+        if (eol == std::string::npos) eol = summary.size();
+        const std::string line = summary.substr(pos, eol - pos);
+        const size_t k = line.find_first_not_of(" \t\r");
+        if (k != std::string::npos && line.compare(k, 6, "x* = [") == 0) {
+            const size_t sb = line.find('['), se = line.find(']');
+            if (sb == std::string::npos || se == std::string::npos || se <= sb) return false;
+            const std::string body = line.substr(sb + 1, se - sb - 1);
+            size_t q = 0;
+            while (q <= body.size()) {
+                size_t comma = body.find(',', q);
+                if (comma == std::string::npos) comma = body.size();
+                x.push_back(std::strtod(body.substr(q, comma - q).c_str(), nullptr));
+                q = comma + 1;
+            }
+            x.resize(nVars, 0.0);
+            return true;
+        }
+        pos = eol + 1;
+    }
+    return false;
+}
+
+}  // namespace
+
+SimplexResult CuttingPlaneRevised::Solve(const LPProblem& problem, UpdatePivot updatePivot) {
+    const double Eps = 1e-9;
+    const std::string& nl = NewLine();
+    RevisedPrimalSimplex solver;
+    LPProblem model = problem.Clone();
+    Cuts.clear();
+    std::string report;
+    auto finish = [&](const std::string& summary) {
+        SimplexResult r;
+        r.Report = report;
+        r.Summary = summary;
+        return r;
+    };
+    for (int iter = 1;; ) {
+        SimplexResult lp = solver.Solve(model, updatePivot);
+        report += "--- Cutting-Plane Iteration " + std::to_string(iter) + " ---" + nl;
+        report += lp.Report + nl;
+        if (lp.Summary.find("Status: OPTIMAL") == std::string::npos) {
+            report += "Stopping: LP not OPTIMAL; cannot continue cutting." + nl;
+            return finish("Terminated: LP not OPTIMAL; cutting-plane stopped.");
+        }
+        std::vector<double> x;
+        if (!extract_solution(lp.Summary, problem.NumVars(), x)) {
+            report += "Stopping: Could not parse primal solution." + nl;
+            return finish("Terminated: could not parse solution.");
+        }
+        int fracIndex = -1;
+        for (int i = 0; i < (int)x.size(); i++) {
+            const double frac = x[i] - std::floor(x[i]);
+            if (frac > Eps && frac < 1 - Eps) {
+                fracIndex = i;
+                break;
+            }
+        }
+        if (fracIndex == -1) {
+            report += "All decision variables are integer. Optimal integer solution found." + nl;
+            std::string summary = lp.Summary;
+            for (size_t at = 0; (at = summary.find("Status: OPTIMAL", at)) != std::string::npos; at += 23)
+                summary.replace(at, 15, "Status: OPTIMAL INTEGER");
+            return finish(summary);
+        }
+        const double floorVal = std::floor(x[fracIndex] + 1e-12);
+        Constraint cut;
+        cut.A.assign(model.NumVars(), 0.0);
+        cut.A[fracIndex] = 1.0;
+        cut.Relation = Rel::LE;
+        cut.B = floorVal;
+        model.Constraints.push_back(cut);
+        Cuts.push_back(cut);
+        report += "Added cut: x" + std::to_string(fracIndex + 1) + " \xE2\x89\xA4 " + text::round_trip(floorVal) + " (current x" +
+                  std::to_string(fracIndex + 1) + " = " + text::custom_hash(x[fracIndex]) + ")" + nl;
+        iter++;
+        if (iter > 50) {
+            report += "Iteration limit reached." + nl;
+            return finish("Iteration limit reached (solution may still be fractional).");
+        }
+    }
 }
 
 }  // namespace lpr381

@@ -104,6 +104,12 @@ struct CuttingPlane : ILPAlgorithm {
     SimplexResult Solve(const LPProblem& problem, UpdatePivot updatePivot = nullptr) override;
 };
 
+// R/Models/CuttingPlaneRevised.cs:9-111 — GUI entry "Revised Cutting Plane" (Form1.cs:256-261)
+struct CuttingPlaneRevised : ILPAlgorithm {
+    std::vector<Constraint> Cuts;
+    SimplexResult Solve(const LPProblem& problem, UpdatePivot updatePivot = nullptr) override;
+};
+
 struct LPSolver {
     Matrix FinalTableau;
     SimplexResult Solve(const LPProblem& problem, const std::string& algorithm, UpdatePivot updatePivot = nullptr);

@@ -352,6 +352,7 @@ orc_text* orc_solve_text(const char* input, const char* algorithm) {
         std::string algo = algorithm;
         if (algo == "knapsack") o = knapsack_bnb(p, sink, nullptr, true);
         else if (algo == "cutting plane") o = cutting_plane(p, sink, &t->cuts);   // Form1.cs:249-254
+        else if (algo == "revised cutting plane") o = cutting_plane_revised(p, sink, &t->cuts);   // Form1.cs:256-261
         else o = lp_solver_solve(p, algo, sink, nullptr, true);
         t->report = o.report;
         t->summary = o.summary;

@@ -7,6 +7,7 @@
 // row — so the cut is read from the row below the fractional variable's (the z-row when that
 // variable sits in the last constraint row).
 #include <cmath>
+#include <cstdlib>
 
 #include "orc_dotnet.hpp"
 #include "orc_solvers.hpp"
@@ -136,6 +137,102 @@ Outcome cutting_plane(const Problem& problem, const Sink& sink, CutTrace* trace)
     o.report = report;
     o.summary = "Status: INCOMPLETE";
     return o;
+}
+
+// ---- CuttingPlaneRevised.Solve (R/Models/CuttingPlaneRevised.cs:14-111) -------------------------
+// Drives RevisedPrimalSimplex; reads the solution back from the Summary TEXT (so it sees x rounded to
+// three decimals, :93-110), adds the bound  x_k <= floor(x_k + 1e-12)  for the first fractional x_k,
+// at most 50 rounds.  Exceptions of the LP solver are not caught.
+Outcome cutting_plane_revised(const Problem& problem, const Sink& sink, CutTrace* trace) {
+    const double Eps = 1e-9;
+    const std::string& nl = g_newline;
+    const int nVars = problem.nvars();
+    Problem model = problem;
+    std::string report;
+    int iter = 1;
+    while (true) {
+        Outcome lp = revised_primal_simplex(model, sink, nullptr);
+        report += "--- Cutting-Plane Iteration " + std::to_string(iter) + " ---" + nl;
+        report += lp.report + nl;
+        auto finish = [&](const std::string& summary, int end) {
+            if (trace) trace->end = end;
+            Outcome o;
+            o.report = report;
+            o.summary = summary;
+            return o;
+        };
+        // Summary.Contains("Status: OPTIMAL", OrdinalIgnoreCase): the solver writes it in this exact case
+        if (lp.summary.find("Status: OPTIMAL") == std::string::npos) {
+            report += "Stopping: LP not OPTIMAL; cannot continue cutting." + nl;
+            return finish("Terminated: LP not OPTIMAL; cutting-plane stopped.", CUT_LP_ERROR);
+        }
+        // ExtractSolution: first line whose trimmed start is "x* = [", numbers between the brackets
+        std::vector<double> x;
+        bool parsed = false;
+        size_t pos = 0;
+        while (pos <= lp.summary.size()) {
+            size_t eol = lp.summary.find('\n', pos);
+            if (eol == std::string::npos) eol = lp.summary.size();
+            std::string line = lp.summary.substr(pos, eol - pos);
+            size_t k = line.find_first_not_of(" \t\r");
+            if (k != std::string::npos && line.compare(k, 6, "x* = [") == 0) {
+                const size_t sb = line.find('['), se = line.find(']');
+                if (sb != std::string::npos && se != std::string::npos && se > sb) {
+                    std::string body = line.substr(sb + 1, se - sb - 1);
+                    size_t q = 0;
+                    while (q <= body.size()) {
+                        size_t comma = body.find(',', q);
+                        if (comma == std::string::npos) comma = body.size();
+                        x.push_back(std::strtod(body.substr(q, comma - q).c_str(), nullptr));
+                        q = comma + 1;
+                    }
+                    parsed = true;
+                }
+                break;
+            }
+            pos = eol + 1;
+        }
+        if (!parsed) {
+            report += "Stopping: Could not parse primal solution." + nl;
+            return finish("Terminated: could not parse solution.", CUT_NONBASIC);
+        }
+        x.resize(nVars, 0.0);
+        int fracIndex = -1;
+        for (int i = 0; i < nVars; i++) {
+            const double frac = x[i] - std::floor(x[i]);
+            if (frac > Eps && frac < 1 - Eps) {
+                fracIndex = i;
+                break;
+            }
+        }
+        if (fracIndex == -1) {
+            report += "All decision variables are integer. Optimal integer solution found." + nl;
+            std::string summary = lp.summary;
+            for (size_t at = 0; (at = summary.find("Status: OPTIMAL", at)) != std::string::npos; at += 23)
+                summary.replace(at, 15, "Status: OPTIMAL INTEGER");
+            return finish(summary, CUT_INTEGER);
+        }
+        const double floorVal = std::floor(x[fracIndex] + 1e-12);
+        Row cut;
+        cut.a.assign(model.nvars(), 0.0);
+        cut.a[fracIndex] = 1.0;
+        cut.rel = LE;
+        cut.b = floorVal;
+        model.rows.push_back(cut);
+        if (trace) {
+            trace->frac_var.push_back(fracIndex);
+            trace->cut_row.push_back(-1);
+            trace->cut_a.push_back(cut.a);
+            trace->cut_b.push_back(cut.b);
+        }
+        report += "Added cut: x" + std::to_string(fracIndex + 1) + " \xE2\x89\xA4 " + fmt_roundtrip(floorVal) + " (current x" +
+                  std::to_string(fracIndex + 1) + " = " + fmt_custom(x[fracIndex]) + ")" + nl;
+        iter++;
+        if (iter > 50) {
+            report += "Iteration limit reached." + nl;
+            return finish("Iteration limit reached (solution may still be fractional).", CUT_INCOMPLETE);
+        }
+    }
 }
 
 }  // namespace orc

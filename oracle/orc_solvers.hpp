@@ -93,5 +93,7 @@ struct CutTrace {
 };
 // R/Models/CuttingPlane.cs:13-164
 Outcome cutting_plane(const Problem& p, const Sink& sink, CutTrace* trace);
+// R/Models/CuttingPlaneRevised.cs:14-111 (cut_row is -1: the cut is a variable bound, not a tableau row)
+Outcome cutting_plane_revised(const Problem& p, const Sink& sink, CutTrace* trace);
 
 }  // namespace orc

@@ -101,3 +101,24 @@ def test_revised_random_text(lpx, orc):
         b = np.round(rng.random(m) * 40 + 1, 2)
         c = np.round(rng.random(n) * 9, 2)
         same_text(orc, workloads.lp_to_text(A, b, c, np.zeros(m, dtype=np.int32), t % 2), "Revised Primal Simplex")
+
+
+CPR_TEXTS = [
+    "Max: 5x1 + 8x2\n1x1 + 1x2 <= 6\n5x1 + 9x2 <= 45\n",          # two bounds, then integral
+    "Max: 3x1 + 5x2\n1x1 + 0x2 <= 4\n0x1 + 2x2 <= 12\n3x1 + 2x2 <= 18\n",   # integral at the root
+    "Max: 1x1 + 1x2\n1x1 - 1x2 <= 1\n",                             # unbounded LP: stops
+    "Max: 7x1 + 3x2 + 4x3\n3x1 + 2x2 + 5x3 <= 17\n4x1 + 1x2 + 2x3 <= 11\n1x1 + 3x2 + 1x3 <= 9\n",
+    "Min: -5x1 - 4x2\n6x1 + 4x2 <= 24\n1x1 + 2x2 <= 6\n",
+    "Max: 1x1 + 1x2\n1x1 + 1x2 <= 4\n1x1 + 0x2 >= 1\n",             # '>=' row: the solver's exception passes through
+]
+
+
+@pytest.mark.parametrize("text", CPR_TEXTS)
+def test_cutting_plane_revised_text(lpx, orc, text):
+    # CuttingPlaneRevised.cs:14-111 over the GPU revised simplex: same text, same bounds added
+    got = same_text(orc, text, "revised cutting plane")
+    want = orc.solve_text(text, "revised cutting plane")
+    assert len(got["cuts"]) == len(want["cuts"])
+    for g, w in zip(got["cuts"], want["cuts"]):
+        assert_bits_equal(g["a"], w["a"], "cut a")
+        assert_bits_equal([g["b"]], [w["b"]], "cut b")
