@@ -62,7 +62,7 @@ typedef struct lpx_options {
     int kernel;           /* LPX_KERNEL_*: force a kernel family (tests/benchmarks); 0 = auto */
     int threads;          /* CTA size override for the per-tableau kernels; 0 = auto */
     int knap_spec_nodes;  /* knapsack B&B: heap nodes speculated per round (0 = default 16) */
-    int knap_spec_depth;  /* knapsack B&B: look-ahead depth under the front runner (0 = default 4) */
+    int knap_spec_depth;  /* knapsack B&B: look-ahead depth under the front runner (0 = default 2) */
     int stream_protocol;  /* streaming kernels: 0 auto (pipelined blocked look-ahead: the look-ahead of block
                              B+1 overlaps the HBM pass of block B), 1 single-CTA select per pivot, 2 multi-CTA
                              prep per pivot, 3 blocked with a one-CTA look-ahead, 4 blocked, not pipelined */

@@ -24,6 +24,8 @@
 #include <queue>
 #include <vector>
 
+#include <cooperative_groups.h>
+
 #include "lpx_common.cuh"
 #include "lpx_runtime.hpp"
 #include "lpx_stream.hpp"
@@ -35,6 +37,7 @@ namespace lpx {
 enum { KF_INFEASIBLE = 1, KF_ALLINT = 2, KF_SKIPPED = 4, KF_EARLY = 8 };
 static const int KN_MAX_CHUNKS = 64;
 static const int KN_CHUNK_SLOTS = 1 << 15;
+static const int KN_MAX_LEVELS = 24;
 
 struct KnIn {
     int inst;
@@ -43,6 +46,9 @@ struct KnIn {
     int var;             // original index to fix (-1: none = root; -2: from the parent's fractional item)
     int side;            // value to fix it to
     int out_slot;
+    int parent_out_slot; // out_slot of parent_pending (filled by run_plan; saves a dependent read)
+    int pad;
+    double best;         // the instance's incumbent when the round was planned (filled by run_plan)
 };
 
 struct KnOut {
@@ -62,25 +68,27 @@ struct KnParams {
     const int* exact;    // [inst] 1: all weights/profits are integers with exact sums (order-free adds)
     int n;
     signed char* chunks[KN_MAX_CHUNKS];
-    const KnIn* in;
-    KnOut* out;
-    int first, count;    // evaluations [first, first+count) form this level
+    const KnIn* in;      // this round's evaluations, sorted by level; read straight from pinned host memory
+    KnOut* out;          // device copy of the results (children look their parent up here)
+    KnOut* out_host;     // the same results written through to pinned host memory
+    int nlev;
+    int lev_first[KN_MAX_LEVELS], lev_count[KN_MAX_LEVELS];  // evaluations [first, first+count) form a level
 };
 
 __device__ __forceinline__ signed char* kn_slot(const KnParams& P, int slot) {
     return P.chunks[slot / KN_CHUNK_SLOTS] + (size_t)(slot % KN_CHUNK_SLOTS) * P.n;
 }
 
-// 8 warps per CTA; dynamic shared memory = 8 * n bytes.
-__global__ void __launch_bounds__(256) knap_eval_kernel(const KnParams P) {
-    extern __shared__ signed char sm_assign[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int idx = blockIdx.x * 8 + warp;
-    if (idx >= P.count) return;
-    const int e = P.first + idx;
+__device__ __forceinline__ void kn_store(const KnParams& P, int e, const KnOut& o) {
+    P.out[e] = o;
+    P.out_host[e] = o;
+}
+
+// One ComputeRelaxation (BranchAndBoundKnapsack.cs:425-500) by one warp; sa = its n-byte shared scratch.
+__device__ void knap_eval_one(const KnParams& P, int e, signed char* sa) {
+    const int lane = threadIdx.x & 31;
     const KnIn in = P.in[e];
     const int n = P.n;
-    signed char* sa = sm_assign + (size_t)warp * n;
     KnOut o;
     o.bound = o.weight = o.frac = 0.0;
     o.frac_rank = -1;
@@ -89,7 +97,7 @@ __global__ void __launch_bounds__(256) knap_eval_kernel(const KnParams P) {
     o.var = in.var;
 
     int parent_slot = in.parent_slot, var = in.var;
-    const double best = P.best[in.inst];
+    const double best = in.best;
     if (in.parent_pending >= 0) {
         const KnOut po = P.out[in.parent_pending];
         // children are only wanted below a node the reference could push: feasible, fractional,
@@ -98,20 +106,37 @@ __global__ void __launch_bounds__(256) knap_eval_kernel(const KnParams P) {
                                 po.bound > best + KN_EPS;
         if (!expandable) {
             o.flags = KF_SKIPPED;
-            if (lane == 0) P.out[e] = o;
+            if (lane == 0) kn_store(P, e, o);
             return;
         }
-        parent_slot = P.in[in.parent_pending].out_slot;
+        parent_slot = in.parent_out_slot;
         var = P.orig_s[(size_t)in.inst * n + po.frac_rank];
         o.var = var;
     }
     const signed char* src = kn_slot(P, parent_slot);
     signed char* dst = kn_slot(P, in.out_slot);
-    for (int i = lane; i < n; i += 32) {
-        signed char a = src[i];
-        if (i == var) a = (signed char)in.side;
-        sa[i] = a;
-        dst[i] = a;
+    if ((n & 15) == 0) {
+        // 16 bytes per load: the parent's assignment is the longest dependent fetch of a relaxation
+        const int4* s4 = reinterpret_cast<const int4*>(src);
+        int4* d4 = reinterpret_cast<int4*>(dst);
+        int4* a4 = reinterpret_cast<int4*>(sa);
+        for (int q = lane; q < (n >> 4); q += 32) {
+            const int4 v = s4[q];
+            a4[q] = v;
+            d4[q] = v;
+        }
+        __syncwarp();
+        if (lane == 0 && var >= 0) {
+            sa[var] = (signed char)in.side;
+            dst[var] = (signed char)in.side;
+        }
+    } else {
+        for (int i = lane; i < n; i += 32) {
+            signed char a = src[i];
+            if (i == var) a = (signed char)in.side;
+            sa[i] = a;
+            dst[i] = a;
+        }
     }
     __syncwarp();
     const double* w_o = P.w_o + (size_t)in.inst * n;
@@ -143,13 +168,53 @@ __global__ void __launch_bounds__(256) knap_eval_kernel(const KnParams P) {
             o.bound = profit;
             o.weight = weight;
             o.flags = KF_INFEASIBLE | KF_EARLY;
-            if (lane == 0) P.out[e] = o;
+            if (lane == 0) kn_store(P, e, o);
             return;
         }
         int s_break = n;
-        for (int base = 0; base < n; base += 32) {
+        int scan_lo = 0, scan_hi = n;
+        bool nothing_breaks = false;
+        if (P.exact[in.inst] == 2) {
+            // Non-negative weights on top: the running weight is monotone, so the first item that does
+            // not fit lies in the first SEGMENT whose inclusive total does not fit.  Every lane sums one
+            // contiguous segment (independent loads, no cross-lane dependency), one warp scan ranks the
+            // segments, and only the breaking segment (<= ceil(n/32) items) is walked item by item below
+            // — 1 + 2 scans instead of n/32.
+            const int seg = (n + 31) / 32;
+            const int s0 = min(n, lane * seg), s1 = min(n, s0 + seg);
+            double lw = 0.0, lp = 0.0;
+#pragma unroll 4
+            for (int s = s0; s < s1; s++)
+                if (sa[orig_s[s]] < 0) {
+                    lw += w_s[s];
+                    lp += p_s[s];
+                }
+            double cw = lw, cp = lp;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const double ow = __shfl_up_sync(0xffffffffu, cw, off);
+                const double op = __shfl_up_sync(0xffffffffu, cp, off);
+                if (lane >= off) {
+                    cw += ow;
+                    cp += op;
+                }
+            }
+            const unsigned over = __ballot_sync(0xffffffffu, !((weight + cw) <= limit));
+            if (over == 0u) {
+                weight += __shfl_sync(0xffffffffu, cw, 31);
+                profit += __shfl_sync(0xffffffffu, cp, 31);
+                nothing_breaks = true;
+            } else {
+                const int L = __ffs(over) - 1;
+                weight += __shfl_sync(0xffffffffu, cw - lw, L);
+                profit += __shfl_sync(0xffffffffu, cp - lp, L);
+                scan_lo = min(n, L * seg);
+                scan_hi = min(n, scan_lo + seg);
+            }
+        }
+        for (int base = scan_lo; base < scan_hi && !nothing_breaks; base += 32) {
             const int s = base + lane;
-            const bool und = s < n && sa[orig_s[s]] < 0;
+            const bool und = s < scan_hi && sa[orig_s[s]] < 0;
             const double wv = und ? w_s[s] : 0.0, pv = und ? p_s[s] : 0.0;
             double cw = wv, cp = pv;
 #pragma unroll
@@ -192,7 +257,7 @@ __global__ void __launch_bounds__(256) knap_eval_kernel(const KnParams P) {
         if (o.frac_rank >= 0) allint = fabs(__dsub_rn(o.frac, rint(o.frac))) < KN_EPS;
         if (allint) o.flags |= KF_ALLINT;
         if (weight > limit) o.flags |= KF_INFEASIBLE;
-        P.out[e] = o;
+        kn_store(P, e, o);
         return;
     }
     if (lane != 0) return;
@@ -209,7 +274,7 @@ __global__ void __launch_bounds__(256) knap_eval_kernel(const KnParams P) {
         o.bound = profit;
         o.weight = weight;
         o.flags = KF_INFEASIBLE | KF_EARLY;
-        P.out[e] = o;
+        kn_store(P, e, o);
         return;
     }
     // 2) undecided items greedily in ratio order (:459-488)
@@ -240,7 +305,28 @@ __global__ void __launch_bounds__(256) knap_eval_kernel(const KnParams P) {
     if (o.frac_rank >= 0) allint = fabs(__dsub_rn(o.frac, rint(o.frac))) < KN_EPS;
     if (allint) o.flags |= KF_ALLINT;
     if (weight > limit) o.flags |= KF_INFEASIBLE;
-    P.out[e] = o;
+    kn_store(P, e, o);
+}
+
+// One round = all levels of the plan in ONE cooperative launch: 8 warps per CTA, a warp per relaxation,
+// a grid barrier between levels (children read their parent's result and assignment).  Inputs come
+// straight from pinned host memory and results are written through to it, so a round costs one launch
+// and one stream synchronisation instead of two uploads, a launch per level and a download.
+// Dynamic shared memory = 8 * n bytes.
+__global__ void __launch_bounds__(256) knap_round_kernel(const KnParams P) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) signed char sm_assign[];
+    const int warp = threadIdx.x >> 5;
+    signed char* sa = sm_assign + (size_t)warp * P.n;
+    const int gw = blockIdx.x * 8 + warp, nw = gridDim.x * 8;
+    for (int lv = 0; lv < P.nlev; lv++) {
+        for (int idx = gw; idx < P.lev_count[lv]; idx += nw) knap_eval_one(P, P.lev_first[lv] + idx, sa);
+        if (lv + 1 < P.nlev) {
+            __threadfence();
+            grid.sync();
+        }
+    }
 }
 
 namespace {
@@ -318,7 +404,7 @@ struct KnDriver {
     lpx_options opt;
     lpx_knap_pop_fn on_pop;
     void* user;
-    int spec_nodes = 16, spec_depth = 4;  // measured best of a small sweep on 16 x 2000-item instances
+    int spec_nodes = 16, spec_depth = 2;  // measured best of a sweep on 16 x 2000-item instances (tools/gpu_probe.py knapsweep)
     bool force_sequential = false;  // tests: take the ordered-summation path even for integer data
 
     std::vector<KInstance> inst;
@@ -468,8 +554,13 @@ struct KnDriver {
         }
     }
 
+    int coop_ctas = 1;
+    double tr_stage = 0, tr_launch = 0, tr_sync = 0, tr_unpack = 0;  // LPX_KNAP_TRACE: inside the device rounds
+    long tr_evals = 0;
+
     int run_plan(Plan& pl) {
         Runtime& r = rt();
+        const auto tp0 = std::chrono::steady_clock::now();
         const int total = (int)pl.in.size();
         if (total == 0) return LPX_OK;
         // order by level (stable), remapping parent_pending
@@ -479,15 +570,24 @@ struct KnDriver {
         for (int i = 0; i < total; i++) pos[order[i]] = i;
         KnIn* h_in = ws_pin_as<KnIn>(WS_KN_AUX, total);
         KnOut* h_out = ws_pin_as<KnOut>(WS_KN_OUT, total);
-        KnIn* d_in = ws_dev_as<KnIn>(WS_KN_AUX, total);
         KnOut* d_out = ws_dev_as<KnOut>(WS_KN_OUT, total);
-        double* h_best = ws_pin_as<double>(WS_MISC0, count);
-        if (!h_in || !h_out || !d_in || !d_out || !h_best) return LPX_E_CUDA;
+        if (!h_in || !h_out || !d_out) return LPX_E_CUDA;
+        // the kernel reads its inputs from, and writes its results through to, pinned host memory
+        KnIn* m_in = nullptr;
+        KnOut* m_out = nullptr;
+        LPX_CUDA(cudaHostGetDevicePointer((void**)&m_in, h_in, 0));
+        LPX_CUDA(cudaHostGetDevicePointer((void**)&m_out, h_out, 0));
         std::vector<int> rec_sorted(total);
         std::vector<int> level_first, level_count;
         for (int i = 0; i < total; i++) {
             KnIn in = pl.in[order[i]];
-            if (in.parent_pending >= 0) in.parent_pending = pos[in.parent_pending];
+            in.parent_out_slot = -1;
+            if (in.parent_pending >= 0) {
+                in.parent_out_slot = pl.in[in.parent_pending].out_slot;
+                in.parent_pending = pos[in.parent_pending];
+            }
+            in.pad = 0;
+            in.best = inst[in.inst].best;
             h_in[i] = in;
             rec_sorted[i] = pl.rec[order[i]];
             const int lv = pl.level[order[i]];
@@ -497,24 +597,37 @@ struct KnDriver {
             }
             level_count[lv]++;
         }
-        for (int k = 0; k < count; k++) h_best[k] = inst[k].best;
+        if ((int)level_first.size() > KN_MAX_LEVELS) {
+            set_error("knapsack: speculation depth exceeds the round kernel's level table");
+            return LPX_E_CAPACITY;
+        }
         cudaStream_t s = r.stream;
-        LPX_CUDA(cudaMemcpyAsync(d_in, h_in, (size_t)total * sizeof(KnIn), cudaMemcpyHostToDevice, s));
-        LPX_CUDA(cudaMemcpyAsync(d_best, h_best, (size_t)count * 8, cudaMemcpyHostToDevice, s));
         for (int k = 0; k < n_chunks; k++) P.chunks[k] = chunks[k];
-        P.in = d_in;
+        P.in = m_in;
         P.out = d_out;
-        const size_t smem = (size_t)8 * n;
+        P.out_host = m_out;
+        P.nlev = 0;
+        int widest = 0;
         for (size_t lv = 0; lv < level_first.size(); lv++) {
             if (level_count[lv] == 0) continue;
-            P.first = level_first[lv];
-            P.count = level_count[lv];
-            knap_eval_kernel<<<(P.count + 7) / 8, 256, smem, s>>>(P);
-            count_launch();
+            P.lev_first[P.nlev] = level_first[lv];
+            P.lev_count[P.nlev] = level_count[lv];
+            P.nlev++;
+            widest = std::max(widest, level_count[lv]);
         }
-        LPX_CUDA(cudaGetLastError());
-        LPX_CUDA(cudaMemcpyAsync(h_out, d_out, (size_t)total * sizeof(KnOut), cudaMemcpyDeviceToHost, s));
+        const size_t smem = (size_t)8 * n;
+        const int grid = std::max(1, std::min((widest + 7) / 8, coop_ctas));
+        void* args[] = {(void*)&P};
+        const auto tp1 = std::chrono::steady_clock::now();
+        LPX_CUDA(cudaLaunchCooperativeKernel((const void*)knap_round_kernel, dim3(grid), dim3(256), args, smem, s));
+        count_launch();
+        const auto tp2 = std::chrono::steady_clock::now();
         LPX_CUDA(cudaStreamSynchronize(s));
+        const auto tp3 = std::chrono::steady_clock::now();
+        tr_stage += std::chrono::duration<double>(tp1 - tp0).count();
+        tr_launch += std::chrono::duration<double>(tp2 - tp1).count();
+        tr_sync += std::chrono::duration<double>(tp3 - tp2).count();
+        tr_evals += total;
         for (int i = 0; i < total; i++) {
             EvalRec& rec = recs[rec_sorted[i]];
             rec.r = h_out[i];
@@ -706,6 +819,11 @@ struct KnDriver {
                 ap += std::fabs(pv);
             }
             h_exact[k] = ok && aw < 4503599627370496.0 && ap < 4503599627370496.0 && !force_sequential;
+            if (h_exact[k]) {
+                bool nonneg = true;
+                for (int i = 0; i < n; i++) nonneg = nonneg && weight[(size_t)k * n + i] >= 0.0;
+                if (nonneg) h_exact[k] = 2;  // lets the kernel rank whole segments before walking one
+            }
         }
         d_exact = ws_dev_as<int>(WS_KN_EXACT, count);
         if (!d_exact) return LPX_E_CUDA;
@@ -735,7 +853,12 @@ struct KnDriver {
         P.best = d_best;
         P.exact = d_exact;
         P.n = n;
-        LPX_CUDA(cudaFuncSetAttribute(knap_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * n)));
+        LPX_CUDA(cudaFuncSetAttribute(knap_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * n)));
+        {   // how many CTAs of the round kernel can be resident at once (a cooperative launch needs them all)
+            int per_sm = 0;
+            LPX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, knap_round_kernel, 256, (size_t)8 * n));
+            coop_ctas = std::max(1, per_sm * r.sms);
+        }
 
         // roots: all undecided (:101-113)
         {
@@ -811,8 +934,10 @@ struct KnDriver {
             }
             if (!any) {
                 if (getenv("LPX_KNAP_TRACE"))
-                    fprintf(stderr, "[knap trace] %ld rounds: plan %.3f s, device %.3f s, commit %.3f s\n", tr_rounds, tr[0],
-                            tr[1], tr[2]);
+                    fprintf(stderr,
+                            "[knap trace] %ld rounds: plan %.3f s, device %.3f s (stage %.3f, launch %.3f, wait %.3f; %ld "
+                            "relaxations), commit %.3f s\n",
+                            tr_rounds, tr[0], tr[1], tr_stage, tr_launch, tr_sync, tr_evals, tr[2]);
                 break;
             }
             const auto t1 = now();

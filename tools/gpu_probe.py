@@ -260,3 +260,15 @@ if __name__ == "__main__":
             us = e0.elapsed_time(e1) * 1e3 / (3 * per)
             s.close()
             print(json.dumps(dict(kblock=kb, us_per_pivot=us, pivots_per_s=1e6 / us, status=int(st))), flush=True)
+    if what == "knapsweep":
+        import time
+        ps, ws, caps = zip(*[workloads.knapsack_c5(seed=13 + k) for k in range(16)])
+        p, w, cap = np.stack(ps), np.stack(ws), np.array(caps)
+        api.bnb_knapsack_batched(p, w, cap)
+        for sn, sd in ((16, 4), (16, 2), (16, 1), (16, 3), (32, 2), (32, 1), (24, 2), (48, 2), (32, 3), (64, 2), (8, 2), (64, 1)):
+            best = 1e9
+            for rep in range(2):
+                t0 = time.perf_counter()
+                r = api.bnb_knapsack_batched(p, w, cap, spec_nodes=sn, spec_depth=sd)
+                best = min(best, time.perf_counter() - t0)
+            print(json.dumps(dict(spec_nodes=sn, spec_depth=sd, s=best, nodes_per_s=int(r["n_evals"].sum()) / best)), flush=True)
