@@ -4,12 +4,15 @@
 // The hot function is ComputeRelaxation (:431-491): a greedy fractional bound whose floating
 // point result depends on the ORDER of its additions (fixed-to-1 items in original index order,
 // then undecided items in ratio-rank order).  One warp evaluates one node: the lanes copy the
-// parent's assignment vector into the child's pool slot (coalesced) and stage it in shared
-// memory; lane 0 then performs the two sums in exactly the reference's order.
+// parent's assignment vector into the child's pool slot (16 bytes per load) and stage it in shared
+// memory; then either lane 0 performs the two sums in exactly the reference's order, or — when the
+// data are integers whose partial sums are exact, so that the order cannot matter — the whole warp
+// forms them by reduction / scan (segment-ranked when the weights are non-negative).
 //
 // GPU node pool: assignment vectors live in a device pool (n bytes per node).  Each round the
 // host speculates on the top-K heap nodes and asks the device for their subtrees down to depth D
-// (level by level; a level reads its parents' results on the device, no host round trip).
+// in ONE cooperative launch (knap_round_kernel: a grid barrier between levels, a level reads its
+// parents' results on the device; inputs and results travel through pinned host memory directly).
 // Relaxations are pure functions of the node, so the host then COMMITS in the reference's order:
 // its own max-heap with the reference's sift rules (:494-547), left child before right child,
 // incumbent updates exactly where the C# code makes them.  Speculative results that were not
@@ -64,7 +67,6 @@ struct KnParams {
     const double* w_o;   // [inst][n] weight by original index
     const double* p_o;   // [inst][n]
     const double* cap;   // [inst]
-    const double* best;  // [inst] incumbent when the round was planned
     const int* exact;    // [inst] 1: all weights/profits are integers with exact sums (order-free adds)
     int n;
     signed char* chunks[KN_MAX_CHUNKS];
@@ -414,7 +416,7 @@ struct KnDriver {
     int n_chunks = 0, next_slot = 0;
     signed char* chunks[KN_MAX_CHUNKS] = {};
     KnParams P{};
-    double *d_ws, *d_ps, *d_wo, *d_po, *d_cap, *d_best;
+    double *d_ws, *d_ps, *d_wo, *d_po, *d_cap;
     int *d_orig, *d_exact;
 
     ~KnDriver() {
@@ -831,8 +833,7 @@ struct KnDriver {
         d_ws = ws_dev_as<double>(WS_KN_ITEMS, cn * 4);
         d_orig = ws_dev_as<int>(WS_KN_ASSIGN, cn);
         d_cap = ws_dev_as<double>(WS_MISC1, count);
-        d_best = ws_dev_as<double>(WS_MISC2, count);
-        if (!d_ws || !d_orig || !d_cap || !d_best) return LPX_E_CUDA;
+        if (!d_ws || !d_orig || !d_cap) return LPX_E_CUDA;
         d_ps = d_ws + cn;
         d_wo = d_ws + 2 * cn;
         d_po = d_ws + 3 * cn;
@@ -850,7 +851,6 @@ struct KnDriver {
         P.w_o = d_wo;
         P.p_o = d_po;
         P.cap = d_cap;
-        P.best = d_best;
         P.exact = d_exact;
         P.n = n;
         LPX_CUDA(cudaFuncSetAttribute(knap_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * n)));

@@ -272,3 +272,10 @@ if __name__ == "__main__":
                 r = api.bnb_knapsack_batched(p, w, cap, spec_nodes=sn, spec_depth=sd)
                 best = min(best, time.perf_counter() - t0)
             print(json.dumps(dict(spec_nodes=sn, spec_depth=sd, s=best, nodes_per_s=int(r["n_evals"].sum()) / best)), flush=True)
+    if what == "smemshape":
+        for (m, n, th) in ((64, 128, 256), (90, 120, 256), (90, 120, 512), (110, 120, 512), (110, 120, 256)):
+            for cnt in (148, 1184):
+                r = time_batched(kernel=F.KERNEL_CTA_SMEM, threads=th, count=cnt, m=m, n=n, reps=3)
+                r["m"], r["n"], r["count"] = m, n, cnt
+                r["us_per_pivot_per_cta_if_1_per_sm"] = r["ms"] * 1e3 / (r["pivots"] / cnt) if cnt == 148 else None
+                print(json.dumps(r), flush=True)
