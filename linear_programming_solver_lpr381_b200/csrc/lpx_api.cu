@@ -179,6 +179,7 @@ void lpx_shutdown(void) {
     std::lock_guard<std::recursive_mutex> lk(r.mu);
     if (!r.ready) return;
     cudaDeviceSynchronize();
+    knapsack_release_cache();
     for (int s = 0; s < WS_COUNT; s++) {
         if (r.dev[s]) cudaFree(r.dev[s]);
         if (r.pin[s]) cudaFreeHost(r.pin[s]);

@@ -419,8 +419,23 @@ struct KnDriver {
     double *d_ws, *d_ps, *d_wo, *d_po, *d_cap;
     int *d_orig, *d_exact;
 
+    // Pool chunks (65 MB at n = 2000) are kept between calls: cudaMalloc / cudaFree of half a gigabyte per
+    // call cost more than the search itself in a process that holds many other allocations.
+    struct ChunkCache {
+        std::vector<signed char*> idle;
+        size_t bytes = 0;
+    };
+    static ChunkCache& chunk_cache() {
+        static ChunkCache c;
+        return c;
+    }
     ~KnDriver() {
-        for (int k = 0; k < n_chunks; k++) cudaFree(chunks[k]);
+        ChunkCache& cc = chunk_cache();
+        const size_t bytes = (size_t)KN_CHUNK_SLOTS * n;
+        for (int k = 0; k < n_chunks; k++) {
+            if (cc.bytes == bytes && cc.idle.size() < 16) cc.idle.push_back(chunks[k]);
+            else cudaFree(chunks[k]);
+        }
     }
 
     int alloc_slot() {
@@ -431,8 +446,18 @@ struct KnDriver {
         }
         if (next_slot >= n_chunks * KN_CHUNK_SLOTS) {
             if (n_chunks >= KN_MAX_CHUNKS) return -1;
+            ChunkCache& cc = chunk_cache();
+            const size_t bytes = (size_t)KN_CHUNK_SLOTS * n;
+            if (cc.bytes != bytes) {  // another item count: the idle chunks have the wrong size
+                for (signed char* q : cc.idle) cudaFree(q);
+                cc.idle.clear();
+                cc.bytes = bytes;
+            }
             void* p = nullptr;
-            if (cudaMalloc(&p, (size_t)KN_CHUNK_SLOTS * n) != cudaSuccess) {
+            if (!cc.idle.empty()) {
+                p = cc.idle.back();
+                cc.idle.pop_back();
+            } else if (cudaMalloc(&p, bytes) != cudaSuccess) {
                 cudaGetLastError();
                 return -1;
             }
@@ -970,6 +995,14 @@ struct KnDriver {
 };
 
 }  // namespace
+
+// idle pool chunks go with the device (lpx_shutdown)
+void knapsack_release_cache() {
+    KnDriver::ChunkCache& cc = KnDriver::chunk_cache();
+    for (signed char* q : cc.idle) cudaFree(q);
+    cc.idle.clear();
+    cc.bytes = 0;
+}
 }  // namespace lpx
 
 using namespace lpx;

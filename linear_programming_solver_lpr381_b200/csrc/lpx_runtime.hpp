@@ -35,6 +35,8 @@ Runtime& rt();
 // Returns nullptr (and sets the error) on failure.
 void* ws_dev(Slot s, size_t bytes);
 void* ws_pin(Slot s, size_t bytes);
+void knapsack_release_cache();  // lpx_knapsack.cu
+
 template <class T>
 T* ws_dev_as(Slot s, size_t count) { return static_cast<T*>(ws_dev(s, count * sizeof(T))); }
 template <class T>

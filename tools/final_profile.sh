@@ -12,6 +12,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 120 --csv --l
 ncu --set full --clock-control none --import-source on -k regex:stream_update_pipe_tma -s 10 -c 2 -f -o gpurun_out/prof_final_pass python bench.py --workload large --no-extras --steps 2 --warmup 3 > gpurun_out/n4.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:stream_lookahead_pipe -s 10 -c 1 -f -o gpurun_out/prof_final_la python bench.py --workload large --no-extras --steps 2 --warmup 3 > gpurun_out/n5.log 2>&1
 LPX_BNB_TRACE=1 python tools/gpu_probe.py bnbrep > gpurun_out/p3.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:cta_cluster_simplex -s 20 -c 1 -f -o gpurun_out/prof_final_cluster python tools/gpu_probe.py bnbrep > gpurun_out/n6.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:cta_cluster_simplex -s 90 -c 1 -f -o gpurun_out/prof_final_cluster python tools/gpu_probe.py bnbrep > gpurun_out/n6.log 2>&1
 cat gpurun_out/final_pytest.log
-tail -2 gpurun_out/n2.log gpurun_out/n4.log gpurun_out/n5.log gpurun_out/n6.log
+for f in n2 n4 n5 n6; do tail -n 2 gpurun_out/$f.log; done

@@ -279,3 +279,5 @@ if __name__ == "__main__":
                 r["m"], r["n"], r["count"] = m, n, cnt
                 r["us_per_pivot_per_cta_if_1_per_sm"] = r["ms"] * 1e3 / (r["pivots"] / cnt) if cnt == 148 else None
                 print(json.dumps(r), flush=True)
+    if what == "smemprof":
+        print(json.dumps(time_batched(kernel=F.KERNEL_CTA_SMEM, threads=512, count=592, m=90, n=120, reps=1)), flush=True)
