@@ -221,7 +221,7 @@ void bnb_trampoline(const lpx_bnb_node* nd, void* user) { static_cast<BnbReplay*
 
 SimplexResult BranchAndBound::Solve(const LPProblem& problem, UpdatePivot updatePivot) {
     const std::string& nl = NewLine();
-    BnbReplay rp{problem, flatten(problem), updatePivot};
+    BnbReplay rp{problem, flatten(problem), updatePivot, -std::numeric_limits<double>::infinity(), {}, {}, false};
     const Flat& f = rp.flat;
     rp.log("=== Branch & Bound Algorithm ===");
     {
@@ -251,8 +251,14 @@ SimplexResult BranchAndBound::Solve(const LPProblem& problem, UpdatePivot update
     throw_on(lpx_bnb_simplex(f.m, f.n, f.sense, f.A.data(), f.rel.data(), f.b.data(), f.c.data(), &opt,
                              updatePivot ? LPX_BNB_WANT_HISTORY : 0, &found, &best_z, best_x.data(), &n_nodes,
                              &lp_pivots, &root_status, updatePivot ? bnb_trampoline : nullptr, &rp));
-    if (root_status < 0) return SimplexResult{"LP relaxation infeasible", "Error: Infeasible"};
-    if (dual_root) return SimplexResult{"Invalid Simplex result", "Error: Invalid result"};
+    auto text_only = [](const char* report, const char* summary) {
+        SimplexResult r;
+        r.Report = report;
+        r.Summary = summary;
+        return r;
+    };
+    if (root_status < 0) return text_only("LP relaxation infeasible", "Error: Infeasible");
+    if (dual_root) return text_only("Invalid Simplex result", "Error: Invalid result");
     if (!rp.have_root) {
         int rows = 0, cols = 0, st = 0, np = 0;
         throw_on(lpx_tableau_dims(f.m, f.n, f.rel.data(), &rows, &cols));
