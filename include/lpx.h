@@ -72,7 +72,10 @@ typedef struct lpx_options {
                                 3 TMA-staged (cp.async.bulk + mbarrier pipeline) */
     int knap_ordered_sums; /* knapsack: 1 = always sum in the reference's order, even for exactly summable
                               integer data (which otherwise take the warp-parallel exact path) */
-    int reserved[6];
+    int knap_shard_tree;   /* knapsack: 1 = ONE search tree evaluated by all ranks of lpx_comm_init: every rank
+                              plans and commits identically, evaluates the speculative subtrees it owns
+                              (round robin), and the relaxations are merged by an NCCL all-reduce per round */
+    int reserved[5];
 } lpx_options;
 
 #define LPX_KERNEL_AUTO        0

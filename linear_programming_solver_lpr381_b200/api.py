@@ -258,12 +258,15 @@ def bnb_simplex(A, b, c, rel=None, sense=0, trace=False, want_history=False, **k
     return out
 
 
-def bnb_knapsack(profit, weight, capacity, trace=False, spec_nodes=0, spec_depth=0, sequential=False):
+def bnb_knapsack(profit, weight, capacity, trace=False, spec_nodes=0, spec_depth=0, sequential=False,
+                 shard_tree=False):
     p = np.ascontiguousarray(profit, dtype=np.float64)
     w = np.ascontiguousarray(weight, dtype=np.float64)
     n = p.shape[0]
     # sequential=True forces the ordered-summation kernel path even for exactly summable integer data
-    opt = F.make_options(spec_nodes=spec_nodes, spec_depth=spec_depth, ordered_sums=1 if sequential else 0)
+    # shard_tree=True: all ranks of lpx_comm_init work on this ONE tree (see lpx_options.knap_shard_tree)
+    opt = F.make_options(spec_nodes=spec_nodes, spec_depth=spec_depth, ordered_sums=1 if sequential else 0,
+                         shard_tree=1 if shard_tree else 0)
     found = C.c_int()
     best = C.c_double()
     bx = np.zeros(n, dtype=np.int32)

@@ -70,6 +70,17 @@ int ensure_buf(size_t bytes) {
 }
 
 }  // namespace
+
+// Exact merge of per-rank result buffers on the device: every 8-byte word is non-zero on at most one
+// rank, so an integer sum reproduces the owner's bits (no rounding, no sign-of-zero loss).
+int comm_merge_u64(unsigned long long* dev, size_t words, cudaStream_t s) {
+    if (!g_comm || words == 0) return LPX_OK;
+    ncclResult_t r = g_api.AllReduce(dev, dev, words, ncclUint64, ncclSum, g_comm, s);
+    if (r != ncclSuccess) return nccl_fail(r, "ncclAllReduce(u64 sum)");
+    return LPX_OK;
+}
+int comm_world() { return g_world; }
+int comm_rank() { return g_rank; }
 }  // namespace lpx
 
 using namespace lpx;

@@ -50,7 +50,7 @@ struct KnIn {
     int side;            // value to fix it to
     int out_slot;
     int parent_out_slot; // out_slot of parent_pending (filled by run_plan; saves a dependent read)
-    int pad;
+    int foreign;         // sharded tree: 1 = another rank evaluates this relaxation
     double best;         // the instance's incumbent when the round was planned (filled by run_plan)
 };
 
@@ -74,6 +74,7 @@ struct KnParams {
     KnOut* out;          // device copy of the results (children look their parent up here)
     KnOut* out_host;     // the same results written through to pinned host memory
     int nlev;
+    int pass;            // sharded tree: 0 = evaluate own entries, 1 = materialise the foreign ones (after the merge)
     int lev_first[KN_MAX_LEVELS], lev_count[KN_MAX_LEVELS];  // evaluations [first, first+count) form a level
 };
 
@@ -91,6 +92,35 @@ __device__ void knap_eval_one(const KnParams& P, int e, signed char* sa) {
     const int lane = threadIdx.x & 31;
     const KnIn in = P.in[e];
     const int n = P.n;
+    if (P.pass == 0 && in.foreign) {  // another rank's relaxation: all-zero words for the merge
+        if (lane == 0) {
+            KnOut zero;
+            memset(&zero, 0, sizeof zero);
+            P.out[e] = zero;
+        }
+        return;
+    }
+    if (P.pass == 1) {
+        // after the merge: give the foreign nodes their assignment vectors, so that every rank's pool
+        // is complete, and pass their results on to the host
+        if (!in.foreign) return;
+        const KnOut mine = P.out[e];
+        if (lane == 0) P.out_host[e] = mine;
+        if (mine.flags & KF_SKIPPED) return;  // its owner wrote no assignment either
+        int pslot = in.parent_slot, pvar = in.var;
+        if (in.parent_pending >= 0) {
+            pslot = in.parent_out_slot;
+            pvar = P.orig_s[(size_t)in.inst * n + P.out[in.parent_pending].frac_rank];
+        }
+        const signed char* src = kn_slot(P, pslot);
+        signed char* dst = kn_slot(P, in.out_slot);
+        for (int i = lane; i < n; i += 32) {
+            signed char a = src[i];
+            if (i == pvar) a = (signed char)in.side;
+            dst[i] = a;
+        }
+        return;
+    }
     KnOut o;
     o.bound = o.weight = o.frac = 0.0;
     o.frac_rank = -1;
@@ -324,6 +354,7 @@ __global__ void __launch_bounds__(256) knap_round_kernel(const KnParams P) {
     const int gw = blockIdx.x * 8 + warp, nw = gridDim.x * 8;
     for (int lv = 0; lv < P.nlev; lv++) {
         for (int idx = gw; idx < P.lev_count[lv]; idx += nw) knap_eval_one(P, P.lev_first[lv] + idx, sa);
+        __syncwarp();
         if (lv + 1 < P.nlev) {
             __threadfence();
             grid.sync();
@@ -527,6 +558,8 @@ struct KnDriver {
         std::vector<KnIn> in;
         std::vector<int> rec;    // EvalRec id per planned evaluation
         std::vector<int> level;
+        std::vector<int> owner;  // sharded tree: ordinal of the speculative subtree the evaluation belongs to
+        int subtrees = 0;
     };
 
     // plan the subtree of evaluation `id` (complete) down to `depth` levels
@@ -574,14 +607,17 @@ struct KnDriver {
                     pl.in.push_back(in);
                     pl.rec.push_back(ch);
                     pl.level.push_back(it.level);
+                    pl.owner.push_back(pl.subtrees);
                     ch_level = it.level + 1;
                 }
                 q.push_back({ch, ch_pending, it.depth - 1, ch_level});
             }
         }
+        pl.subtrees++;
     }
 
     int coop_ctas = 1;
+    int shard_world = 1, shard_rank = 0;  // > 1: one tree over all ranks of the communicator
     double tr_stage = 0, tr_launch = 0, tr_sync = 0, tr_unpack = 0;  // LPX_KNAP_TRACE: inside the device rounds
     long tr_evals = 0;
 
@@ -613,7 +649,7 @@ struct KnDriver {
                 in.parent_out_slot = pl.in[in.parent_pending].out_slot;
                 in.parent_pending = pos[in.parent_pending];
             }
-            in.pad = 0;
+            in.foreign = (shard_world > 1 && pl.owner[order[i]] % shard_world != shard_rank) ? 1 : 0;
             in.best = inst[in.inst].best;
             h_in[i] = in;
             rec_sorted[i] = pl.rec[order[i]];
@@ -646,8 +682,18 @@ struct KnDriver {
         const int grid = std::max(1, std::min((widest + 7) / 8, coop_ctas));
         void* args[] = {(void*)&P};
         const auto tp1 = std::chrono::steady_clock::now();
+        P.pass = 0;
         LPX_CUDA(cudaLaunchCooperativeKernel((const void*)knap_round_kernel, dim3(grid), dim3(256), args, smem, s));
         count_launch();
+        if (shard_world > 1) {
+            // the exchange step of the round: merge every rank's relaxations, then complete the pools
+            static_assert(sizeof(KnOut) % 8 == 0, "KnOut is merged as 8-byte words");
+            int rc = comm_merge_u64(reinterpret_cast<unsigned long long*>(d_out), (size_t)total * (sizeof(KnOut) / 8), s);
+            if (rc != LPX_OK) return rc;
+            P.pass = 1;
+            LPX_CUDA(cudaLaunchCooperativeKernel((const void*)knap_round_kernel, dim3(grid), dim3(256), args, smem, s));
+            count_launch();
+        }
         const auto tp2 = std::chrono::steady_clock::now();
         LPX_CUDA(cudaStreamSynchronize(s));
         const auto tp3 = std::chrono::steady_clock::now();
@@ -910,6 +956,7 @@ struct KnDriver {
                 pl.in.push_back(in);
                 pl.rec.push_back(id);
                 pl.level.push_back(0);
+                pl.owner.push_back(pl.subtrees++);
             }
             int rc = run_plan(pl);
             if (rc != LPX_OK) return rc;
@@ -981,6 +1028,18 @@ struct KnDriver {
                 if (rc != LPX_OK) return rc;
                 if (I.pops != before || I.done) progressed = true;
             }
+            if (shard_world > 1) {
+                // the 8-byte incumbent max-allreduce of the batch: with replicated commits it must be a no-op
+                std::vector<double> bests(count), mine(count);
+                for (int k = 0; k < count; k++) bests[k] = mine[k] = inst[k].best;
+                rc = lpx_comm_allreduce_max(bests.data(), count);
+                if (rc != LPX_OK) return rc;
+                for (int k = 0; k < count; k++)
+                    if (cmp_double(bests[k], mine[k]) != 0) {
+                        set_error("knapsack (sharded tree): ranks disagree on the incumbent");
+                        return LPX_E_NCCL;
+                    }
+            }
             tr[0] += secs(t0, t1);
             tr[1] += secs(t1, t2);
             tr[2] += secs(t2, now());
@@ -1032,6 +1091,10 @@ static int knapsack_entry(int count, int n, const double* profit, const double* 
     if (d.opt.knap_spec_nodes > 0) d.spec_nodes = d.opt.knap_spec_nodes;
     if (d.opt.knap_spec_depth > 0) d.spec_depth = d.opt.knap_spec_depth;
     d.force_sequential = d.opt.knap_ordered_sums != 0;
+    if (d.opt.knap_shard_tree && comm_world() > 1) {
+        d.shard_world = comm_world();
+        d.shard_rank = comm_rank();
+    }
     d.on_pop = on_pop;
     d.user = user;
     rc = d.run();

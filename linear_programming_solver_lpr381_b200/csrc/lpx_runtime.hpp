@@ -36,6 +36,9 @@ Runtime& rt();
 void* ws_dev(Slot s, size_t bytes);
 void* ws_pin(Slot s, size_t bytes);
 void knapsack_release_cache();  // lpx_knapsack.cu
+int comm_merge_u64(unsigned long long* dev, size_t words, cudaStream_t s);  // lpx_comm.cu
+int comm_world();
+int comm_rank();
 
 template <class T>
 T* ws_dev_as(Slot s, size_t count) { return static_cast<T*>(ws_dev(s, count * sizeof(T))); }
