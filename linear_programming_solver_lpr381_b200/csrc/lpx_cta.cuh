@@ -153,53 +153,74 @@ __device__ __forceinline__ void cta_copy_out(double* dst, const double* T, int l
     }
 }
 
-template <int THREADS, bool SMEM_T>
-__global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = THREADS / 32;
-    const int p = blockIdx.x;
-
-    const int inst = B.node_inst ? B.node_inst[p] : p;
-    const int nex = B.node_extra_cnt ? B.node_extra_cnt[p] : 0;
-    const int exo = B.node_extra_off ? B.node_extra_off[p] : 0;
-    const int mode = B.node_mode ? B.node_mode[p] : B.mode;
-    const int n = B.n;
-    const int m = B.m_base + nex;
-    const int rows = m + 1, width = n + m + 1, ld = width;
-    const int rhs = width - 1;
-
-    const CtaCarve cv = cta_carve(B.max_rows, B.max_width, SMEM_T);
-    double* prow = reinterpret_cast<double*>(smem_raw + cv.prow);
-    double* fcol = reinterpret_cast<double*>(smem_raw + cv.fcol);
-    ArgMin* red = reinterpret_cast<ArgMin*>(smem_raw + cv.red);
-    int* rsrc = reinterpret_cast<int*>(smem_raw + cv.rsrc);
-    int* rsgn = reinterpret_cast<int*>(smem_raw + cv.rsgn);
-    int* sbasis = reinterpret_cast<int*>(smem_raw + cv.basis);
-    int* ctl = reinterpret_cast<int*>(smem_raw + cv.ctl);
-    double* T;
-    if (SMEM_T) T = reinterpret_cast<double*>(smem_raw + cv.T);
-    else T = B.tableau ? B.tableau + (size_t)p * B.tableau_stride : B.scratch + (size_t)p * B.scratch_stride;
-
-    const double* Ai = B.A + (size_t)inst * B.strideA;
-    const double* bi = B.b + (size_t)inst * B.strideB;
-    const double* ci = B.c + (size_t)inst * B.strideC;
-
-    // ---- row map + the reference's up-front checks (PrimalSimplex.cs:66-77) -------------------
-    if (tid == 0) {
-        int st = LPX_RUNNING, k = 0;
-        for (int r = 0; r < B.m_in + nex; r++) {
+// Row map of one tableau: tableau row k <- (source row, sign), after ExpandEqualitiesToInequalities
+// (PrimalSimplex.cs:161-177) or PrepareForTableau (DualSimplex.cs:117-158), plus the reference's up-front
+// checks (PrimalSimplex.cs:66-77).  ctl[0] = status, ctl[1] = number of tableau rows m.
+// Without '=' rows the map is the identity and is filled by all threads (a B&B node at depth 120 has
+// 180 rows; one thread walking them through global memory was 4-15 % of a node solve); with '=' rows
+// one thread walks the rows in order.  Ends with the caller's barrier.
+template <int THREADS>
+__device__ __forceinline__ void cta_row_map(const CtaBatch& B, const double* bi, int nex, int exo, int mode, int* rsrc,
+                                            int* rsgn, int* ctl) {
+    const int tid = threadIdx.x;
+    const int nr = B.m_in + nex;
+    auto fetch = [&](int r, int& rl, double& bv, int& src) {
+        if (r < B.m_in) {
+            rl = B.rel ? B.rel[r] : 0;
+            bv = bi[r];
+            src = r;
+        } else {
+            rl = B.ex_rel[exo + r - B.m_in];
+            bv = B.ex_rhs[exo + r - B.m_in];
+            src = -1 - (r - B.m_in);
+        }
+    };
+    int has_eq = 0;
+    for (int r = tid; r < nr; r += THREADS) {
+        int rl, src;
+        double bv;
+        fetch(r, rl, bv, src);
+        if (rl == 2) has_eq = 1;
+    }
+    if (tid == 0) ctl[4] = INT_MAX;
+    if (!__syncthreads_or(has_eq)) {
+        for (int r = tid; r < nr; r += THREADS) {
             int rl, src;
             double bv;
-            if (r < B.m_in) {
-                rl = B.rel ? B.rel[r] : 0;
-                bv = bi[r];
-                src = r;
+            fetch(r, rl, bv, src);
+            int flip = 0;
+            if (mode == 0) {
+                if (rl == 1 || bv < -1e-9) atomicMin(&ctl[4], r);  // the FIRST offending row decides the message
             } else {
-                rl = B.ex_rel[exo + r - B.m_in];
-                bv = B.ex_rhs[exo + r - B.m_in];
-                src = -1 - (r - B.m_in);
+                if (rl == 1) {
+                    flip ^= 1;
+                    bv = __dmul_rn(bv, -1.0);
+                }
+                if (bv < -LPX_EPS) flip ^= 1;
             }
+            rsrc[r] = src;
+            rsgn[r] = flip;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int st = LPX_RUNNING;
+            if (mode == 0 && ctl[4] != INT_MAX) {
+                int rl, src;
+                double bv;
+                fetch(ctl[4], rl, bv, src);
+                st = rl == 1 ? LPX_S_GE_ROW : LPX_S_NEG_RHS;
+            }
+            ctl[0] = st;
+            ctl[1] = nr;
+        }
+        return;
+    }
+    if (tid == 0) {
+        int st = LPX_RUNNING, k = 0;
+        for (int r = 0; r < nr; r++) {
+            int rl, src;
+            double bv;
+            fetch(r, rl, bv, src);
             if (mode == 0) {
                 if (st == LPX_RUNNING) {
                     if (rl == 1) st = LPX_S_GE_ROW;
@@ -237,6 +258,42 @@ __global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) 
         ctl[0] = st;
         ctl[1] = k;  // == m
     }
+}
+
+template <int THREADS, bool SMEM_T>
+__global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = THREADS / 32;
+    const int p = blockIdx.x;
+
+    const int inst = B.node_inst ? B.node_inst[p] : p;
+    const int nex = B.node_extra_cnt ? B.node_extra_cnt[p] : 0;
+    const int exo = B.node_extra_off ? B.node_extra_off[p] : 0;
+    const int mode = B.node_mode ? B.node_mode[p] : B.mode;
+    const int n = B.n;
+    const int m = B.m_base + nex;
+    const int rows = m + 1, width = n + m + 1, ld = width;
+    const int rhs = width - 1;
+
+    const CtaCarve cv = cta_carve(B.max_rows, B.max_width, SMEM_T);
+    double* prow = reinterpret_cast<double*>(smem_raw + cv.prow);
+    double* fcol = reinterpret_cast<double*>(smem_raw + cv.fcol);
+    ArgMin* red = reinterpret_cast<ArgMin*>(smem_raw + cv.red);
+    int* rsrc = reinterpret_cast<int*>(smem_raw + cv.rsrc);
+    int* rsgn = reinterpret_cast<int*>(smem_raw + cv.rsgn);
+    int* sbasis = reinterpret_cast<int*>(smem_raw + cv.basis);
+    int* ctl = reinterpret_cast<int*>(smem_raw + cv.ctl);
+    double* T;
+    if (SMEM_T) T = reinterpret_cast<double*>(smem_raw + cv.T);
+    else T = B.tableau ? B.tableau + (size_t)p * B.tableau_stride : B.scratch + (size_t)p * B.scratch_stride;
+
+    const double* Ai = B.A + (size_t)inst * B.strideA;
+    const double* bi = B.b + (size_t)inst * B.strideB;
+    const double* ci = B.c + (size_t)inst * B.strideC;
+
+    // ---- row map + the reference's up-front checks (PrimalSimplex.cs:66-77) -------------------
+    cta_row_map<THREADS>(B, bi, nex, exo, mode, rsrc, rsgn, ctl);
     __syncthreads();
     int status = ctl[0];
 

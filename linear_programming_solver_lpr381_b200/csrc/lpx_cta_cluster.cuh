@@ -96,57 +96,7 @@ __global__ void __launch_bounds__(THREADS) cta_cluster_simplex_kernel(const CtaB
     const double* ci = B.c + (size_t)inst * B.strideC;
 
     // ---- row map + the reference's up-front checks, replicated in every CTA (PrimalSimplex.cs:66-77)
-    if (tid == 0) {
-        int st = LPX_RUNNING, k = 0;
-        for (int r = 0; r < B.m_in + nex; r++) {
-            int rl, src;
-            double bv;
-            if (r < B.m_in) {
-                rl = B.rel ? B.rel[r] : 0;
-                bv = bi[r];
-                src = r;
-            } else {
-                rl = B.ex_rel[exo + r - B.m_in];
-                bv = B.ex_rhs[exo + r - B.m_in];
-                src = -1 - (r - B.m_in);
-            }
-            if (mode == 0) {
-                if (st == LPX_RUNNING) {
-                    if (rl == 1) st = LPX_S_GE_ROW;
-                    else if (bv < -1e-9) st = LPX_S_NEG_RHS;
-                }
-                rsrc[k] = src;
-                rsgn[k] = 0;
-                k++;
-                if (rl == 2) {
-                    rsrc[k] = src;
-                    rsgn[k] = 1;
-                    k++;
-                }
-            } else {
-                if (rl == 2) {
-                    rsrc[k] = src;
-                    rsgn[k] = 0;
-                    k++;
-                    rsrc[k] = src;
-                    rsgn[k] = 1;
-                    k++;
-                } else {
-                    int flip = 0;
-                    if (rl == 1) {
-                        flip ^= 1;
-                        bv = __dmul_rn(bv, -1.0);
-                    }
-                    if (bv < -LPX_EPS) flip ^= 1;
-                    rsrc[k] = src;
-                    rsgn[k] = flip;
-                    k++;
-                }
-            }
-        }
-        ctl[0] = st;
-        ctl[1] = k;  // == m
-    }
+    cta_row_map<THREADS>(B, bi, nex, exo, mode, rsrc, rsgn, ctl);
     __syncthreads();
     int status = ctl[0];
 
