@@ -281,3 +281,28 @@ if __name__ == "__main__":
                 print(json.dumps(r), flush=True)
     if what == "smemprof":
         print(json.dumps(time_batched(kernel=F.KERNEL_CTA_SMEM, threads=512, count=592, m=90, n=120, reps=1)), flush=True)
+    if what == "knapweak":
+        import time
+        for kind in ("uncorrelated", "weak"):
+            ps, ws, caps = zip(*[workloads.knapsack_c5(seed=13 + k, kind=kind) for k in range(16)])
+            p, w, cap = np.stack(ps), np.stack(ws), np.array(caps)
+            api.bnb_knapsack_batched(p, w, cap)
+            best = 1e9
+            for rep in range(3):
+                t0 = time.perf_counter()
+                r = api.bnb_knapsack_batched(p, w, cap)
+                best = min(best, time.perf_counter() - t0)
+            print(json.dumps(dict(kind=kind, s=best, nodes=int(r["n_evals"].sum()), nodes_per_s=int(r["n_evals"].sum()) / best,
+                                  per_instance=r["n_evals"].tolist())), flush=True)
+    if what == "knapsingle":
+        import time
+        for kind, seed in (("uncorrelated", 13), ("weak", 22)):
+            p, w, cap = workloads.knapsack_c5(seed=seed, kind=kind)
+            api.bnb_knapsack(p, w, cap)
+            for sn, sd in ((16, 2), (32, 2), (64, 2), (128, 2), (64, 3), (128, 3), (256, 2)):
+                best = 1e9
+                for rep in range(2):
+                    t0 = time.perf_counter()
+                    r = api.bnb_knapsack(p, w, cap, spec_nodes=sn, spec_depth=sd)
+                    best = min(best, time.perf_counter() - t0)
+                print(json.dumps(dict(kind=kind, spec_nodes=sn, spec_depth=sd, s=best, nodes_per_s=r["n_evals"] / best)), flush=True)
