@@ -177,3 +177,20 @@ def test_empty_and_blank_inputs(lpx, orc):
     for text in ("", "\n\n", "Max: 3x1\n"):
         want, got = orc.solve_text(text, "Primal Simplex"), H.solve_text(text, "Primal Simplex")
         assert got["error"] == want["error"] == "Input must contain an objective and at least one constraint."
+
+
+def test_windows_newlines(lpx, orc):
+    """Environment.NewLine is "\r\n" where the reference runs; literal "\n" inside format strings stay."""
+    import orc_ffi
+    texts = [(workloads.WYNDOR_TEXT, a) for a in ("Primal Simplex", "Dual Simplex", "Branch and Bound",
+                                                   "Revised Primal Simplex", "cutting plane", "revised cutting plane")]
+    texts.append(("Max: 60x1 + 100x2 + 120x3\n10x1 + 20x2 + 30x3 <= 50\n", "knapsack"))
+    orc_ffi.lib().orc_set_newline(b"\r\n")
+    H.lib().lpr_set_newline(b"\r\n")
+    try:
+        for text, algo in texts:
+            got = same_text(orc, text, algo)
+            assert "\r\n" in got["report"] + got["log"], algo
+    finally:
+        orc_ffi.lib().orc_set_newline(b"\n")
+        H.lib().lpr_set_newline(b"\n")
