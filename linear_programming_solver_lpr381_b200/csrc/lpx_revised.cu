@@ -372,7 +372,15 @@ int lpx_revised_solve(int m, int n, int sense, const double* A, const int* rel, 
     LPX_CUDA(cudaStreamSynchronize(s));
     *status = hstat[0];
     if (n_iters) *n_iters = hstat[1];
-    if (hstat[0] != LPX_S_SINGULAR) {
+    if (hstat[0] == LPX_S_SINGULAR) {
+        // Invert threw inside iteration n_iters (or on the initial basis when n_iters == 0): the blocks of
+        // the iterations before it had already been printed, so their records are returned
+        if (history && history_cap && hstat[1] > 0) {
+            const int nh = std::min(hstat[1], history_cap);
+            LPX_CUDA(cudaMemcpyAsync(history, dH, hs * nh * 8, cudaMemcpyDeviceToHost, s));
+            LPX_CUDA(cudaStreamSynchronize(s));
+        }
+    } else {
         const int np = std::min(hstat[1], pivots_cap);
         if (np > 0) {
             LPX_CUDA(cudaMemcpyAsync(pivots, dpiv, (size_t)np * 8, cudaMemcpyDeviceToHost, s));

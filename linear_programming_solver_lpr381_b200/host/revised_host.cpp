@@ -104,7 +104,7 @@ SimplexResult RevisedPrimalSimplex::Solve(const LPProblem& original, UpdatePivot
         // the engine returns every iteration's record in one call; a first pass sizes the buffer
         throw_on(lpx_revised_solve(f.m, f.n, f.sense, f.A.data(), f.rel.data(), f.b.data(), f.c.data(), &opt, &status,
                                    &iters, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0));
-        if (status >= 0 || status == LPX_S_ITER_LIMIT) {
+        if (status >= 0 || status == LPX_S_ITER_LIMIT || status == LPX_S_SINGULAR) {
             hist_cap = iters + 1;
             hist.resize(lpx_revised_history_stride(f.m, f.n) * (size_t)hist_cap);
         }
@@ -120,7 +120,7 @@ SimplexResult RevisedPrimalSimplex::Solve(const LPProblem& original, UpdatePivot
     if (updatePivot) {
         const size_t hs = lpx_revised_history_stride(f.m, f.n);
         // a singular basis is met inside Invert, before the block of that iteration is printed
-        const int blocks = status == LPX_S_SINGULAR ? 0 : std::min(hist_cap, iters + 1);
+        const int blocks = std::min(hist_cap, status == LPX_S_SINGULAR ? iters : iters + 1);
         for (int k = 0; k < blocks; k++) {
             const RevRecord r = view(hist.data() + hs * k, f.m, f.n);
             Highlight hl;
