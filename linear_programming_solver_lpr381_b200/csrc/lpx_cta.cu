@@ -96,8 +96,10 @@ int cta_launch(const CtaBatch& B, int count, int kernel_pref, int threads_pref, 
     if (used_smem) *used_smem = smem_T;
     int threads = threads_pref;
     if (threads != 128 && threads != 256 && threads != 512) {
-        // narrow tableaux: 256; wide or global-memory ones: 512 for more loads in flight
-        threads = (!smem_T || B.max_width > 256) ? 512 : 256;
+        // small tableaux: 256; from about 8 k elements on (and for global-memory ones) 512 threads keep more
+        // loads in flight and win despite the dearer barriers (measured: 64x128 2.54 -> 2.36 ms per 4096 LPs,
+        // 90x120 1.89 -> 1.51 ms per 1184; tools/gpu_probe.py smemshape)
+        threads = (!smem_T || (size_t)B.max_rows * B.max_width >= 8192) ? 512 : 256;
     }
     if (smem_T) {
         if (threads == 128) return launch_variant<128, true>(B, count, smem, stream);
