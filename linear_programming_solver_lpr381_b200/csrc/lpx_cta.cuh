@@ -64,7 +64,7 @@ __host__ __device__ inline CtaCarve cta_carve(int max_rows, int max_width, bool 
     CtaCarve c;
     size_t off = 0;
     c.prow = off;
-    off += (size_t)max_width * 8;
+    off += (size_t)((max_width + 2) & ~1) * 8;  // even length: the update reads it two entries at a time
     c.fcol = off;
     off += (size_t)max_rows * 8;
     c.red = off;
@@ -79,7 +79,7 @@ __host__ __device__ inline CtaCarve cta_carve(int max_rows, int max_width, bool 
     off += 16 * 4;
     off = (off + 15) & ~(size_t)15;
     c.T = off;
-    if (smem_T) off += (size_t)max_rows * max_width * 8;
+    if (smem_T) off += (size_t)max_rows * ((max_width + 1) & ~1) * 8;  // rows padded to an even length (16-byte aligned)
     c.total = off;
     return c;
 }
@@ -92,14 +92,47 @@ __device__ __forceinline__ double dneg(double v) {
 // The factor column and the normalised pivot row are staged in shared memory first, so every
 // element sees factor = T[i,e] as it was BEFORE row i changed and the ROUNDED quotient T[l,j]/piv.
 // Rows with factor 0 are updated too (sign-of-zero parity).
-template <int THREADS>
+// PAIR (shared-memory tableau, even ld): every thread updates two adjacent columns with 16-byte loads
+// and stores — half the memory instructions for the same bytes; the pad column of an odd width is
+// carried along and never read back.
+template <int THREADS, bool PAIR = false>
 __device__ __forceinline__ void cta_pivot(double* T, int ld, int rows, int width, int l, int e, double* prow,
                                           double* fcol) {
     const int tid = threadIdx.x;
     const double piv = T[(size_t)l * ld + e];
     for (int j = tid; j < width; j += THREADS) prow[j] = ddiv_by_pivot(T[(size_t)l * ld + j], piv);
     for (int i = tid; i < rows; i += THREADS) fcol[i] = T[(size_t)i * ld + e];
+    if (PAIR && tid == 0 && (width & 1)) prow[width] = 0.0;
     __syncthreads();
+    if (PAIR) {
+        const int pairs = (width + 1) >> 1;
+        const int cw2 = (pairs + 31) & ~31;
+        const int G = cw2 >= THREADS ? 1 : THREADS / cw2;
+        for (int q0 = 0; q0 < pairs; q0 += THREADS) {  // one trip unless the tableau is wider than 2 * THREADS
+            const int g = cw2 >= THREADS ? 0 : tid / cw2;
+            const int q = cw2 >= THREADS ? q0 + tid : tid - g * cw2;
+            if (g < G && q < pairs) {
+                const double2 pj = *reinterpret_cast<const double2*>(prow + 2 * q);
+                double* t = T + (size_t)g * ld + 2 * q;
+                const size_t step = (size_t)G * ld;
+#pragma unroll 4
+                for (int i = g; i < rows; i += G, t += step) {
+                    double2 cur = *reinterpret_cast<double2*>(t);
+                    const double f = fcol[i];
+                    if (i == l) {
+                        cur = pj;
+                    } else {
+                        cur.x = __dsub_rn(cur.x, __dmul_rn(f, pj.x));
+                        cur.y = __dsub_rn(cur.y, __dmul_rn(f, pj.y));
+                    }
+                    *reinterpret_cast<double2*>(t) = cur;
+                }
+            }
+            if (cw2 < THREADS) break;
+        }
+        __syncthreads();
+        return;
+    }
     const int cw = (width + 31) & ~31;
     if (cw >= THREADS) {
         for (int j = tid; j < width; j += THREADS) {
@@ -273,7 +306,7 @@ __global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) 
     const int mode = B.node_mode ? B.node_mode[p] : B.mode;
     const int n = B.n;
     const int m = B.m_base + nex;
-    const int rows = m + 1, width = n + m + 1, ld = width;
+    const int rows = m + 1, width = n + m + 1, ld = SMEM_T ? ((width + 1) & ~1) : width;
     const int rhs = width - 1;
 
     const CtaCarve cv = cta_carve(B.max_rows, B.max_width, SMEM_T);
@@ -336,6 +369,8 @@ __global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) 
                 }
             }
         }
+        if (ld > width)
+            for (int i = tid; i < rows; i += THREADS) T[(size_t)i * ld + width] = 0.0;  // pad column
         for (int i = tid; i < m; i += THREADS) sbasis[i] = n + i;
         __syncthreads();
 
@@ -357,7 +392,7 @@ __global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) 
                 __syncthreads();
                 const int l = ctl[2];
                 if (l < 0) break;
-                cta_pivot<THREADS>(T, ld, rows, width, l, e, prow, fcol);
+                cta_pivot<THREADS, SMEM_T>(T, ld, rows, width, l, e, prow, fcol);
                 if (tid == 0) {
                     sbasis[l] = e;
                     if (plog && n_piv < B.pivots_cap) {
@@ -436,7 +471,7 @@ __global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) 
                     break;
                 }
             }
-            cta_pivot<THREADS>(T, ld, rows, width, l, e, prow, fcol);
+            cta_pivot<THREADS, SMEM_T>(T, ld, rows, width, l, e, prow, fcol);
             if (tid == 0) {
                 sbasis[l] = e;
                 if (plog && n_piv < B.pivots_cap) {
