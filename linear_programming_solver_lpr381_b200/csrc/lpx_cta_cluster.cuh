@@ -31,7 +31,7 @@ __host__ __device__ inline CtaClusterCarve cta_cluster_carve(int max_rows, int m
     const int vec = max_rows > max_width ? max_rows : max_width;
     size_t off = 0;
     c.prow = off;
-    off += (size_t)max_width * 8;
+    off += (size_t)((max_width + 2) & ~1) * 8;  // even length: the update reads it two entries at a time
     c.ratio = off;
     off += (size_t)vec * 8;
     c.fcol = off;
@@ -50,7 +50,7 @@ __host__ __device__ inline CtaClusterCarve cta_cluster_carve(int max_rows, int m
     off += 16 * 4;
     off = (off + 15) & ~(size_t)15;
     c.T = off;
-    off += (size_t)c.H * max_width * 8;
+    off += (size_t)c.H * ((max_width + 1) & ~1) * 8;  // rows padded to an even length (16-byte aligned)
     c.total = off;
     return c;
 }
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(THREADS) cta_cluster_simplex_kernel(const CtaB
     const int mode = B.node_mode ? B.node_mode[p] : B.mode;
     const int n = B.n;
     const int m = B.m_base + nex;
-    const int rows = m + 1, width = n + m + 1, ld = width;
+    const int rows = m + 1, width = n + m + 1, ld = (width + 1) & ~1;
     const int rhs = width - 1;
     const int H = (rows + CL - 1) / CL;                  // rows per CTA for THIS tableau
     const int r_lo = min(rows, rank * H), r_hi = min(rows, r_lo + H);
@@ -140,6 +140,10 @@ __global__ void __launch_bounds__(THREADS) cta_cluster_simplex_kernel(const CtaB
                 }
             }
         }
+        if (ld > width) {  // pad column and pad entry of the pivot row (never read back, kept finite)
+            for (int i = r_lo + tid; i < r_hi; i += THREADS) loc(i)[width] = 0.0;
+            if (tid == 0) prow[width] = 0.0;
+        }
         for (int i = tid; i < m; i += THREADS) sbasis[i] = n + i;
         __syncthreads();
 
@@ -194,30 +198,31 @@ __global__ void __launch_bounds__(THREADS) cta_cluster_simplex_kernel(const CtaB
             }
             for (int i = r_lo + tid; i < r_hi; i += THREADS) fcol[i - r_lo] = loc(i)[e];
             __syncthreads();
-            const int cw = (width + 31) & ~31;
-            if (cw >= THREADS) {
-                for (int j = tid; j < width; j += THREADS) {
-                    const double pj = prow[j];
-                    double* t = T + j;
-#pragma unroll 4
-                    for (int i = r_lo; i < r_hi; i++, t += ld) {
-                        const double cur = *t;
-                        *t = (i == l) ? pj : __dsub_rn(cur, __dmul_rn(fcol[i - r_lo], pj));
-                    }
-                }
-            } else {
-                const int G = THREADS / cw;
-                const int g = tid / cw, j = tid - g * cw;
-                if (g < G && j < width) {
-                    const double pj = prow[j];
-                    double* t = T + (size_t)g * ld + j;
+            // two adjacent columns per thread, 16-byte shared accesses (rows start 16-byte aligned)
+            const int pairs = (width + 1) >> 1;
+            const int cw2 = (pairs + 31) & ~31;
+            const int G = cw2 >= THREADS ? 1 : THREADS / cw2;
+            for (int q0 = 0; q0 < pairs; q0 += THREADS) {
+                const int g = cw2 >= THREADS ? 0 : tid / cw2;
+                const int q = cw2 >= THREADS ? q0 + tid : tid - g * cw2;
+                if (g < G && q < pairs) {
+                    const double2 pj = *reinterpret_cast<const double2*>(prow + 2 * q);
+                    double* t = T + (size_t)g * ld + 2 * q;
                     const size_t step = (size_t)G * ld;
 #pragma unroll 4
                     for (int i = r_lo + g; i < r_hi; i += G, t += step) {
-                        const double cur = *t;
-                        *t = (i == l) ? pj : __dsub_rn(cur, __dmul_rn(fcol[i - r_lo], pj));
+                        double2 cur = *reinterpret_cast<double2*>(t);
+                        const double f = fcol[i - r_lo];
+                        if (i == l) {
+                            cur = pj;
+                        } else {
+                            cur.x = __dsub_rn(cur.x, __dmul_rn(f, pj.x));
+                            cur.y = __dsub_rn(cur.y, __dmul_rn(f, pj.y));
+                        }
+                        *reinterpret_cast<double2*>(t) = cur;
                     }
                 }
+                if (cw2 < THREADS) break;
             }
             __syncthreads();
         };
