@@ -2,7 +2,7 @@
 against the oracle, bit for bit, on shapes and data chosen to stress ties, near-ties inside the
 margins, zero pivots rows/columns, degenerate and unbounded instances.
 
-    python tools/fuzz_parity.py [seed] [rounds]
+    python tests/fuzz_parity.py [seed] [rounds]
 """
 import os
 import sys
