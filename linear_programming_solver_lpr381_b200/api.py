@@ -241,8 +241,8 @@ def bnb_simplex(A, b, c, rel=None, sense=0, trace=False, want_history=False, **k
                    n_pivots=nd.n_pivots, silent=nd.silent_pivots, rows=nd.rows, cols=nd.cols, z=nd.z,
                    x=np.array([nd.x[i] for i in range(n)]) if nd.x else None, branch_var=nd.branch_var,
                    floor_val=nd.floor_val, ceil_val=nd.ceil_val,
-                   pivots=np.array([nd.pivots[i] for i in range(2 * min(nd.n_pivots, 4096))],
-                                   dtype=np.int32).reshape(-1, 2) if nd.pivots else None)
+                   pivots=np.ctypeslib.as_array(nd.pivots, shape=(2 * nd.n_pivots,)).copy().reshape(-1, 2)
+                   if nd.pivots and nd.n_pivots else None)
         if nd.n_history:
             cnt = nd.n_history * nd.rows * nd.cols
             rec["history"] = np.ctypeslib.as_array(nd.history, shape=(cnt,)).copy().reshape(nd.n_history, nd.rows,

@@ -165,7 +165,9 @@ struct Driver {
             std::vector<Node*>& G = group[g];
             if (G.empty()) continue;
             const bool want_piv = on_node != nullptr;
-            const int pivots_cap = want_piv ? std::min(opt.max_iterations + 100, 4096) : 0;
+            // every pivot of a node is logged: a primal node makes at most max_iterations, a dual node at most
+            // 100 silent + LPX_DUAL_MAX_ITER (consumers index pivots[0 .. n_pivots), include/lpx.h)
+            const int pivots_cap = want_piv ? std::max(opt.max_iterations, LPX_DUAL_MAX_ITER) + 100 : 0;
             if (!want_history) {
                 int rc = launch_group(G, 0, G.size(), pivots_cap, 0);
                 if (rc != LPX_OK) return rc;

@@ -19,6 +19,7 @@
 #define LPX_EPS 1e-9            // PrimalSimplex.Eps / DualSimplex.Eps
 #define LPX_MARGIN_PRIMAL 1e-9  // PrimalSimplex.cs:235
 #define LPX_MARGIN_DUAL 1e-12   // DualSimplex.cs:85,220
+#define LPX_DUAL_MAX_ITER 10000  // DualSimplex.cs:39: a literal, independent of PrimalSimplex.MaxIterations
 
 namespace lpx {
 

@@ -237,6 +237,45 @@ static void fill_uniform_batch(CtaBatch& B, int m, int n, int sense, int mm, con
     B.tableau_stride = (long long)(mm + 1) * (n + mm + 1);
 }
 
+// Launch of one uniform batch whose row relations are already known on the host (mm = rows after EQ
+// expansion, all_le = no '>=' / '=' row): lpx_primal_solve_batched calls this per chunk without the
+// device-to-host read of rel (and the stream drain that comes with it) the public _dev entry point needs.
+static int batched_dev_launch(int count, int m, int n, int sense, const double* A, const int* drel, int mm, bool all_le,
+                              const double* b, const double* c, const lpx_options& o, int* status, int* n_pivots,
+                              int* basis, double* x, double* z, double* tableau, unsigned long long* total_pivots,
+                              cudaStream_t stream) {
+    if (o.kernel == LPX_KERNEL_CTA_REG && !all_le) {
+        set_error("LPX_KERNEL_CTA_REG: the register-resident kernel serves all-'<=' problems only");
+        return LPX_E_CAPACITY;
+    }
+    // an all-LE rel array is the same problem as rel == NULL: it keeps the register-resident kernel
+    if (o.kernel == LPX_KERNEL_CTA_REG || (o.kernel == LPX_KERNEL_AUTO && all_le && reg_kernel_supports(m, n, mm, false)))
+        return reg_launch_batched(count, m, n, sense, A, b, c, o, status, n_pivots, basis, x, z, tableau, total_pivots,
+                                  stream);
+    CtaBatch B;
+    fill_uniform_batch(B, m, n, sense, mm, o);
+    B.A = A;
+    B.b = b;
+    B.c = c;
+    B.rel = all_le ? nullptr : drel;
+    B.status = status;
+    B.n_pivots = n_pivots;
+    B.basis = basis;
+    B.x = x;
+    B.z = z;
+    B.tableau = tableau;
+    B.total_pivots = total_pivots;
+    if (!cta_fits_smem(B.max_rows, B.max_width) || o.kernel == LPX_KERNEL_CTA_GLOBAL) {
+        if (!tableau) {
+            double* sc = ws_dev_as<double>(WS_SCRATCH, (size_t)count * B.tableau_stride);
+            if (!sc) return LPX_E_CUDA;
+            B.scratch = sc;
+            B.scratch_stride = B.tableau_stride;
+        }
+    }
+    return cta_launch(B, count, o.kernel, o.threads, stream, nullptr);
+}
+
 }  // namespace lpx
 
 using namespace lpx;
@@ -308,37 +347,16 @@ int lpx_primal_solve_batched_dev(int count, int m, int n, int sense, const doubl
     if (opt) o = *opt;
     // rel is a device pointer here; the tableau shape needs it on the host
     int mm = m;
+    bool all_le = true;
     if (rel) {
         std::vector<int> hrel(m);
         LPX_CUDA(cudaMemcpyAsync(hrel.data(), rel, (size_t)m * 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
         LPX_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
         mm = expanded_rows(m, hrel.data());
+        for (int i = 0; i < m; i++) all_le = all_le && hrel[i] == 0;
     }
-    if (o.kernel == LPX_KERNEL_CTA_REG || (o.kernel == LPX_KERNEL_AUTO && reg_kernel_supports(m, n, mm, rel != nullptr)))
-        return reg_launch_batched(count, m, n, sense, A, b, c, o, status, n_pivots, basis, x, z, tableau, total_pivots,
-                                  (cudaStream_t)stream);
-    CtaBatch B;
-    fill_uniform_batch(B, m, n, sense, mm, o);
-    B.A = A;
-    B.b = b;
-    B.c = c;
-    B.rel = rel;
-    B.status = status;
-    B.n_pivots = n_pivots;
-    B.basis = basis;
-    B.x = x;
-    B.z = z;
-    B.tableau = tableau;
-    B.total_pivots = total_pivots;
-    if (!cta_fits_smem(B.max_rows, B.max_width) || o.kernel == LPX_KERNEL_CTA_GLOBAL) {
-        if (!tableau) {
-            double* sc = ws_dev_as<double>(WS_SCRATCH, (size_t)count * B.tableau_stride);
-            if (!sc) return LPX_E_CUDA;
-            B.scratch = sc;
-            B.scratch_stride = B.tableau_stride;
-        }
-    }
-    return cta_launch(B, count, o.kernel, o.threads, (cudaStream_t)stream, nullptr);
+    return batched_dev_launch(count, m, n, sense, A, rel, mm, all_le, b, c, o, status, n_pivots, basis, x, z, tableau,
+                              total_pivots, (cudaStream_t)stream);
 }
 
 int lpx_primal_solve_batched(int count, int m, int n, int sense, const double* A, const int* rel, const double* b,
@@ -382,11 +400,28 @@ int lpx_primal_solve_batched(int count, int m, int n, int sense, const double* A
     const int chunks = count >= 1024 ? 8 : (count >= 64 ? 4 : 1);
     static const int ramp[9] = {0, 1, 3, 7, 12, 17, 22, 27, 32};
     auto bound = [&](int k) -> size_t { return chunks == 8 ? cnt * ramp[k] / 32 : cnt * k / chunks; };
+    struct Events {  // destroyed on every return path, the LPX_CUDA early returns included
+        std::vector<cudaEvent_t> ev;
+        ~Events() {
+            for (cudaEvent_t e : ev) cudaEventDestroy(e);
+        }
+        int add(cudaEvent_t* out) {
+            LPX_CUDA(cudaEventCreateWithFlags(out, cudaEventDisableTiming));
+            ev.push_back(*out);
+            return LPX_OK;
+        }
+    } events;
     std::vector<cudaEvent_t> up(chunks), done(chunks);
     for (int k = 0; k < chunks; k++) {
-        LPX_CUDA(cudaEventCreateWithFlags(&up[k], cudaEventDisableTiming));
-        LPX_CUDA(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
+        if ((rc = events.add(&up[k])) != LPX_OK) return rc;
+        if ((rc = events.add(&done[k])) != LPX_OK) return rc;
     }
+    lpx_options o;
+    lpx_default_options(&o);
+    if (opt) o = *opt;
+    bool all_le = true;
+    if (rel)
+        for (int i = 0; i < m; i++) all_le = all_le && rel[i] == 0;
     int result = LPX_OK;
     for (int k = 0; k < chunks && result == LPX_OK; k++) {
         const size_t lo = bound(k), hi = bound(k + 1), len = hi - lo;
@@ -396,9 +431,9 @@ int lpx_primal_solve_batched(int count, int m, int n, int sense, const double* A
         LPX_CUDA(cudaMemcpyAsync(dc + lo * n, c + lo * n, len * n * 8, cudaMemcpyHostToDevice, r.h2d));
         LPX_CUDA(cudaEventRecord(up[k], r.h2d));
         LPX_CUDA(cudaStreamWaitEvent(r.stream, up[k], 0));
-        result = lpx_primal_solve_batched_dev((int)len, m, n, sense, dA + lo * m * n, rel ? drel : nullptr, db + lo * m,
-                                              dc + lo * n, opt, dstat + lo, dnp + lo, dbasis + lo * mm, dx + lo * n,
-                                              dz + lo, dT ? dT + lo * tsize : nullptr, dtot, r.stream);
+        result = batched_dev_launch((int)len, m, n, sense, dA + lo * m * n, rel ? drel : nullptr, mm, all_le, db + lo * m,
+                                    dc + lo * n, o, dstat + lo, dnp + lo, dbasis + lo * mm, dx + lo * n, dz + lo,
+                                    dT ? dT + lo * tsize : nullptr, dtot, r.stream);
         if (result != LPX_OK) break;
         LPX_CUDA(cudaEventRecord(done[k], r.stream));
         LPX_CUDA(cudaStreamWaitEvent(r.d2h, done[k], 0));
@@ -420,10 +455,6 @@ int lpx_primal_solve_batched(int count, int m, int n, int sense, const double* A
         if (e != cudaSuccess) result = cuda_fail(e, "batched pipeline sync", __FILE__, __LINE__);
     } else {
         cudaDeviceSynchronize();
-    }
-    for (int k = 0; k < chunks; k++) {
-        cudaEventDestroy(up[k]);
-        cudaEventDestroy(done[k]);
     }
     if (total_pivots) *total_pivots = (long long)htot;
     return result;

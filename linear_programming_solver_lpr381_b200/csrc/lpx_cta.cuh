@@ -293,6 +293,24 @@ __device__ __forceinline__ void cta_row_map(const CtaBatch& B, const double* bi,
     }
 }
 
+// A problem the reference rejects before building a tableau (PrimalSimplex.cs:66-77) has no result: its
+// output slots are zero-filled, so callers never see leftovers of an earlier solve in reused buffers.
+template <int THREADS>
+__device__ __forceinline__ void cta_zero_outputs(const CtaBatch& B, int p, int m, int n, int rows, int width,
+                                                 int rank = 0, int nranks = 1) {
+    const int tid = threadIdx.x + rank * THREADS, step = THREADS * nranks;
+    if (B.basis)
+        for (int i = tid; i < m; i += step) B.basis[(size_t)p * B.basis_stride + i] = 0;
+    if (B.x)
+        for (int j = tid; j < n; j += step) B.x[(size_t)p * n + j] = 0.0;
+    if (B.z && tid == 0) B.z[p] = 0.0;
+    if (B.tableau) {
+        double* To = B.tableau + (size_t)p * B.tableau_stride;
+        const int total = rows * width;
+        for (int k = tid; k < total; k += step) To[k] = 0.0;
+    }
+}
+
 template <int THREADS, bool SMEM_T>
 __global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -412,7 +430,7 @@ __global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) 
 
         int iter = 1;
         while (true) {
-            if (iter > B.max_iter) {
+            if (iter > (mode == 1 ? LPX_DUAL_MAX_ITER : B.max_iter)) {
                 status = LPX_S_ITER_LIMIT;
                 break;
             }
@@ -501,6 +519,8 @@ __global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) 
         if (B.z && tid == 0) B.z[p] = T[(size_t)m * ld + rhs];
         if (B.tableau && (SMEM_T || T != B.tableau + (size_t)p * B.tableau_stride))
             cta_copy_out<THREADS>(B.tableau + (size_t)p * B.tableau_stride, T, ld, rows, width);
+    } else {
+        cta_zero_outputs<THREADS>(B, p, m, n, rows, width);
     }
 
     if (tid == 0) {

@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(THREADS) cta_cluster_simplex_kernel(const CtaB
 
         int iter = 1;
         while (true) {
-            if (iter > B.max_iter) {
+            if (iter > (mode == 1 ? LPX_DUAL_MAX_ITER : B.max_iter)) {
                 status = LPX_S_ITER_LIMIT;
                 break;
             }
@@ -396,6 +396,8 @@ __global__ void __launch_bounds__(THREADS) cta_cluster_simplex_kernel(const CtaB
             for (int i = r_lo; i < r_hi; i++)
                 for (int j = tid; j < width; j += THREADS) dst[(size_t)i * width + j] = loc(i)[j];
         }
+    } else {
+        cta_zero_outputs<THREADS>(B, p, m, n, rows, width, rank, CL);
     }
 
     if (rank == 0 && tid == 0) {

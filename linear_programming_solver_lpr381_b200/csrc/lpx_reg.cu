@@ -318,6 +318,17 @@ __global__ void __launch_bounds__((NW + 1) * 32, OCC) reg_simplex_kernel(const R
                 if (s_basis[i] < n) xo[s_basis[i]] = s_rhs[i];
         }
         if (tid == 0 && B.z) B.z[p] = s_rhs[ROWS];
+    } else {
+        // rejected up front (negative RHS): no result; zero-fill so reused buffers carry no leftovers
+        if (B.tableau) {
+            double* To = B.tableau + (size_t)p * (m + 1) * width;
+            for (int k = tid; k < (m + 1) * width; k += NT) To[k] = 0.0;
+        }
+        if (B.x)
+            for (int j = tid; j < n; j += NT) B.x[(size_t)p * n + j] = 0.0;
+        if (B.basis)
+            for (int i = tid; i < m; i += NT) B.basis[(size_t)p * m + i] = 0;
+        if (tid == 0 && B.z) B.z[p] = 0.0;
     }
 #undef T_GET
 #undef T_SET

@@ -9,6 +9,8 @@ using namespace lpr381;
 
 struct lpr_text {
     int code = 0, chunks = 0, highlighted = 0;
+    std::vector<Highlight> masks;    // one per callback chunk (rows == 0: null)
+    std::vector<size_t> chunk_len;
     std::string error, log, report, summary;
     SimplexResult result;
     std::vector<Constraint> cuts;
@@ -28,6 +30,8 @@ lpr_text* lpr_solve_text(const char* input, const char* algorithm) {
     UpdatePivot cb = [t](const std::string& s, const Highlight& h) {
         t->log += s;
         t->chunks++;
+        t->masks.push_back(h);
+        t->chunk_len.push_back(s.size());
         if (h.rows) t->highlighted++;
     };
     try {
@@ -58,6 +62,18 @@ lpr_text* lpr_solve_text(const char* input, const char* algorithm) {
 int lpr_text_code(const lpr_text* t) { return t->code; }
 int lpr_text_chunks(const lpr_text* t) { return t->chunks; }
 int lpr_text_highlighted(const lpr_text* t) { return t->highlighted; }
+long lpr_text_chunk_len(const lpr_text* t, int k) { return k >= 0 && k < t->chunks ? (long)t->chunk_len[k] : -1; }
+// the bool[,] handed to updatePivot with chunk k (what Form1.AppendPivotRow paints, Form1.cs:326-368)
+int lpr_text_mask(const lpr_text* t, int k, int* rows, int* cols, unsigned char* bits, long cap) {
+    if (k < 0 || k >= t->chunks) return -1;
+    const Highlight& h = t->masks[k];
+    *rows = h.rows;
+    *cols = h.cols;
+    const long need = (long)h.rows * h.cols;
+    if (bits && cap >= need)
+        for (long q = 0; q < need; q++) bits[q] = h.v[q];
+    return h.rows ? 1 : 0;
+}
 const char* lpr_text_error(const lpr_text* t) { return t->error.c_str(); }
 const char* lpr_text_log(const lpr_text* t) { return t->log.c_str(); }
 const char* lpr_text_report(const lpr_text* t) { return t->report.c_str(); }

@@ -4,6 +4,7 @@
 //   lpr381 "<algorithm>" [input.txt]        algorithm: Primal Simplex | Revised Primal Simplex | Dual Simplex |
 //                                           Branch and Bound | Cutting Plane | Revised Cutting Plane | BranchAndBoundKnapsack | ...
 //   lpr381 --export "<algorithm>" [input]   the export file layout ("Linear Program:" / "Iterations:")
+//   lpr381 --crlf ...                       Environment.NewLine = "\r\n" (where the reference runs)
 #include <cstdio>
 #include <fstream>
 #include <iostream>
@@ -16,12 +17,14 @@ using namespace lpr381;
 int main(int argc, char** argv) {
     int arg = 1;
     bool as_export = false;
-    if (arg < argc && std::string(argv[arg]) == "--export") {
-        as_export = true;
-        arg++;
+    for (; arg < argc; arg++) {
+        const std::string a = argv[arg];
+        if (a == "--export") as_export = true;
+        else if (a == "--crlf") NewLine() = "\r\n";
+        else break;
     }
     if (arg >= argc) {
-        std::fprintf(stderr, "usage: lpr381 [--export] \"<algorithm>\" [input.txt]\n");
+        std::fprintf(stderr, "usage: lpr381 [--export] [--crlf] \"<algorithm>\" [input.txt]\n");
         return 2;
     }
     const std::string algorithm = argv[arg++];
@@ -61,7 +64,9 @@ int main(int argc, char** argv) {
         std::fprintf(stderr, "Error: %s\n", e.what());
         return 1;
     }
-    if (as_export) std::cout << "Linear Program:\n" << input << "\n\nIterations:\n" << box << "\n";
+    // BtnExport_Click (Form1.cs:310-314): five StreamWriter.WriteLine calls, each ending in Environment.NewLine
+    const std::string& nl = NewLine();
+    if (as_export) std::cout << "Linear Program:" << nl << input << nl << nl << "Iterations:" << nl << box << nl;
     else std::cout << box;
     return 0;
 }

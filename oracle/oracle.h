@@ -83,6 +83,10 @@ const char* orc_text_log(const orc_text* t);
 const char* orc_text_report(const orc_text* t);
 const char* orc_text_summary(const orc_text* t);
 int orc_text_masks(const orc_text* t);          /* number of callback chunks */
+long orc_text_chunk_len(const orc_text* t, int k);   /* characters of chunk k */
+/* bool[,] highlight of chunk k (PrimalSimplex.cs:117-119, DualSimplex.cs:65-69,104-106): returns 1 and the
+ * rows x cols cells, or 0 for a null mask */
+int orc_text_mask(const orc_text* t, int k, int* rows, int* cols, unsigned char* bits, long cap);
 /* numeric part of the returned SimplexResult; returns 1 when Tableau != null */
 int orc_text_result_dims(const orc_text* t, int* rows, int* cols, int* nx, int* nbasis);
 const double* orc_text_tableau(const orc_text* t);

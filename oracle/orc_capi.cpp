@@ -335,6 +335,8 @@ int orc_revised_solve(int m, int n, int sense, const double* A, const int* rel, 
 struct orc_text {
     int code = 0;
     int chunks = 0;
+    std::vector<Mask> masks;          // one per callback chunk (rows == 0: null)
+    std::vector<size_t> chunk_len;    // characters of each chunk
     std::string error, log, report, summary;
     Outcome result;   // numeric part of the SimplexResult (Tableau / Solution / Basis may be null)
     CutTrace cuts;
@@ -342,9 +344,11 @@ struct orc_text {
 
 orc_text* orc_solve_text(const char* input, const char* algorithm) {
     orc_text* t = new orc_text();
-    Sink sink = [t](const std::string& s, const Mask&) {
+    Sink sink = [t](const std::string& s, const Mask& mk) {
         t->log += s;
         t->chunks++;
+        t->masks.push_back(mk);
+        t->chunk_len.push_back(s.size());
     };
     try {
         Problem p = parse_text(input);
@@ -369,6 +373,17 @@ const char* orc_text_log(const orc_text* t) { return t->log.c_str(); }
 const char* orc_text_report(const orc_text* t) { return t->report.c_str(); }
 const char* orc_text_summary(const orc_text* t) { return t->summary.c_str(); }
 int orc_text_masks(const orc_text* t) { return t->chunks; }
+long orc_text_chunk_len(const orc_text* t, int k) { return k >= 0 && k < t->chunks ? (long)t->chunk_len[k] : -1; }
+int orc_text_mask(const orc_text* t, int k, int* rows, int* cols, unsigned char* bits, long cap) {
+    if (k < 0 || k >= t->chunks) return -1;
+    const Mask& mk = t->masks[k];
+    *rows = mk.rows;
+    *cols = mk.cols;
+    const long need = (long)mk.rows * mk.cols;
+    if (bits && cap >= need)
+        for (long q = 0; q < need; q++) bits[q] = mk.bits[q];
+    return mk.rows ? 1 : 0;
+}
 int orc_text_result_dims(const orc_text* t, int* rows, int* cols, int* nx, int* nbasis) {
     *rows = t->result.has_tableau ? t->result.rows : 0;
     *cols = t->result.has_tableau ? t->result.cols : 0;

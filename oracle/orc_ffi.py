@@ -262,6 +262,24 @@ def revised_solve(A, b, c, rel=None, sense=0, max_iterations=10000, cap=16384):
                 basis=basis, xB=xB, Binv=Binv, x=x, z=z.value)
 
 
+def _masks(f_mask, f_len, h, chunks):
+    """Per callback chunk: the bool[,] highlight (None for a null mask) and the chunk's length."""
+    f_mask.argtypes = [C.c_void_p, C.c_int, c_ip, c_ip, C.c_void_p, C.c_long]
+    f_len.argtypes = [C.c_void_p, C.c_int]
+    f_len.restype = C.c_long
+    masks, lens = [], []
+    for k in range(chunks):
+        r, c = C.c_int(), C.c_int()
+        has = f_mask(h, k, C.byref(r), C.byref(c), None, 0)
+        mk = None
+        if has == 1:
+            mk = np.zeros((r.value, c.value), dtype=np.uint8)
+            f_mask(h, k, C.byref(r), C.byref(c), mk.ctypes.data_as(C.c_void_p), mk.size)
+        masks.append(mk)
+        lens.append(f_len(h, k))
+    return masks, lens
+
+
 def solve_text(text, algorithm):
     L = lib()
     h = L.orc_solve_text(text.encode("utf-8"), algorithm.encode("utf-8"))
@@ -276,6 +294,7 @@ def solve_text(text, algorithm):
         out["x"] = np.ctypeslib.as_array(L.orc_text_solution(h), (nx.value,)).copy() if nx.value else None
         out["basis"] = np.ctypeslib.as_array(L.orc_text_basis(h), (nb.value,)).copy() if nb.value else None
         out["z"] = L.orc_text_z(h)
+        out["masks"], out["chunk_len"] = _masks(L.orc_text_mask, L.orc_text_chunk_len, h, out["chunks"])
         cuts = []
         n = max(nx.value, 1024)
         for k in range(L.orc_text_cut_count(h)):

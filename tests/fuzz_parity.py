@@ -18,7 +18,6 @@ import orc_ffi as orc  # noqa: E402
 from linear_programming_solver_lpr381_b200 import _ffi as F  # noqa: E402
 from linear_programming_solver_lpr381_b200 import api  # noqa: E402
 
-F.check(F.lib().lpx_init(0))
 
 
 def bits(a):
@@ -45,9 +44,10 @@ def gen(rng, m, n, kind):
     return A, b, c
 
 
-def main():
-    seed = int(sys.argv[1]) if len(sys.argv) > 1 else 1
-    rounds = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+def sweep(seed=1, rounds=3, cnt=192, singles=60, revised=30, every=4, threads=16):
+    """`rounds` rounds of the sweep; returns the number of mismatches.  The defaults are the heavy
+    stand-alone run; tests/test_gpu_fuzz.py runs a bounded fixed-seed slice of the same code."""
+    F.check(F.lib().lpx_init(0))
     rng = np.random.default_rng(seed)
     bad = 0
     t0 = time.time()
@@ -55,11 +55,10 @@ def main():
         # 1. batched register kernel (both builds) on full and ragged shapes
         for kind in ("int", "tie", "dec"):
             for (m, n) in ((64, 128), (64, 100), (37, 90), (5, 150), (64, 1)):
-                cnt = 192
                 A = np.stack([gen(rng, m, n, kind)[0] for _ in range(cnt)])
                 b = np.stack([np.abs(gen(rng, m, n, kind)[1]) for _ in range(cnt)])
                 c = np.stack([gen(rng, m, n, kind)[2] for _ in range(cnt)])
-                want = orc.primal_batch(A, b, c, threads=16, want_tableau=True, max_iterations=400)
+                want = orc.primal_batch(A, b, c, threads=threads, want_tableau=True, max_iterations=400)
                 for rv in (1, 2):
                     got = api.primal_solve_batched(A, b, c, max_iterations=400, kernel=F.KERNEL_CTA_REG, reg_variant=rv)
                     ok = (np.array_equal(got["status"], want["status"]) and np.array_equal(got["n_pivots"], want["n_pivots"])
@@ -69,7 +68,7 @@ def main():
                         bad += 1
                         print("MISMATCH reg", kind, m, n, rv, flush=True)
         # 2. single solves through every per-tableau kernel, primal and dual
-        for t in range(60):
+        for t in range(singles):
             m, n = int(rng.integers(1, 70)), int(rng.integers(1, 90))
             kind = ("int", "tie", "dec")[t % 3]
             A, b, c = gen(rng, m, n, kind)
@@ -113,7 +112,7 @@ def main():
                 bad += 1
                 print("MISMATCH cluster", m, n, flush=True)
         # 4. revised simplex
-        for t in range(30):
+        for t in range(revised):
             m, n = int(rng.integers(1, 40)), int(rng.integers(1, 50))
             A, b, c = gen(rng, m, n, ("int", "tie", "dec")[t % 3])
             sense = int(rng.integers(0, 2))
@@ -127,13 +126,13 @@ def main():
                 bad += 1
                 print("MISMATCH revised", m, n, want["status"], got["status"], flush=True)
         # 5. Branch & Bound: batches of small IPs (threaded host commit, cluster kernel for deep nodes)
-        if rd % 4 == 0:
-            m, n, cnt = int(rng.integers(3, 9)), int(rng.integers(3, 10)), 48
-            A = rng.integers(1, 12, size=(cnt, m, n)).astype(float)
-            b = rng.integers(3 * n, 12 * n, size=(cnt, m)).astype(float)
-            c = rng.integers(1, 15, size=(cnt, n)).astype(float)
+        if rd % every == 0:
+            m, n, bcnt = int(rng.integers(3, 9)), int(rng.integers(3, 10)), 48
+            A = rng.integers(1, 12, size=(bcnt, m, n)).astype(float)
+            b = rng.integers(3 * n, 12 * n, size=(bcnt, m)).astype(float)
+            c = rng.integers(1, 15, size=(bcnt, n)).astype(float)
             got = api.bnb_simplex_batched(A, b, c)
-            for k in range(cnt):
+            for k in range(bcnt):
                 want = orc.bnb_simplex(A[k], b[k], c[k], node_cap=1 << 16)
                 ok = (bool(got["found"][k]) == want["found"] and got["n_nodes"][k] == want["n_nodes"]
                       and got["lp_pivots"][k] == want["total_pivots"])
@@ -154,7 +153,7 @@ def main():
                 bad += 1
                 print("MISMATCH bnb deep", g1["n_nodes"][0], want["n_nodes"], flush=True)
         # 6. knapsack: integer (order-free sums) and fractional (ordered sums) data, several speculation settings
-        if rd % 4 == 1:
+        if rd % every == (1 if every > 1 else 0):
             for t in range(6):
                 nk = int(rng.integers(5, 120))
                 w = rng.integers(1, 60, size=nk).astype(float)
@@ -174,6 +173,13 @@ def main():
                         bad += 1
                         print("MISMATCH knapsack", nk, spec, got["n_evals"], want["n_evals"], flush=True)
         print(f"round {rd} done, mismatches so far {bad}, {time.time() - t0:.0f} s", flush=True)
+    return bad
+
+
+def main():
+    seed = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+    rounds = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    bad = sweep(seed, rounds)
     print("FUZZ RESULT:", "OK" if bad == 0 else f"{bad} MISMATCHES")
     sys.exit(1 if bad else 0)
 

@@ -56,6 +56,7 @@ def solve_text(text, algorithm):
         out["x"] = np.ctypeslib.as_array(L.lpr_text_solution(h), (nx.value,)).copy() if nx.value else None
         out["basis"] = np.ctypeslib.as_array(L.lpr_text_basis(h), (nb.value,)).copy() if nb.value else None
         out["z"] = L.lpr_text_z(h)
+        out["masks"], out["chunk_len"] = _masks(L.lpr_text_mask, L.lpr_text_chunk_len, h, out["chunks"])
         cuts = []
         for k in range(L.lpr_text_cut_count(h)):
             a, b = np.zeros(4096), C.c_double()
@@ -65,6 +66,24 @@ def solve_text(text, algorithm):
         return out
     finally:
         L.lpr_text_free(h)
+
+
+def _masks(f_mask, f_len, h, chunks):
+    """Per callback chunk: the bool[,] highlight (None for a null mask) and the chunk's length."""
+    f_mask.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.c_long]
+    f_len.argtypes = [C.c_void_p, C.c_int]
+    f_len.restype = C.c_long
+    masks, lens = [], []
+    for k in range(chunks):
+        r, c = C.c_int(), C.c_int()
+        has = f_mask(h, k, C.byref(r), C.byref(c), None, 0)
+        mk = None
+        if has == 1:
+            mk = np.zeros((r.value, c.value), dtype=np.uint8)
+            f_mask(h, k, C.byref(r), C.byref(c), mk.ctypes.data_as(C.c_void_p), mk.size)
+        masks.append(mk)
+        lens.append(f_len(h, k))
+    return masks, lens
 
 
 def parse_text(text):

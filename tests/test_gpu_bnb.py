@@ -73,6 +73,26 @@ def test_bnb_batched_instances(lpx, orc):
             assert_bits_equal(got["best_x"][k], want["best_x"], f"best_x {k}")
 
 
+def test_bnb_batched_c4_shape(lpx, orc):
+    """BASELINE config 4 as bench.py runs it: >= 32 instances of 60 x 120, so the host commit is
+    threaded and each round mixes the shared-memory and the cluster launch groups
+    (R/Models/Branch&Bound.cs:128-258).  Every instance against the oracle."""
+    count = 36
+    As, bs, cs = zip(*[workloads.ip_c4(seed=300 + k) for k in range(count)])
+    got = lpx.bnb_simplex_batched(np.stack(As), np.stack(bs), np.stack(cs))
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(8) as ex:  # the oracle call releases the GIL
+        wants = list(ex.map(lambda k: orc.bnb_simplex(As[k], bs[k], cs[k]), range(count)))
+    for k in range(count):
+        want = wants[k]
+        assert bool(got["found"][k]) == want["found"], k
+        assert got["n_nodes"][k] == want["n_nodes"], k
+        assert got["lp_pivots"][k] == want["total_pivots"], k
+        if want["found"]:
+            assert_bits_equal([got["best_z"][k]], [want["best_z"]], f"best_z {k}")
+            assert_bits_equal(got["best_x"][k], want["best_x"], f"best_x {k}")
+
+
 def test_bnb_node_history(lpx, orc, kat):
     case = kat["ip"]["ip_floor_path"]
     A, b, c, rel = case_arrays(case)
@@ -87,6 +107,26 @@ def test_bnb_node_history(lpx, orc, kat):
     w2 = orc.dual_solve(A2, np.append(b, 2.0), c, np.append(rel, 1).astype(np.int32), case["sense"], history=True)
     assert ceil["n_pivots"] == w2["n_pivots"] and ceil["silent"] == w2["silent"]
     assert_bits_equal(ceil["history"], w2["history"], "dual child history")
+
+
+def test_bnb_cycling_root_logs_every_pivot(lpx, orc):
+    """A root LP that cycles to the iteration limit (Beale): B&B reports "Error: Infeasible"
+    (R/Models/Branch&Bound.cs:59-63) and the node record carries all 10 000 pivot pairs and, on request,
+    all 10 001 tableaux — consumers index pivots[0 .. n_pivots) (include/lpx.h)."""
+    from test_gpu_primal import BEALE_A, BEALE_B, BEALE_C
+    want = orc.primal_solve(BEALE_A, BEALE_B, BEALE_C, max_iterations=10000)
+    for hist in (False, True):
+        r = lpx.bnb_simplex(BEALE_A, BEALE_B, BEALE_C, trace=True, want_history=hist)
+        assert not r["found"] and r["n_nodes"] == 1
+        root = r["nodes"][0]
+        assert root["lp_status"] == -3 and root["outcome"] == 0 and root["n_pivots"] == 10000
+        assert root["pivots"].tolist() == want["pivots"].tolist()
+        if hist:
+            assert root["history"].shape[0] == 10001
+    import host_ffi as H
+    text = workloads.lp_to_text(BEALE_A, BEALE_B, BEALE_C)
+    got, wt = H.solve_text(text, "Branch and Bound"), orc.solve_text(text, "Branch and Bound")
+    assert got["log"] == wt["log"] and got["report"] == wt["report"] and got["summary"] == wt["summary"]
 
 
 # ---- knapsack -----------------------------------------------------------------------------------

@@ -350,3 +350,39 @@ def test_extreme_aspect_ratios(lpx, orc):
         want = orc.primal_solve(A, b, c)
         got = lpx.primal_solve(A, b, c)
         compare_primal(got, want, f"{m}x{n}")
+
+
+def test_forced_register_kernel_refuses_non_le_rows(lpx):
+    """LPX_KERNEL_CTA_REG serves all-'<=' batches only: a '>=' or '=' row is an error of the call, never a
+    silent solve of a different problem; an all-LE rel array is the same batch as rel = None."""
+    A, b, c = workloads.batch_c2(count=4, m=8, n=12, seed=5)
+    for bad in (1, 2):
+        rel = np.zeros(8, dtype=np.int32)
+        rel[3] = bad
+        with pytest.raises(F.LpxError) as ei:
+            lpx.primal_solve_batched(A, b, c, rel=rel, kernel=F.KERNEL_CTA_REG)
+        assert ei.value.code == F.E_CAPACITY
+    g0 = lpx.primal_solve_batched(A, b, c, kernel=F.KERNEL_CTA_REG)
+    g1 = lpx.primal_solve_batched(A, b, c, rel=np.zeros(8, dtype=np.int32), kernel=F.KERNEL_CTA_REG)
+    assert_bits_equal(g0["tableau"], g1["tableau"], "tableau")
+
+
+@pytest.mark.parametrize("kernel", [F.KERNEL_AUTO, F.KERNEL_CTA_REG, F.KERNEL_CTA_SMEM, F.KERNEL_CTA_GLOBAL])
+def test_rejected_problems_return_zeroed_outputs(lpx, orc, kernel):
+    """Problems the reference rejects before building a tableau (negative RHS, PrimalSimplex.cs:73-76)
+    get their status and zero-filled result slots, not leftovers of an earlier solve in reused buffers."""
+    A, b, c = workloads.batch_c2(count=6, m=8, n=12, seed=9)
+    first = lpx.primal_solve_batched(A, b, c, kernel=kernel)  # fills the cached device buffers
+    assert (first["status"] == 0).all()
+    b2 = b.copy()
+    b2[2, 5] = -3.0
+    b2[4, 0] = -1.0
+    out = {k: np.full_like(v, 77) for k, v in first.items() if isinstance(v, np.ndarray)}
+    got = lpx.primal_solve_batched(A, b2, c, kernel=kernel, out=out)
+    for k in range(6):
+        if k in (2, 4):
+            assert got["status"][k] == F.S_NEG_RHS and got["n_pivots"][k] == 0
+            assert not got["tableau"][k].any() and not got["x"][k].any() and got["z"][k] == 0 and not got["basis"][k].any()
+        else:
+            want = orc.primal_solve(A[k], b2[k], c[k])
+            assert_bits_equal(got["tableau"][k], want["tableau"], f"tableau {k}")

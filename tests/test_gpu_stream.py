@@ -20,6 +20,21 @@ def build_tableau(A, b, c):
     return T
 
 
+_C3 = {}
+
+
+def _c3_oracle(orc, npiv):
+    """The oracle's tableau after `npiv` pivots of the C3 instance (≈ 6 s on one core; computed once)."""
+    if npiv not in _C3:
+        A, b, c = workloads.large_c3()
+        T = build_tableau(A, b, c)
+        basis = np.arange(8192, 8192 + 4096, dtype=np.int32)
+        ost, onp, opiv = orc.primal_core(T, basis, npiv)
+        assert onp == npiv
+        _C3[npiv] = (A, b, c, T, basis, opiv)
+    return _C3[npiv]
+
+
 PROTOCOLS = [(0, 0), (0, 1), (0, 3), (0, 5), (0, 16), (0, 11), (4, 0), (4, 3), (3, 0), (3, 5), (1, 0), (2, 0)]  # (protocol, pivots per HBM pass)
 
 
@@ -123,6 +138,29 @@ def test_c3_full_size_first_pivots(lpx, orc):
         unit = np.zeros(4097)
         unit[i] = 1.0
         assert np.array_equal(np.abs(col), unit)
+    s.close()
+
+
+@pytest.mark.parametrize("protocol,kblock,pass_variant", [(0, 0, 0), (0, 0, 3), (0, 16, 0), (4, 0, 3)])
+def test_c3_full_size_pipelined_blocks(lpx, orc, protocol, kblock, pass_variant):
+    """4096 x 8192 through the production protocols over >= 8 look-ahead blocks, stepped in uneven
+    chunks (so blocks are cut short and the Fbuf/Pbuf/Lbuf halves and the ping-pong tableau buffers
+    flip at odd places): pivot list and every tableau bit against the oracle's arithmetic loop
+    (R/Models/PrimalSimplex.cs:205-257)."""
+    chunks = (5, 11, 48, 8, 1)
+    npiv = sum(chunks)
+    A, b, c, T, basis, opiv = _c3_oracle(orc, npiv)
+    s = lpx.Session(A, b, c, single_cta_select=protocol, kblock=kblock, pass_variant=pass_variant)
+    tot = 0
+    for k in chunks:
+        st, tot = s.step(k)
+        assert st == F.RUNNING
+    assert tot == npiv
+    assert s.pivots(npiv)[:npiv].tolist() == opiv.tolist()
+    assert_bits_equal(s.tableau(), T, "C3 tableau after %d pivots" % npiv)
+    gb, gx, gz = s.solution()
+    assert gb.tolist() == basis.tolist()
+    assert_bits_equal([gz], [T[-1, -1]], "z")
     s.close()
 
 

@@ -25,6 +25,13 @@ def same_text(orc, text, algorithm):
     assert got["report"] == want["report"]
     assert got["summary"] == want["summary"]
     assert got["chunks"] == want["chunks"]
+    # the bool[,] highlight of every callback chunk, cell by cell (PrimalSimplex.cs:117-119,
+    # DualSimplex.cs:65-69,104-106; consumer: Form1.AppendPivotRow, Form1.cs:326-368)
+    assert got["chunk_len"] == want["chunk_len"]
+    for k, (g, w) in enumerate(zip(got["masks"], want["masks"])):
+        assert (g is None) == (w is None), f"chunk {k}: null mask on one side only"
+        if g is not None:
+            assert g.shape == w.shape and np.array_equal(g, w), f"chunk {k}: highlight cells differ"
     return got
 
 
@@ -161,6 +168,35 @@ def test_cli_example_input(lpx, orc, tmp_path):
     assert out.stdout == open(os.path.join(ROOT, "tests", "golden", "example_output.txt")).read()
     bad = subprocess.run([exe, "Primal Simplex"], input="Max: 1x1\n1x1 >= 2\n", capture_output=True, text=True, timeout=120)
     assert bad.returncode == 1 and "Constraint contains '>=' sign." in bad.stderr
+
+
+@pytest.mark.parametrize("algorithm,oracle_key", [("Primal Simplex", "Primal Simplex"), ("Dual Simplex", "Dual Simplex"),
+                                                  ("Branch and Bound", "Branch and Bound"),
+                                                  ("Branch and Bound Knapsack", "Branch and Bound"),
+                                                  ("Cutting Plane", "cutting plane"),
+                                                  ("BranchAndBoundKnapsack", "knapsack")])
+@pytest.mark.parametrize("crlf", [False, True])
+def test_cli_export_layout(lpx, orc, algorithm, oracle_key, crlf):
+    """`lpr381 --export`: BtnExport_Click's file (R/Form1.cs:310-314) = WriteLine("Linear Program:"),
+    WriteLine(input), WriteLine(), WriteLine("Iterations:"), WriteLine(box) where box is the callback
+    stream + "\n\nFinal Report:\n" + Report + "\n\nSummary:\n" + Summary (R/Form1.cs:277-278; those
+    "\n" are literals, the WriteLine terminators are Environment.NewLine)."""
+    import orc_ffi
+    exe = os.path.join(ROOT, "linear_programming_solver_lpr381_b200", "lpr381")
+    text = "Max: 60x1 + 100x2 + 120x3\n10x1 + 20x2 + 30x3 <= 50\n" if "napsack" in algorithm else workloads.WYNDOR_TEXT
+    nl = "\r\n" if crlf else "\n"
+    orc_ffi.lib().orc_set_newline(nl.encode())
+    try:
+        want = orc.solve_text(text, oracle_key)
+    finally:
+        orc_ffi.lib().orc_set_newline(b"\n")
+    assert want["code"] == 0
+    box = want["log"] + "\n\nFinal Report:\n" + want["report"] + "\n\nSummary:\n" + want["summary"]
+    expect = "Linear Program:" + nl + text + nl + nl + "Iterations:" + nl + box + nl
+    args = [exe, "--export"] + (["--crlf"] if crlf else []) + [algorithm]
+    out = subprocess.run(args, input=text.encode(), capture_output=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.decode() == expect
 
 
 def test_ragged_rows_fail_like_build_tableau(lpx, orc):
