@@ -31,6 +31,8 @@ sys.path.insert(0, ROOT)
 
 C2 = dict(count=4096, m=64, n=128)
 C3 = dict(m=4096, n=8192)
+KNAP_INSTANCES = 16             # C5 instances per GPU in the bnb_knapsack section
+KNAP_INSTANCES_FRACTIONAL = 4
 
 
 def load_peaks():
@@ -400,7 +402,34 @@ def run_ours(args):
                          "ms_per_step": 1e3 * e2e_s / steps}, roofline=roof, host=(A, b, c))
 
     # ---------------- configs 4 and 5 (sections) ------------------------------------------------
+    def oracle():
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import orc_ffi
+        orc_ffi.lib()
+        return orc_ffi
+
+    def timed_pool(fn, items, threads):
+        """fn over items on `threads` host threads (the oracle's ctypes calls release the GIL)."""
+        from concurrent.futures import ThreadPoolExecutor
+        t0 = time.perf_counter()
+        if threads <= 1:
+            out = [fn(it) for it in items]
+        else:
+            with ThreadPoolExecutor(threads) as ex:
+                out = list(ex.map(fn, items))
+        return out, time.perf_counter() - t0
+
+    port_note = "C++ restatement (oracle/) of the C# loops, not the C# binary (no .NET toolchain here)"
+    with_cpu = rank == 0 and world == 1
+    host_cores = os.cpu_count() or 1
+
+    def fp64_rate():
+        rate = F.C.c_double()
+        F.check(F.lib().lpx_measure_fp64_rate(F.C.byref(rate)))
+        return rate.value
+
     def bench_bnb(count):
+        import ctypes as C
         As, bs, cs = zip(*[workloads.ip_c4(seed=1000 * rank + 11 + k) for k in range(count)])
         A, b, c = np.stack(As), np.stack(bs), np.stack(cs)
         api.bnb_simplex_batched(A, b, c)  # warm-up at full size: the node pool and pinned staging grow once
@@ -409,15 +438,41 @@ def run_ours(args):
         t0 = time.perf_counter()
         r = api.bnb_simplex_batched(A, b, c)
         dt = max_over_ranks(time.perf_counter() - t0)
+        st4 = (C.c_double * 4)()
+        F.check(F.lib().lpx_bnb_last_stats(st4))
+        flops, gpu_s, rounds = st4[0], st4[1], int(st4[3])
         nodes = sum_over_ranks(int(r["n_nodes"].sum()))
-        return {"metric": "B&B simplex nodes/sec (LP relaxations solved per second)", "value": nodes / dt,
-                "unit": "nodes/s", "instances_per_gpu": count, "nodes": nodes, "lp_pivots": sum_over_ranks(int(r["lp_pivots"].sum())),
-                "seconds": dt, "gpu_launches": F.lib().lpx_kernel_launches() - l0,
-                "mode": "reference-exact tree (SURVEY F5), independent instances per GPU, host commit in DFS order",
-                "timing": "end to end through lpx_bnb_simplex_batched (host buffers)"}
+        rate = fp64_rate()
+        ach = flops / gpu_s / 1e12 if gpu_s > 0 else 0.0
+        out = {"metric": "B&B simplex nodes/sec (LP relaxations solved per second)", "value": nodes / dt,
+               "unit": "nodes/s", "instances_per_gpu": count, "nodes": nodes, "lp_pivots": sum_over_ranks(int(r["lp_pivots"].sum())),
+               "seconds": dt, "gpu_launches": F.lib().lpx_kernel_launches() - l0,
+               "mode": "reference-exact tree (SURVEY F5), independent instances per GPU, host commit in DFS order",
+               "timing": "end to end through lpx_bnb_simplex_batched (host buffers)",
+               "roofline": {"bound": "fp64", "achieved": ach, "peak": rate, "unit": "TFLOP/s",
+                            "frac": ach / rate if rate else None, "traffic": None,
+                            "peak_source": "measured in this run: unfused DMUL+DADD issue rate",
+                            "kernel": "cta_simplex_kernel / cta_cluster_simplex_kernel (all node LPs of a round in one "
+                                      "launch per kernel family)",
+                            "algorithmic_flops": flops, "gpu_seconds": gpu_s, "evaluation_rounds": rounds,
+                            "note": "flops = sum over node LPs of pivots x (2 m_d (n+m_d+1) + (n+m_d+1)) at each node's "
+                                    "own shape (rank 0's instances); gpu_seconds = host wall inside the evaluation calls "
+                                    "(descriptor upload, kernels, result download, sync), rank 0"}}
+        if with_cpu:
+            orc = oracle()
+            k1 = min(4, count)
+            r1, t1 = timed_pool(lambda k: orc.bnb_simplex(As[k], bs[k], cs[k]), range(k1), 1)
+            kn = min(count, 2 * host_cores)
+            rn, tn = timed_pool(lambda k: orc.bnb_simplex(As[k], bs[k], cs[k]), range(kn), host_cores)
+            out["cpu_baseline"] = {"value": sum(x["n_nodes"] for x in r1) / t1, "unit": "nodes/s", "cores": 1, "kind": "port",
+                                   "sample": f"the first {k1} instances of the batch, one thread",
+                                   "all_threads": {"value": sum(x["n_nodes"] for x in rn) / tn, "unit": "nodes/s",
+                                                   "cores": host_cores, "sample": f"the first {kn} instances, one instance per thread"},
+                                   "note": port_note}
+        return out
 
-    def bench_knap(count):
-        ps, ws, caps = zip(*[workloads.knapsack_c5(seed=1000 * rank + 13 + k) for k in range(count)])
+    def bench_knap(count, kind="uncorrelated", label=None):
+        ps, ws, caps = zip(*[workloads.knapsack_c5(seed=1000 * rank + 13 + k, kind=kind) for k in range(count)])
         p, w, cap = np.stack(ps), np.stack(ws), np.array(caps)
         api.bnb_knapsack_batched(p, w, cap)  # warm-up at full size
         barrier()
@@ -426,10 +481,54 @@ def run_ours(args):
         r = api.bnb_knapsack_batched(p, w, cap)
         dt = max_over_ranks(time.perf_counter() - t0)
         nodes = sum_over_ranks(int(r["n_evals"].sum()))
-        return {"metric": "B&B knapsack nodes/sec (ComputeRelaxation evaluations committed per second)",
-                "value": nodes / dt, "unit": "nodes/s", "instances_per_gpu": count, "nodes": nodes, "seconds": dt,
-                "gpu_launches": F.lib().lpx_kernel_launches() - l0,
-                "timing": "end to end through lpx_bnb_knapsack_batched (host buffers)"}
+        n_items = p.shape[1]
+        bytes_per_node = 16 * n_items  # 4n assigned read + 4n child assigned write + 8n relaxed write
+        ach = nodes / world * bytes_per_node / dt / 1e9
+        out = {"metric": "B&B knapsack nodes/sec (ComputeRelaxation evaluations committed per second)",
+               "value": nodes / dt, "unit": "nodes/s", "instances_per_gpu": count, "items": n_items, "data": kind,
+               "nodes": nodes, "seconds": dt, "gpu_launches": F.lib().lpx_kernel_launches() - l0,
+               "timing": "end to end through lpx_bnb_knapsack_batched (host buffers)",
+               "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                            "traffic": None, "peak_source": peak_kind, "algorithmic_bytes_per_node": bytes_per_node,
+                            "note": "SURVEY 8d's per-node figure (the reference's int[n] assignment read and written, "
+                                    "double[n] relaxed written) x committed evaluations / wall time of the call; the "
+                                    "search is bound by the dependent pop -> evaluate -> push chain, not by HBM"}}
+        if label:
+            out["label"] = label
+        if with_cpu:
+            orc = oracle()
+            k1 = min(4 if kind != "fractional" else 1, count)
+            r1, t1 = timed_pool(lambda k: orc.knapsack(ps[k], ws[k], caps[k]), range(k1), 1)
+            kn = min(count, 2 * host_cores)
+            rn, tn = timed_pool(lambda k: orc.knapsack(ps[k], ws[k], caps[k]), range(kn), host_cores)
+            out["cpu_baseline"] = {"value": sum(x["n_evals"] for x in r1) / t1, "unit": "nodes/s", "cores": 1, "kind": "port",
+                                   "sample": f"the first {k1} instance(s) of the batch, one thread",
+                                   "all_threads": {"value": sum(x["n_evals"] for x in rn) / tn, "unit": "nodes/s",
+                                                   "cores": host_cores, "sample": f"the first {kn} instances, one instance per thread"},
+                                   "note": port_note}
+        return out
+
+    def cpu_baseline_large():
+        """The oracle's arithmetic loop on the same 4096 x 8192 tableau, one thread (a single tableau is one
+        thread upstream)."""
+        orc = oracle()
+        A, b, c = workloads.large_c3(**C3, seed=7)
+        m, n = A.shape
+        T = np.zeros((m + 1, n + m + 1))
+        T[:m, :n] = A
+        T[:m, n:n + m] = np.eye(m)
+        T[:m, -1] = b
+        T[m, :n] = -c
+        basis = np.arange(n, n + m, dtype=np.int32)
+        orc.primal_core(T, basis, 4)
+        t0 = time.perf_counter()
+        done = 0
+        while time.perf_counter() - t0 < 6.0:
+            done += orc.primal_core(T, basis, 16)[1]
+        dt = time.perf_counter() - t0
+        return {"value": done / dt, "unit": "pivots/s", "cores": 1, "kind": "port",
+                "sample": f"{done} pivots of the same 4097x12289 tableau after 4 warm-up pivots, one thread, arithmetic "
+                          "loop only", "note": port_note}
 
     # ---------------- CPU baseline on rank 0, N = 1 ---------------------------------------------
     def cpu_baseline(host):
@@ -463,7 +562,8 @@ def run_ours(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "C3 single large dense LP 4096x8192 (tableau 4097x12289), window of "
                                        f"{per_step} pivots per step", **C3, "inputs_larger_than_L2": True},
-                "roofline": L["roofline"], "gpu_launches": L["launches"], "clocks": L["clocks"], "cpu_baseline": None,
+                "roofline": L["roofline"], "gpu_launches": L["launches"], "clocks": L["clocks"],
+                "cpu_baseline": cpu_baseline_large() if with_cpu else None,
                 "e2e": {"value": L["value"], "unit": "pivots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                         "note": "the tableau is resident in HBM for the whole session; only 16 bytes of status "
                                 "cross PCIe per step"}}
@@ -476,7 +576,8 @@ def run_ours(args):
                 extras["large_tableau"] = {"metric": "simplex pivots/sec, one 4096x8192 LP (tableau 4097x12289)",
                                            "value": Lg["value"], "unit": "pivots/s", "ms_per_pivot":
                                            Lg["ms_per_step"] / Lg["pivots_per_step"], "roofline": Lg["roofline"],
-                                           "gpu_launches": Lg["launches"]}
+                                           "gpu_launches": Lg["launches"],
+                                           "cpu_baseline": cpu_baseline_large() if with_cpu else None}
             except Exception as e:  # a section must not take the headline down
                 extras["large_tableau"] = {"error": str(e)}
             try:
@@ -484,9 +585,14 @@ def run_ours(args):
             except Exception as e:
                 extras["bnb_simplex"] = {"error": str(e)}
             try:
-                extras["bnb_knapsack"] = bench_knap(16)
+                extras["bnb_knapsack"] = bench_knap(KNAP_INSTANCES)
             except Exception as e:
                 extras["bnb_knapsack"] = {"error": str(e)}
+            try:  # non-integer data: every sum in the reference's order (the ordered-summation path)
+                extras["bnb_knapsack_fractional"] = bench_knap(KNAP_INSTANCES_FRACTIONAL, kind="fractional",
+                                                               label="ordered-summation path (non-integer data)")
+            except Exception as e:
+                extras["bnb_knapsack_fractional"] = {"error": str(e)}
         line = {"metric": "simplex pivots/sec", "value": Bm["value"], "unit": "pivots/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": Bm["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",

@@ -280,6 +280,12 @@ int lpx_session_profile(lpx_session* s, int n, double* us);
 /* Development aid: phase timestamps (ns, %globaltimer) of one look-ahead step. */
 int lpx_session_debug_stamps(lpx_session* s, unsigned long long* out8);
 
+/* Work of this thread's last lpx_bnb_simplex(_batched) call: stats4[0] = floating-point operations of all
+ * node LPs (sum of pivots x (2 m_d (n+m_d+1) + (n+m_d+1)), m_d = constraint rows of that node's tableau:
+ * SURVEY.md 8d), [1] = seconds inside the GPU evaluation calls (upload, kernels, download, sync),
+ * [2] = seconds of the whole search, [3] = evaluation rounds (kernel launch groups). */
+int lpx_bnb_last_stats(double* stats4);
+
 /* ---- counters (for benchmarks: "how many of my kernels launched") --------------------------- */
 long long lpx_kernel_launches(void);   /* since lpx_init / last reset */
 void lpx_reset_counters(void);

@@ -67,6 +67,7 @@ struct Instance {
     std::vector<double> best_x;
     int records = 0;
     long long lp_pivots = 0;
+    double lp_flops = 0;  // sum over node LPs of pivots x flops per pivot at that node's shape
     int root_status = 0;
     bool finished = false;
 };
@@ -385,6 +386,12 @@ struct Driver {
         (void)I;
     }
 
+    // 2 m (n+m+1) + (n+m+1) flops per pivot of an (m+1) x (n+m+1) tableau, m = this node's rows
+    double pivot_flops(const Node& nd) const {
+        const double md = mm + (double)nd.extras.size(), w = n + md + 1;
+        return (double)nd.n_pivots * (2.0 * md * w + w);
+    }
+
     // One SolveNode body (Branch&Bound.cs:128-258) for an evaluated node.
     void commit_node(Instance& I, std::unique_ptr<Node> ndp) {
         Node& nd = *ndp;
@@ -394,6 +401,7 @@ struct Driver {
             return;
         }
         I.lp_pivots += nd.n_pivots;
+        I.lp_flops += pivot_flops(nd);
         if (nd.lp_status < 0) {  // the solve threw
             emit(I, nd, LPX_BNB_ERROR, -1, 0, 0, rec);
             return;
@@ -467,6 +475,7 @@ struct Driver {
         Node& nd = *ndp;
         const int rec = I.records++;
         I.lp_pivots += nd.n_pivots;
+        I.lp_flops += pivot_flops(nd);
         I.root_status = nd.lp_status;
         if (nd.lp_status < 0) {
             emit(I, nd, LPX_BNB_ERROR, -1, 0, 0, rec);
@@ -575,7 +584,15 @@ struct Driver {
 
 using namespace lpx;
 
+static thread_local double g_last_stats[4] = {0, 0, 0, 0};
+
 extern "C" {
+
+int lpx_bnb_last_stats(double* stats4) {
+    if (!stats4) return LPX_E_BAD_ARGS;
+    for (int k = 0; k < 4; k++) stats4[k] = g_last_stats[k];
+    return LPX_OK;
+}
 
 int lpx_bnb_simplex_batched(int count, int m, int n, int sense, const double* A, const int* rel, const double* b,
                             const double* c, const lpx_options* opt, int flags, int* found, double* best_z,
@@ -609,8 +626,14 @@ int lpx_bnb_simplex_batched(int count, int m, int n, int sense, const double* A,
     d.flags = flags;
     d.on_node = on_node;
     d.user = user;
+    const auto t_run = std::chrono::steady_clock::now();
     rc = d.run();
     if (rc != LPX_OK) return rc;
+    g_last_stats[0] = 0;
+    g_last_stats[1] = d.tr_time[0] + d.tr_time[1];
+    g_last_stats[2] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_run).count();
+    g_last_stats[3] = (double)(d.tr_launch[0] + d.tr_launch[1]);
+    for (int k = 0; k < count; k++) g_last_stats[0] += d.inst[k].lp_flops;
     for (int k = 0; k < count; k++) {
         const Instance& I = d.inst[k];
         if (found) found[k] = I.have_best ? 1 : 0;
