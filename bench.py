@@ -31,8 +31,8 @@ sys.path.insert(0, ROOT)
 
 C2 = dict(count=4096, m=64, n=128)
 C3 = dict(m=4096, n=8192)
-KNAP_INSTANCES = 16             # C5 instances per GPU in the bnb_knapsack section
-KNAP_INSTANCES_FRACTIONAL = 4
+KNAP_INSTANCES = 592            # C5 instances per GPU in the bnb_knapsack section (4 per SM: one warp each)
+KNAP_INSTANCES_FRACTIONAL = 148
 
 
 def load_peaks():

@@ -30,6 +30,7 @@
 #include <cooperative_groups.h>
 
 #include "lpx_common.cuh"
+#include "lpx_knap.hpp"
 #include "lpx_runtime.hpp"
 #include "lpx_stream.hpp"
 
@@ -1061,6 +1062,7 @@ void knapsack_release_cache() {
     for (signed char* q : cc.idle) cudaFree(q);
     cc.idle.clear();
     cc.bytes = 0;
+    knapsack_dev_release_cache();
 }
 }  // namespace lpx
 
@@ -1080,6 +1082,16 @@ static int knapsack_entry(int count, int n, const double* profit, const double* 
     int rc = ensure_device();
     if (rc != LPX_OK) return rc;
     std::lock_guard<std::recursive_mutex> lk(rt().mu);
+    {
+        lpx_options o;
+        lpx_default_options(&o);
+        if (opt) o = *opt;
+        // The search loop runs on the device (lpx_knap_dev.cu).  Only the one-tree-over-all-ranks mode still
+        // plans rounds on the host, because its exchange step is a host-driven NCCL collective.
+        if (!(o.knap_shard_tree && comm_world() > 1))
+            return knapsack_search_device(count, n, profit, weight, capacity, o, found, best_value, best_x, n_evals,
+                                          n_pops, rank_order, on_pop, user);
+    }
     KnDriver d;
     d.count = count;
     d.n = n;
