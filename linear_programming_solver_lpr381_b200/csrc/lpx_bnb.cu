@@ -52,6 +52,7 @@ struct Node {
     // evaluation
     bool evaluated = false;
     int lp_status = 0, n_pivots = 0, silent = 0;
+    int flags = 0, branch = -1;  // node epilogue of the kernel: bit 0 IsFeasible, bit 1 IsIntegral; branching variable
     double z = 0;
     std::vector<double> x;
     std::vector<int> pivots;
@@ -75,43 +76,12 @@ struct Instance {
 // Math.Round(double): ties to even
 inline double round_even(double v) { return std::nearbyint(v); }
 
-bool is_integral(const std::vector<double>& x) {
-    for (double v : x)
-        if (std::fabs(v - round_even(v)) > BB_EPS) return false;
-    return true;
-}
-
 struct BaseProblem {
     int m, n;
     const double* A;
     const int* rel;
     const double* b;
 };
-
-// BranchAndBound.IsFeasible (Branch&Bound.cs:276-294): row sums in index order, 1e-6 slack.
-bool is_feasible(const std::vector<double>& x, const BaseProblem& bp, const std::vector<Extra>& extras) {
-    const int n = bp.n;
-    for (int r = 0; r < bp.m; r++) {
-        const double* a = bp.A + (size_t)r * n;
-        double sum = 0;
-        for (int i = 0; i < n; i++) sum += a[i] * x[i];
-        const int rl = bp.rel ? bp.rel[r] : 0;
-        if (rl == 0 && sum > bp.b[r] + BB_EPS) return false;
-        if (rl == 1 && sum < bp.b[r] - BB_EPS) return false;
-        if (rl == 2 && std::fabs(sum - bp.b[r]) > BB_EPS) return false;
-    }
-    for (const Extra& e : extras) {
-        // unit row: the reference still adds 0*x terms; 0*x is +-0 and does not change a finite sum
-        double sum = 0;
-        for (int i = 0; i < n; i++) sum += (i == e.var ? 1.0 : 0.0) * x[i];
-        if (e.rel == 0 && sum > e.rhs + BB_EPS) return false;
-        if (e.rel == 1 && sum < e.rhs - BB_EPS) return false;
-        if (e.rel == 2 && std::fabs(sum - e.rhs) > BB_EPS) return false;
-    }
-    for (double v : x)
-        if (v < -BB_EPS) return false;
-    return true;
-}
 
 int choose_mode(const BaseProblem& bp, const std::vector<Extra>& extras) {
     for (int r = 0; r < bp.m; r++)
@@ -235,14 +205,14 @@ struct Driver {
         int* d_var = ws_dev_as<int>(WS_EX_VAR, total_extra + 1);
         int* d_rel = ws_dev_as<int>(WS_EX_REL, total_extra + 1);
         double* d_rhs = ws_dev_as<double>(WS_EX_RHS, total_extra + 1);
-        int* d_stat = ws_dev_as<int>(WS_STATUS, (size_t)cnt * 4);
+        int* d_stat = ws_dev_as<int>(WS_STATUS, (size_t)cnt * 6);
         double* d_x = ws_dev_as<double>(WS_X, (size_t)cnt * n);
         double* d_z = ws_dev_as<double>(WS_Z, cnt);
         int* d_piv = pivots_cap ? ws_dev_as<int>(WS_PIVOTS, (size_t)cnt * pivots_cap * 2) : nullptr;
         double* d_hist = history_cap ? ws_dev_as<double>(WS_HISTORY, (size_t)cnt * history_cap * tsize) : nullptr;
         const bool fits = cta_fits_smem(max_rows, max_width);
         double* d_scratch = fits ? nullptr : ws_dev_as<double>(WS_SCRATCH, (size_t)cnt * tsize);
-        int* h_stat = ws_pin_as<int>(WS_STATUS, (size_t)cnt * 4);
+        int* h_stat = ws_pin_as<int>(WS_STATUS, (size_t)cnt * 6);
         double* h_x = ws_pin_as<double>(WS_X, (size_t)cnt * n);
         double* h_z = ws_pin_as<double>(WS_Z, cnt);
         if (!h_inst || !h_off || !h_cnt || !h_mode || !h_var || !h_rel || !h_rhs || !d_inst || !d_off || !d_cnt ||
@@ -304,6 +274,8 @@ struct Driver {
         B.n_pivots = d_stat + cnt;
         B.silent = d_stat + 2 * cnt;
         B.n_history = d_stat + 3 * cnt;
+        B.node_flags = d_stat + 4 * cnt;
+        B.node_branch = d_stat + 5 * cnt;
         B.pivots = d_piv;
         B.pivots_cap = pivots_cap;
         B.x = d_x;
@@ -314,7 +286,7 @@ struct Driver {
         int rc = cta_launch(B, cnt, opt.kernel == LPX_KERNEL_CTA_GLOBAL ? LPX_KERNEL_CTA_GLOBAL : LPX_KERNEL_AUTO,
                             opt.threads, s, nullptr);
         if (rc != LPX_OK) return rc;
-        LPX_CUDA(cudaMemcpyAsync(h_stat, d_stat, (size_t)cnt * 16, cudaMemcpyDeviceToHost, s));
+        LPX_CUDA(cudaMemcpyAsync(h_stat, d_stat, (size_t)cnt * 24, cudaMemcpyDeviceToHost, s));
         LPX_CUDA(cudaMemcpyAsync(h_x, d_x, (size_t)cnt * n * 8, cudaMemcpyDeviceToHost, s));
         LPX_CUDA(cudaMemcpyAsync(h_z, d_z, (size_t)cnt * 8, cudaMemcpyDeviceToHost, s));
         LPX_CUDA(cudaStreamSynchronize(s));
@@ -331,6 +303,8 @@ struct Driver {
             nd->lp_status = h_stat[k];
             nd->n_pivots = h_stat[cnt + k];
             nd->silent = h_stat[2 * cnt + k];
+            nd->flags = h_stat[4 * cnt + k];
+            nd->branch = h_stat[5 * cnt + k];
             nd->z = h_z[k];
             nd->x.assign(h_x + (size_t)k * n, h_x + (size_t)(k + 1) * n);
             if (pivots_cap) {
@@ -413,7 +387,8 @@ struct Driver {
         const std::vector<double>& x = nd.x;
         const double z = nd.z;
         const BaseProblem bp = base(nd.inst);
-        if (!is_feasible(x, bp, nd.extras)) {
+        // IsFeasible, IsIntegral and the branching variable were computed by the node's kernel (cta_node_epilogue)
+        if (!(nd.flags & 1)) {
             emit(I, nd, LPX_BNB_INFEASIBLE, -1, 0, 0, rec);
             return;
         }
@@ -421,7 +396,7 @@ struct Driver {
             emit(I, nd, LPX_BNB_PRUNED, -1, 0, 0, rec);
             return;
         }
-        if (is_integral(x)) {
+        if (nd.flags & 2) {
             I.best = z;
             I.have_best = true;
             I.best_x.resize(n);
@@ -429,18 +404,7 @@ struct Driver {
             emit(I, nd, LPX_BNB_INCUMBENT, -1, 0, 0, rec);
             return;
         }
-        int frac_index = -1;
-        double min_dist = std::numeric_limits<double>::max();
-        for (int i = 0; i < n; i++) {
-            const double frac = x[i] - std::floor(x[i]);
-            if (frac > BB_EPS && (1 - frac) > BB_EPS) {
-                const double dist = std::fabs(frac - 0.5);
-                if (dist < min_dist || (dist == min_dist && i < frac_index)) {
-                    min_dist = dist;
-                    frac_index = i;
-                }
-            }
-        }
+        const int frac_index = nd.branch;
         if (frac_index == -1) {
             emit(I, nd, LPX_BNB_NOFRAC, -1, 0, 0, rec);
             return;
@@ -488,7 +452,7 @@ struct Driver {
             return;
         }
         const BaseProblem bp = base(nd.inst);
-        if (is_integral(nd.x) && is_feasible(nd.x, bp, nd.extras)) {
+        if ((nd.flags & 3) == 3) {
             I.best = nd.z;
             I.have_best = true;
             I.best_x.resize(n);

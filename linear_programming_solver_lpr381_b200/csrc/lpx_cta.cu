@@ -1,6 +1,7 @@
 // lpx_cta.cu — launcher of the one-CTA-per-tableau kernels and the C-ABI entry points built on
 // them: lpx_primal_solve, lpx_dual_solve, lpx_primal_solve_batched(_dev).
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -196,8 +197,24 @@ static int solve_single_cta(int mode, int m, int n, int sense, const double* A, 
     B.history = dH;
     B.history_stride = (long long)(tsize * (size_t)history_cap);
     B.history_cap = history_cap;
+    static const bool want_prof = getenv("LPX_CTA_PROF") != nullptr;  // measurement aid, prints to stderr
+    long long* d_prof = nullptr;
+    if (want_prof) {
+        LPX_CUDA(cudaMalloc(&d_prof, 64));
+        LPX_CUDA(cudaMemsetAsync(d_prof, 0, 64, s));
+        B.dbg = d_prof;
+    }
     int rc = cta_launch(B, 1, o.kernel, o.threads, s, nullptr);
     if (rc != LPX_OK) return rc;
+    if (want_prof) {
+        long long h[8];
+        LPX_CUDA(cudaMemcpyAsync(h, d_prof, 64, cudaMemcpyDeviceToHost, s));
+        LPX_CUDA(cudaStreamSynchronize(s));
+        cudaFree(d_prof);
+        const double np = (double)std::max(1LL, h[4]);
+        fprintf(stderr, "[cta prof] %lld x %lld tableau, %lld pivots; cycles per pivot: ratios %.0f, scan %.0f, staging %.0f, "
+                        "update %.0f\n", h[5], h[6], h[4], h[0] / np, h[1] / np, h[2] / np, h[3] / np);
+    }
 
     int hstat[4] = {0, 0, 0, 0};
     LPX_CUDA(cudaMemcpyAsync(hstat, dstat, sizeof hstat, cudaMemcpyDeviceToHost, s));

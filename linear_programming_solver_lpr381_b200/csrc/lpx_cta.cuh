@@ -54,11 +54,16 @@ struct CtaBatch {
     int history_cap;
     int* n_history;
     unsigned long long* total_pivots;
+    // Branch & Bound node epilogue (nullable): per problem, bit 0 = IsFeasible(x), bit 1 = IsIntegral(x)
+    // (R/Models/Branch&Bound.cs:268-294), and the branching variable (:198-213), -1 if none
+    int* node_flags;
+    int* node_branch;
+    long long* dbg;  // LPX_CTA_PROF=1: clock64() sums per phase of the LAST problem of the batch (8 slots)
 };
 
 // Shared-memory carve shared by host (sizing) and device.
 struct CtaCarve {
-    size_t prow, fcol, red, rsrc, rsgn, basis, ctl, T, total;
+    size_t prow, fcol, zc, red, rsrc, rsgn, basis, ctl, T, total;
 };
 __host__ __device__ inline CtaCarve cta_carve(int max_rows, int max_width, bool smem_T) {
     CtaCarve c;
@@ -67,6 +72,8 @@ __host__ __device__ inline CtaCarve cta_carve(int max_rows, int max_width, bool 
     off += (size_t)((max_width + 2) & ~1) * 8;  // even length: the update reads it two entries at a time
     c.fcol = off;
     off += (size_t)max_rows * 8;
+    c.zc = off;  // the control warp's private copy of the objective row
+    off += (size_t)max_width * 8;
     c.red = off;
     off += 34 * 16;
     c.rsrc = off;
@@ -159,6 +166,87 @@ __device__ __forceinline__ void cta_pivot(double* T, int ld, int rows, int width
         }
     }
     __syncthreads();
+}
+
+// The update alone, by the UT threads utid = 0 .. UT-1 (the control warp does not take part): prow and
+// fcol are staged already.  Same arithmetic and element order as cta_pivot.
+template <bool PAIR>
+__device__ __forceinline__ void cta_update(double* T, int ld, int rows, int width, int l, const double* prow,
+                                           const double* fcol, int utid, int UT) {
+    if (PAIR) {
+        const int pairs = (width + 1) >> 1;
+        const int cw2 = (pairs + 31) & ~31;
+        const int G = cw2 >= UT ? 1 : UT / cw2;
+        for (int q0 = 0; q0 < pairs; q0 += UT) {  // one trip unless the tableau is wider than 2 * UT
+            const int g = cw2 >= UT ? 0 : utid / cw2;
+            const int q = cw2 >= UT ? q0 + utid : utid - g * cw2;
+            if (g < G && q < pairs) {
+                const double2 pj = *reinterpret_cast<const double2*>(prow + 2 * q);
+                double* t = T + (size_t)g * ld + 2 * q;
+                const size_t step = (size_t)G * ld;
+#pragma unroll 4
+                for (int i = g; i < rows; i += G, t += step) {
+                    double2 cur = *reinterpret_cast<double2*>(t);
+                    const double f = fcol[i];
+                    if (i == l) {
+                        cur = pj;
+                    } else {
+                        cur.x = __dsub_rn(cur.x, __dmul_rn(f, pj.x));
+                        cur.y = __dsub_rn(cur.y, __dmul_rn(f, pj.y));
+                    }
+                    *reinterpret_cast<double2*>(t) = cur;
+                }
+            }
+            if (cw2 < UT) break;
+        }
+        return;
+    }
+    const int cw = (width + 31) & ~31;
+    if (cw >= UT) {
+        for (int j = utid; j < width; j += UT) {
+            const double pj = prow[j];
+            double* t = T + j;
+#pragma unroll 4
+            for (int i = 0; i < rows; i++, t += ld) {
+                const double cur = *t;
+                *t = (i == l) ? pj : __dsub_rn(cur, __dmul_rn(fcol[i], pj));
+            }
+        }
+    } else {
+        const int G = UT / cw;
+        const int g = utid / cw, j = utid - g * cw;
+        if (g < G && j < width) {
+            const double pj = prow[j];
+            double* t = T + (size_t)g * ld + j;
+            const size_t step = (size_t)G * ld;
+#pragma unroll 4
+            for (int i = g; i < rows; i += G, t += step) {
+                const double cur = *t;
+                *t = (i == l) ? pj : __dsub_rn(cur, __dmul_rn(fcol[i], pj));
+            }
+        }
+    }
+}
+
+// ChooseEntering by ONE warp over v[0 .. n): most negative entry below thresh, lowest index on ties, -1 if
+// none; NaN never wins (PrimalSimplex.cs:205-220).  All 32 lanes return the answer.
+__device__ __forceinline__ int warp_argmin_below(const double* v, int n, double thresh) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long kl = ~0ULL;
+    int il = INT_MAX;
+    for (int j = lane; j < n; j += 32) {
+        const double z = v[j];
+        if (z < thresh) {
+            const unsigned long long k = dkey(z);
+            if (k < kl) {
+                kl = k;
+                il = j;
+            }
+        }
+    }
+    const unsigned long long K = warp_min_u64(kl);
+    const int idx = __reduce_min_sync(0xffffffffu, kl == K ? il : INT_MAX);
+    return K == ~0ULL ? -1 : idx;
 }
 
 // Ratios of the min-ratio test, one division per thread (a double division is a ~40-instruction
@@ -311,6 +399,85 @@ __device__ __forceinline__ void cta_zero_outputs(const CtaBatch& B, int p, int m
     }
 }
 
+// The part of SolveNode that only looks at the node's own solution (R/Models/Branch&Bound.cs:175-213), on the
+// device so that the host commit merely orders records:
+//   IsFeasible (:276-294)  every row sum a . x in index order (one thread per row, separate multiply and add),
+//                          1e-6 slack per relation; the node's unit rows the same way; x >= -1e-6
+//   IsIntegral (:268-274)  |x - Math.Round(x)| <= 1e-6 (ties to even) for every variable
+//   branching variable (:198-213)  fractional part in (1e-6, 1 - 1e-6) closest to 0.5, lowest index on ties
+// x = the solution in global memory (complete and visible to this block); xs = n doubles of shared scratch.
+template <int THREADS>
+__device__ __forceinline__ void cta_node_epilogue(const CtaBatch& B, int p, int inst, int nex, int exo, const double* x,
+                                                  double* xs, ArgMin* red) {
+    const int tid = threadIdx.x;
+    const int n = B.n;
+    const double BB = 1e-6;  // BranchAndBound.EPS
+    for (int j = tid; j < n; j += THREADS) xs[j] = x[j];
+    __syncthreads();
+    int bad = 0;  // infeasible
+    const double* Ai = B.A + (size_t)inst * B.strideA;
+    const double* bi = B.b + (size_t)inst * B.strideB;
+    for (int r = tid; r < B.m_in + nex; r += THREADS) {
+        double sum = 0.0, bv;
+        int rl;
+        if (r < B.m_in) {
+            const double* a = Ai + (size_t)r * n;
+            for (int i = 0; i < n; i++) sum = __dadd_rn(sum, __dmul_rn(a[i], xs[i]));
+            rl = B.rel ? B.rel[r] : 0;
+            bv = bi[r];
+        } else {
+            const int var = B.ex_var[exo + r - B.m_in];
+            for (int i = 0; i < n; i++) sum = __dadd_rn(sum, __dmul_rn(i == var ? 1.0 : 0.0, xs[i]));
+            rl = B.ex_rel[exo + r - B.m_in];
+            bv = B.ex_rhs[exo + r - B.m_in];
+        }
+        if (rl == 0 && sum > __dadd_rn(bv, BB)) bad = 1;
+        if (rl == 1 && sum < __dsub_rn(bv, BB)) bad = 1;
+        if (rl == 2 && fabs(__dsub_rn(sum, bv)) > BB) bad = 1;
+    }
+    int nonint = 0;
+    unsigned long long kl = ~0ULL;  // key of |frac - 0.5|, then the index
+    int il = INT_MAX;
+    for (int i = tid; i < n; i += THREADS) {
+        const double v = xs[i];
+        if (v < -BB) bad = 1;
+        if (fabs(__dsub_rn(v, rint(v))) > BB) nonint = 1;
+        const double frac = __dsub_rn(v, floor(v));
+        if (frac > BB && __dsub_rn(1.0, frac) > BB) {
+            const unsigned long long k = dkey(fabs(__dsub_rn(frac, 0.5)));
+            if (k < kl) {
+                kl = k;
+                il = i;
+            }
+        }
+    }
+    const int any_bad = __syncthreads_or(bad), any_nonint = __syncthreads_or(nonint);
+    // block argmin of (distance key, index): per warp, then over the warp partials
+    const int lane = tid & 31, warp = tid >> 5;
+    const unsigned long long K = warp_min_u64(kl);
+    const int iw = __reduce_min_sync(0xffffffffu, kl == K ? il : INT_MAX);
+    if (lane == 0) {
+        red[warp].v = __longlong_as_double((long long)K);
+        red[warp].i = iw;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long k2 = ~0ULL;
+        int i2 = INT_MAX;
+        if (lane < THREADS / 32) {
+            k2 = (unsigned long long)__double_as_longlong(red[lane].v);
+            i2 = red[lane].i;
+        }
+        const unsigned long long K2 = warp_min_u64(k2);
+        const int idx = __reduce_min_sync(0xffffffffu, k2 == K2 ? i2 : INT_MAX);
+        if (lane == 0) {
+            B.node_flags[p] = (any_bad ? 0 : 1) | (any_nonint ? 0 : 2);
+            B.node_branch[p] = K2 == ~0ULL ? -1 : idx;
+        }
+    }
+    __syncthreads();
+}
+
 template <int THREADS, bool SMEM_T>
 __global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -393,101 +560,136 @@ __global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) 
         __syncthreads();
 
         const double* zrow = T + (size_t)m * ld;
+        double* zc = reinterpret_cast<double*>(smem_raw + cv.zc);
+        long long pc[4] = {0, 0, 0, 0}, c0 = 0;
+        const bool prof = B.dbg != nullptr && p == (int)gridDim.x - 1;
+#define CTA_TICK(slot)                       \
+    if (prof) {                              \
+        const long long c1 = clock64();      \
+        pc[slot] += c1 - c0;                 \
+        c0 = c1;                             \
+    }
 
-        if (mode == 1) {
-            // ---- ForceDualFeasibility: <= 100 silent primal pivots, ratio margin 1e-12 -------
-            for (int guard = 0; guard < 100; guard++) {
-                const int e = block_argmin_below<THREADS>(zrow, width - 1, -LPX_EPS, red);
-                if (e < 0) break;
-                cta_stage_ratios<THREADS>(T, ld, m, e, rhs, prow);
-                if (warp == 0) {
-                    const int l = warp_margin_scan_cert(m, LPX_MARGIN_DUAL, [&](int i, double& r) {
-                        r = prow[i];
-                        return r == r;
-                    });
-                    if (lane == 0) ctl[2] = l;
-                }
-                __syncthreads();
-                const int l = ctl[2];
-                if (l < 0) break;
-                cta_pivot<THREADS, SMEM_T>(T, ld, rows, width, l, e, prow, fcol);
-                if (tid == 0) {
-                    sbasis[l] = e;
-                    if (plog && n_piv < B.pivots_cap) {
-                        plog[2 * n_piv] = e;
-                        plog[2 * n_piv + 1] = l;
-                    }
-                }
-                n_piv++;
-                n_silent++;
+        // ---- primal pivots (PrimalSimplex.cs:92-124; ForceDualFeasibility, DualSimplex.cs:195-228) -------
+        // Four block barriers per pivot.  Warp 0 is the CONTROL warp: it keeps a private copy of the
+        // objective row (zc, updated with the very operations the tableau's own row sees, so bit-identical)
+        // and, while the other warps stream the rank-1 update through shared memory, it updates that copy
+        // and picks the NEXT entering column — ChooseEntering never costs the block a phase.  After the
+        // update: ratios, one division per thread | the control warp's margin scan | pivot row / factor
+        // column staged | update.
+        // Returns why it stopped: 0 = `limit` pivots done, 1 = no entering column, 2 = no leaving row.
+        auto primal_steps = [&](double margin, int limit, bool silent) -> int {
+            if (warp == 0) {
+                for (int j = lane; j < width; j += 32) zc[j] = zrow[j];
+                __syncwarp();
+                const int e0 = warp_argmin_below(zc, width - 1, -LPX_EPS);
+                if (lane == 0) ctl[3] = e0;
             }
-        }
-
-        if (hist && n_hist < B.history_cap) {
-            cta_copy_out<THREADS>(hist + (size_t)n_hist * tsize, T, ld, rows, width);
-            n_hist++;
-        }
-
-        int iter = 1;
-        while (true) {
-            if (iter > (mode == 1 ? LPX_DUAL_MAX_ITER : B.max_iter)) {
-                status = LPX_S_ITER_LIMIT;
-                break;
-            }
-            int e, l;
-            if (mode == 0) {
-                // ChooseEntering: most negative z-row entry below -1e-9, lowest index on ties
-                e = block_argmin_below<THREADS>(zrow, width - 1, -LPX_EPS, red);
-                if (e < 0) {
-                    status = LPX_OPTIMAL;
-                    break;
-                }
-                // ChooseLeaving: sequential margin scan over rows with T[i,e] > 1e-9
+            __syncthreads();
+            int steps = 0;
+            while (true) {
+                if (steps >= limit) return 0;
+                if (prof) c0 = clock64();
+                const int e = ctl[3];
+                if (e < 0) return 1;
                 cta_stage_ratios<THREADS>(T, ld, m, e, rhs, prow);
+                CTA_TICK(0)
                 if (warp == 0) {
-                    const int lv = warp_margin_scan_cert(m, LPX_MARGIN_PRIMAL, [&](int i, double& r) {
+                    const int lv = warp_margin_scan_cert(m, margin, [&](int i, double& r) {
                         r = prow[i];
                         return r == r;
                     });
                     if (lane == 0) ctl[2] = lv;
                 }
                 __syncthreads();
-                l = ctl[2];
-                if (l < 0) {
-                    status = LPX_UNBOUNDED;
-                    break;
-                }
-            } else {
-                // dual: leaving row = most negative RHS below -1e-9 (DualSimplex.cs:45-55)
-                l = block_argmin_below_strided<THREADS>(T + rhs, (size_t)ld, m, -LPX_EPS, red);
-                if (l < 0) {
-                    status = LPX_OPTIMAL;
-                    break;
-                }
-                // entering column: min z_j / (-a) over a < -1e-9, margin 1e-12 (DualSimplex.cs:76-91)
-                {
-                    const double* lrow = T + (size_t)l * ld;
-                    for (int j = tid; j < width - 1; j += THREADS) {
-                        const double a = lrow[j];
-                        double r = __longlong_as_double(0x7ff8000000000000LL);
-                        if (a < -LPX_EPS) r = ddiv_by_pivot(zrow[j], dneg(a));
-                        prow[j] = r;
-                    }
-                    __syncthreads();
-                }
-                if (warp == 0) {
-                    const int ev = warp_margin_scan_cert(width - 1, LPX_MARGIN_DUAL, [&](int j, double& r) {
-                        r = prow[j];
-                        return r == r;
-                    });
-                    if (lane == 0) ctl[2] = ev;
+                CTA_TICK(1)
+                const int l = ctl[2];
+                if (l < 0) return 2;
+                {   // the normalised pivot row and the factor column: every element sees T[i,e] as it was before
+                    // row i changed and the ROUNDED quotient T[l,j] / piv (PrimalSimplex.cs:245-257)
+                    const double piv = T[(size_t)l * ld + e];
+                    for (int j = tid; j < width; j += THREADS) prow[j] = ddiv_by_pivot(T[(size_t)l * ld + j], piv);
+                    for (int i = tid; i < rows; i += THREADS) fcol[i] = T[(size_t)i * ld + e];
+                    if (SMEM_T && tid == 0 && (width & 1)) prow[width] = 0.0;
                 }
                 __syncthreads();
-                e = ctl[2];
-                if (e < 0) {
-                    status = LPX_INFEASIBLE;
-                    break;
+                CTA_TICK(2)
+                if (warp == 0) {
+                    const double fz = fcol[m];
+                    for (int j = lane; j < width; j += 32) zc[j] = __dsub_rn(zc[j], __dmul_rn(fz, prow[j]));
+                    __syncwarp();
+                    const int en = warp_argmin_below(zc, width - 1, -LPX_EPS);
+                    if (lane == 0) {
+                        ctl[3] = en;
+                        sbasis[l] = e;
+                        if (plog && n_piv < B.pivots_cap) {
+                            plog[2 * n_piv] = e;
+                            plog[2 * n_piv + 1] = l;
+                        }
+                    }
+                } else {
+                    cta_update<SMEM_T>(T, ld, rows, width, l, prow, fcol, tid - 32, THREADS - 32);
                 }
+                __syncthreads();
+                CTA_TICK(3)
+                n_piv++;
+                if (silent) n_silent++;
+                else if (hist && n_hist < B.history_cap) {
+                    cta_copy_out<THREADS>(hist + (size_t)n_hist * tsize, T, ld, rows, width);
+                    n_hist++;
+                }
+                steps++;
+            }
+        };
+
+        if (mode == 1) primal_steps(LPX_MARGIN_DUAL, 100, true);  // <= 100 silent pivots, ratio margin 1e-12
+
+        if (hist && n_hist < B.history_cap) {
+            cta_copy_out<THREADS>(hist + (size_t)n_hist * tsize, T, ld, rows, width);
+            n_hist++;
+        }
+
+        if (mode == 0) {
+            // "if (iter > MaxIterations) throw" comes before the optimality test (PrimalSimplex.cs:95-96)
+            const int why = primal_steps(LPX_MARGIN_PRIMAL, B.max_iter, false);
+            status = why == 0 ? LPX_S_ITER_LIMIT : (why == 1 ? LPX_OPTIMAL : LPX_UNBOUNDED);
+        }
+        int iter = 1;
+        while (mode == 1) {
+            if (iter > LPX_DUAL_MAX_ITER) {
+                status = LPX_S_ITER_LIMIT;
+                break;
+            }
+            int e, l;
+            // dual: leaving row = most negative RHS below -1e-9 (DualSimplex.cs:45-55)
+            l = block_argmin_below_strided<THREADS>(T + rhs, (size_t)ld, m, -LPX_EPS, red);
+            if (l < 0) {
+                status = LPX_OPTIMAL;
+                break;
+            }
+            // entering column: min z_j / (-a) over a < -1e-9, margin 1e-12 (DualSimplex.cs:76-91)
+            {
+                const double* lrow = T + (size_t)l * ld;
+                for (int j = tid; j < width - 1; j += THREADS) {
+                    const double a = lrow[j];
+                    double r = __longlong_as_double(0x7ff8000000000000LL);
+                    if (a < -LPX_EPS) r = ddiv_by_pivot(zrow[j], dneg(a));
+                    prow[j] = r;
+                }
+                __syncthreads();
+            }
+            if (warp == 0) {
+                const int ev = warp_margin_scan_cert(width - 1, LPX_MARGIN_DUAL, [&](int j, double& r) {
+                    r = prow[j];
+                    return r == r;
+                });
+                if (lane == 0) ctl[2] = ev;
+            }
+            __syncthreads();
+            e = ctl[2];
+            if (e < 0) {
+                status = LPX_INFEASIBLE;
+                break;
             }
             cta_pivot<THREADS, SMEM_T>(T, ld, rows, width, l, e, prow, fcol);
             if (tid == 0) {
@@ -504,6 +706,13 @@ __global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) 
             }
             iter++;
         }
+#undef CTA_TICK
+        if (prof && tid == 0) {
+            for (int t = 0; t < 4; t++) B.dbg[t] = pc[t];
+            B.dbg[4] = n_piv;
+            B.dbg[5] = rows;
+            B.dbg[6] = width;
+        }
         __syncthreads();
 
         // ---- FinalizeReport's numeric part (PrimalSimplex.cs:132-138) -------------------------
@@ -519,6 +728,10 @@ __global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) 
         if (B.z && tid == 0) B.z[p] = T[(size_t)m * ld + rhs];
         if (B.tableau && (SMEM_T || T != B.tableau + (size_t)p * B.tableau_stride))
             cta_copy_out<THREADS>(B.tableau + (size_t)p * B.tableau_stride, T, ld, rows, width);
+        if (B.node_flags && B.x && mode == 0) {  // prow (width > n doubles) is free now
+            __syncthreads();
+            cta_node_epilogue<THREADS>(B, p, inst, nex, exo, B.x + (size_t)p * n, prow, red);
+        }
     } else {
         cta_zero_outputs<THREADS>(B, p, m, n, rows, width);
     }

@@ -22,7 +22,7 @@
 namespace lpx {
 
 struct CtaClusterCarve {
-    size_t prow, ratio, fcol, red, part, rsrc, rsgn, basis, ctl, T, total;
+    size_t prow, ratio, fcol, zc, red, part, rsrc, rsgn, basis, ctl, T, total;
     int H;  // rows per CTA
 };
 __host__ __device__ inline CtaClusterCarve cta_cluster_carve(int max_rows, int max_width, int cl) {
@@ -36,6 +36,8 @@ __host__ __device__ inline CtaClusterCarve cta_cluster_carve(int max_rows, int m
     off += (size_t)vec * 8;
     c.fcol = off;
     off += (size_t)c.H * 8;
+    c.zc = off;  // every CTA's control warp keeps its own copy of the whole objective row
+    off += (size_t)max_width * 8;
     c.red = off;
     off += 34 * 16;
     c.part = off;
@@ -81,6 +83,7 @@ __global__ void __launch_bounds__(THREADS) cta_cluster_simplex_kernel(const CtaB
     double* prow = reinterpret_cast<double*>(smem_raw + cv.prow);
     double* ratio = reinterpret_cast<double*>(smem_raw + cv.ratio);
     double* fcol = reinterpret_cast<double*>(smem_raw + cv.fcol);
+    double* zc = reinterpret_cast<double*>(smem_raw + cv.zc);
     ArgMin* red = reinterpret_cast<ArgMin*>(smem_raw + cv.red);
     ArgMin* part = reinterpret_cast<ArgMin*>(smem_raw + cv.part);
     int* rsrc = reinterpret_cast<int*>(smem_raw + cv.rsrc);
@@ -147,37 +150,7 @@ __global__ void __launch_bounds__(THREADS) cta_cluster_simplex_kernel(const CtaB
         for (int i = tid; i < m; i += THREADS) sbasis[i] = n + i;
         __syncthreads();
 
-        // ---- the exchanges ------------------------------------------------------------------------
-        // entering column of a primal step: owner of the objective row -> ctl[3] of every CTA
-        auto entering_primal = [&]() -> int {
-            if (rank == zr) {
-                const int e = block_argmin_below<THREADS>(loc(m), width - 1, -LPX_EPS, red);
-                if (tid < CL) cluster.map_shared_rank(ctl, tid)[3] = e;
-            }
-            cluster.sync();
-            return ctl[3];
-        };
-        // leaving row of a primal step: ratios of own rows -> every CTA, then the exact scan everywhere
-        auto leaving_primal = [&](int e, double margin) -> int {
-            for (int i = r_lo + tid; i < r_hi && i < m; i += THREADS) {
-                const double a = loc(i)[e];
-                double r = __longlong_as_double(0x7ff8000000000000LL);
-                if (a > LPX_EPS) r = ddiv_by_pos(loc(i)[rhs], a);
-#pragma unroll
-                for (int rk = 0; rk < CL; rk++) cluster.map_shared_rank(ratio, rk)[i] = r;
-            }
-            cluster.sync();
-            if (warp == 0) {
-                const int l = warp_margin_scan_cert(m, margin, [&](int i, double& r) {
-                    r = ratio[i];
-                    return r == r;
-                });
-                if (lane == 0) ctl[2] = l;
-            }
-            __syncthreads();
-            return ctl[2];
-        };
-        // Gauss-Jordan pivot on (l, e).  raw_row_everywhere: prow of every CTA already holds the raw
+        // Gauss-Jordan pivot of a DUAL step on (l, e).  raw_row_everywhere: prow of every CTA already holds the raw
         // row l (dual step); otherwise its owner normalises it and sends the quotients.
         auto pivot = [&](int l, int e, bool raw_row_everywhere) {
             if (!raw_row_everywhere) {
@@ -244,41 +217,133 @@ __global__ void __launch_bounds__(THREADS) cta_cluster_simplex_kernel(const CtaB
             }
         };
 
-        if (mode == 1) {
-            // ---- ForceDualFeasibility: <= 100 silent primal pivots, ratio margin 1e-12 -------------
-            for (int guard = 0; guard < 100; guard++) {
-                const int e = entering_primal();
-                if (e < 0) break;
-                const int l = leaving_primal(e, LPX_MARGIN_DUAL);
-                if (l < 0) break;
-                pivot(l, e, false);
-                log_pivot(e, l);
-                n_piv++;
-                n_silent++;
+        // ---- primal pivots: two cluster barriers and two block barriers each -------------------------
+        // Warp 0 of EVERY CTA is a control warp with its own copy of the whole objective row (zc): all
+        // copies see the same operations in the same order as the tableau's row, so they stay bit-identical
+        // to it and to one another, and each CTA picks the next entering column by itself while its other
+        // warps update their rows — no exchange, no barrier for ChooseEntering.  What still crosses the
+        // cluster: the ratios of every CTA's rows (all -> all; every control warp repeats the exact scan)
+        // and the normalised pivot row (owner -> all).
+        // Returns why it stopped: 0 = `limit` pivots done, 1 = no entering column, 2 = no leaving row.
+        auto primal_steps = [&](double margin, int limit, bool silent) -> int {
+            // the objective row as it stands: its owner sends it to every CTA's copy
+            if (rank == zr) {
+                const double* zrow = loc(m);
+                for (int j = tid; j < width; j += THREADS) {
+                    const double v = zrow[j];
+#pragma unroll
+                    for (int rk = 0; rk < CL; rk++) cluster.map_shared_rank(zc, rk)[j] = v;
+                }
             }
-        }
+            cluster.sync();
+            if (warp == 0) {
+                const int e0 = warp_argmin_below(zc, width - 1, -LPX_EPS);
+                if (lane == 0) ctl[3] = e0;
+            }
+            __syncthreads();
+            int steps = 0;
+            while (true) {
+                if (steps >= limit) return 0;
+                const int e = ctl[3];
+                if (e < 0) return 1;
+                // ratios and factors of the own rows (the tableau is current: the update ended with a barrier)
+                for (int i = r_lo + tid; i < r_hi; i += THREADS) {
+                    const double a = loc(i)[e];
+                    fcol[i - r_lo] = a;
+                    if (i < m) {
+                        double r = __longlong_as_double(0x7ff8000000000000LL);
+                        if (a > LPX_EPS) r = ddiv_by_pos(loc(i)[rhs], a);
+#pragma unroll
+                        for (int rk = 0; rk < CL; rk++) cluster.map_shared_rank(ratio, rk)[i] = r;
+                    }
+                }
+                cluster.sync();
+                if (warp == 0) {
+                    const int lv = warp_margin_scan_cert(m, margin, [&](int i, double& r) {
+                        r = ratio[i];
+                        return r == r;
+                    });
+                    if (lane == 0) ctl[2] = lv;
+                }
+                __syncthreads();
+                const int l = ctl[2];
+                if (l < 0) return 2;
+                if (rank == owner(l)) {  // the owner normalises the pivot row and sends the quotients
+                    const double* Tl = loc(l);
+                    const double piv = Tl[e];
+                    for (int j = tid; j < width; j += THREADS) {
+                        const double pj = ddiv_by_pivot(Tl[j], piv);
+#pragma unroll
+                        for (int rk = 0; rk < CL; rk++) cluster.map_shared_rank(prow, rk)[j] = pj;
+                    }
+                }
+                cluster.sync();
+                if (warp == 0) {
+                    const double fz = zc[e];  // the objective row's factor: its entry in the entering column
+                    __syncwarp();
+                    for (int j = lane; j < width; j += 32) zc[j] = __dsub_rn(zc[j], __dmul_rn(fz, prow[j]));
+                    __syncwarp();
+                    const int en = warp_argmin_below(zc, width - 1, -LPX_EPS);
+                    if (lane == 0) {
+                        ctl[3] = en;
+                        sbasis[l] = e;
+                        if (plog && n_piv < B.pivots_cap) {
+                            plog[2 * n_piv] = e;
+                            plog[2 * n_piv + 1] = l;
+                        }
+                    }
+                } else {
+                    // own rows, two adjacent columns per thread, 16-byte shared accesses
+                    const int utid = tid - 32, UT = THREADS - 32;
+                    const int pairs = (width + 1) >> 1;
+                    const int cw2 = (pairs + 31) & ~31;
+                    const int G = cw2 >= UT ? 1 : UT / cw2;
+                    for (int q0 = 0; q0 < pairs; q0 += UT) {
+                        const int g = cw2 >= UT ? 0 : utid / cw2;
+                        const int q = cw2 >= UT ? q0 + utid : utid - g * cw2;
+                        if (g < G && q < pairs) {
+                            const double2 pj = *reinterpret_cast<const double2*>(prow + 2 * q);
+                            double* t = T + (size_t)g * ld + 2 * q;
+                            const size_t step = (size_t)G * ld;
+#pragma unroll 4
+                            for (int i = r_lo + g; i < r_hi; i += G, t += step) {
+                                double2 cur = *reinterpret_cast<double2*>(t);
+                                const double f = fcol[i - r_lo];
+                                if (i == l) {
+                                    cur = pj;
+                                } else {
+                                    cur.x = __dsub_rn(cur.x, __dmul_rn(f, pj.x));
+                                    cur.y = __dsub_rn(cur.y, __dmul_rn(f, pj.y));
+                                }
+                                *reinterpret_cast<double2*>(t) = cur;
+                            }
+                        }
+                        if (cw2 < UT) break;
+                    }
+                }
+                __syncthreads();
+                n_piv++;
+                if (silent) n_silent++;
+                else snapshot();
+                steps++;
+            }
+        };
+
+        if (mode == 1) primal_steps(LPX_MARGIN_DUAL, 100, true);  // ForceDualFeasibility: <= 100 silent pivots
         snapshot();
 
+        if (mode == 0) {
+            const int why = primal_steps(LPX_MARGIN_PRIMAL, B.max_iter, false);
+            status = why == 0 ? LPX_S_ITER_LIMIT : (why == 1 ? LPX_OPTIMAL : LPX_UNBOUNDED);
+        }
         int iter = 1;
-        while (true) {
-            if (iter > (mode == 1 ? LPX_DUAL_MAX_ITER : B.max_iter)) {
+        while (mode == 1) {
+            if (iter > LPX_DUAL_MAX_ITER) {
                 status = LPX_S_ITER_LIMIT;
                 break;
             }
             int e, l;
-            if (mode == 0) {
-                e = entering_primal();
-                if (e < 0) {
-                    status = LPX_OPTIMAL;
-                    break;
-                }
-                l = leaving_primal(e, LPX_MARGIN_PRIMAL);
-                if (l < 0) {
-                    status = LPX_UNBOUNDED;
-                    break;
-                }
-                pivot(l, e, false);
-            } else {
+            {
                 // dual: leaving row = most negative RHS below -1e-9, lowest row on ties (DualSimplex.cs:45-55)
                 {
                     const int cnt_own = max(0, min(r_hi, m) - r_lo);
@@ -391,6 +456,10 @@ __global__ void __launch_bounds__(THREADS) cta_cluster_simplex_kernel(const CtaB
                 if (sbasis[i] < n) xo[sbasis[i]] = loc(i)[rhs];
         }
         if (B.z && rank == zr && tid == 0) B.z[p] = loc(m)[rhs];
+        if (B.node_flags && B.x && mode == 0) {
+            cluster.sync();  // every CTA's part of x is written and visible
+            if (rank == 0) cta_node_epilogue<THREADS>(B, p, inst, nex, exo, B.x + (size_t)p * n, prow, red);
+        }
         if (B.tableau) {
             double* dst = B.tableau + (size_t)p * B.tableau_stride;
             for (int i = r_lo; i < r_hi; i++)
