@@ -31,6 +31,7 @@ sys.path.insert(0, ROOT)
 
 C2 = dict(count=4096, m=64, n=128)
 C3 = dict(m=4096, n=8192)
+BNB_INSTANCES = 512             # C4 instances per GPU in the bnb_simplex section ("e.g. 512")
 KNAP_INSTANCES = 592            # C5 instances per GPU in the bnb_knapsack section (4 per SM: one warp each)
 KNAP_INSTANCES_FRACTIONAL = 148
 
@@ -581,7 +582,7 @@ def run_ours(args):
             except Exception as e:  # a section must not take the headline down
                 extras["large_tableau"] = {"error": str(e)}
             try:
-                extras["bnb_simplex"] = bench_bnb(256)
+                extras["bnb_simplex"] = bench_bnb(BNB_INSTANCES)
             except Exception as e:
                 extras["bnb_simplex"] = {"error": str(e)}
             try:

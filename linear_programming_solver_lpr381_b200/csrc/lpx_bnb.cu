@@ -327,6 +327,158 @@ struct Driver {
         return LPX_OK;
     }
 
+    // ---- asynchronous evaluation (batches without a callback) -------------------------------------
+    // One evaluation SET = all open nodes of half of the instances: descriptors staged in one pinned blob,
+    // one upload, one launch per kernel family (nodes that fit one SM's shared memory | cluster / global-
+    // memory nodes), one download, one event.  Two sets alternate on the stream, so the host commits one
+    // half's round while the GPU solves the other half's.
+    struct EvalSet {
+        std::vector<Node*> nodes;  // kind 0 first, then kind 1
+        int c0 = 0, total = 0;
+        cudaEvent_t done = nullptr;
+        bool active = false;
+        int *h_stat = nullptr;
+        double *h_x = nullptr, *h_z = nullptr;
+    } sets[2];
+
+    int evaluate_async(std::vector<Node*>& todo, int set) {
+        EvalSet& E = sets[set];
+        E.active = false;
+        if (todo.empty()) return LPX_OK;
+        Runtime& r = rt();
+        const auto tr_t0 = std::chrono::steady_clock::now();
+        E.nodes.clear();
+        std::vector<Node*> big;
+        size_t total_extra = 0;
+        int max_extra[2] = {0, 0};
+        for (Node* nd : todo) {
+            const int rows = mm + (int)nd->extras.size() + 1, width = n + rows;
+            const bool fits = cta_fits_smem(rows, width);
+            (fits ? E.nodes : big).push_back(nd);
+            max_extra[fits ? 0 : 1] = std::max(max_extra[fits ? 0 : 1], (int)nd->extras.size());
+            total_extra += nd->extras.size();
+        }
+        E.c0 = (int)E.nodes.size();
+        E.nodes.insert(E.nodes.end(), big.begin(), big.end());
+        const int total = E.total = (int)E.nodes.size();
+        // input blob: inst, off, cnt, mode (ints per node), var, rel (ints per extra), rhs (doubles per extra)
+        const size_t in_ints = (size_t)4 * total + 2 * (total_extra + 1);
+        const size_t in_bytes = ((in_ints * 4 + 7) & ~(size_t)7) + (total_extra + 1) * 8;
+        // output blob: status, n_pivots, silent, n_history, flags, branch (ints), z, x (doubles)
+        const size_t out_bytes = (size_t)total * 6 * 4 + (size_t)total * 8 + (size_t)total * n * 8;
+        const Slot s_in = set ? WS_BB_IN1 : WS_BB_IN0, s_out = set ? WS_BB_OUT1 : WS_BB_OUT0,
+                   s_scr = set ? WS_BB_SCR1 : WS_BB_SCR0;
+        unsigned char* h_in = (unsigned char*)ws_pin(s_in, in_bytes);
+        unsigned char* d_in = (unsigned char*)ws_dev(s_in, in_bytes);
+        unsigned char* h_out = (unsigned char*)ws_pin(s_out, out_bytes);
+        unsigned char* d_out = (unsigned char*)ws_dev(s_out, out_bytes);
+        if (!h_in || !d_in || !h_out || !d_out) return LPX_E_CUDA;
+        int* hi = (int*)h_in;
+        int *h_inst = hi, *h_off = hi + total, *h_cnt = hi + 2 * total, *h_mode = hi + 3 * total;
+        int *h_var = hi + 4 * total, *h_rel = h_var + total_extra + 1;
+        double* h_rhs = (double*)(h_in + ((in_ints * 4 + 7) & ~(size_t)7));
+        size_t off = 0;
+        for (int k = 0; k < total; k++) {
+            Node* nd = E.nodes[k];
+            h_inst[k] = nd->inst;
+            h_off[k] = (int)off;
+            h_cnt[k] = (int)nd->extras.size();
+            h_mode[k] = nd->mode;
+            for (const Extra& e : nd->extras) {
+                h_var[off] = e.var;
+                h_rel[off] = e.rel;
+                h_rhs[off] = e.rhs;
+                off++;
+            }
+        }
+        cudaStream_t s = r.stream;
+        LPX_CUDA(cudaMemcpyAsync(d_in, h_in, in_bytes, cudaMemcpyHostToDevice, s));
+        int* di = (int*)d_in;
+        int* d_stat = (int*)d_out;
+        double* d_z = (double*)(d_out + (size_t)total * 24);
+        double* d_x = d_z + total;
+        for (int kind = 0; kind < 2; kind++) {
+            const int lo = kind ? E.c0 : 0, cnt = kind ? total - E.c0 : E.c0;
+            if (cnt == 0) continue;
+            const int max_rows = mm + max_extra[kind] + 1, max_width = n + max_rows;
+            const size_t tsize = (size_t)max_rows * max_width;
+            CtaBatch B;
+            std::memset(&B, 0, sizeof B);
+            B.A = dA;
+            B.b = db;
+            B.c = dc;
+            B.rel = rel ? drel : nullptr;
+            B.strideA = (long long)m * n;
+            B.strideB = m;
+            B.strideC = n;
+            B.m_in = m;
+            B.n = n;
+            B.sense = sense;
+            B.m_base = mm;
+            B.node_inst = di + lo;
+            B.node_extra_off = di + total + lo;
+            B.node_extra_cnt = di + 2 * total + lo;
+            B.node_mode = di + 3 * total + lo;
+            B.ex_var = di + 4 * total;
+            B.ex_rel = di + 4 * total + total_extra + 1;
+            B.ex_rhs = (const double*)(d_in + ((in_ints * 4 + 7) & ~(size_t)7));
+            B.max_iter = opt.max_iterations;
+            B.max_rows = max_rows;
+            B.max_width = max_width;
+            if (kind == 1 && cta_cluster_size_for(max_rows, max_width) == 0) {  // beyond a 4-CTA cluster: global memory
+                double* sc = (double*)ws_dev(s_scr, (size_t)cnt * tsize * 8);
+                if (!sc) return LPX_E_CUDA;
+                B.scratch = sc;
+                B.scratch_stride = (long long)tsize;
+            }
+            B.status = d_stat + lo;
+            B.n_pivots = d_stat + total + lo;
+            B.silent = d_stat + 2 * total + lo;
+            B.n_history = d_stat + 3 * total + lo;
+            B.node_flags = d_stat + 4 * total + lo;
+            B.node_branch = d_stat + 5 * total + lo;
+            B.x = d_x + (size_t)lo * n;
+            B.z = d_z + lo;
+            int rc = cta_launch(B, cnt, opt.kernel == LPX_KERNEL_CTA_GLOBAL ? LPX_KERNEL_CTA_GLOBAL : LPX_KERNEL_AUTO,
+                                opt.threads, s, nullptr);
+            if (rc != LPX_OK) return rc;
+            tr_launch[kind]++;
+            tr_nodes[kind] += cnt;
+        }
+        LPX_CUDA(cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, s));
+        if (!E.done) LPX_CUDA(cudaEventCreateWithFlags(&E.done, cudaEventDisableTiming));
+        LPX_CUDA(cudaEventRecord(E.done, s));
+        E.h_stat = (int*)h_out;
+        E.h_z = (double*)(h_out + (size_t)total * 24);
+        E.h_x = E.h_z + total;
+        E.active = true;
+        tr_time[1] += std::chrono::duration<double>(std::chrono::steady_clock::now() - tr_t0).count();
+        return LPX_OK;
+    }
+
+    int evaluate_finish(int set) {
+        EvalSet& E = sets[set];
+        if (!E.active) return LPX_OK;
+        const auto tr_t0 = std::chrono::steady_clock::now();
+        LPX_CUDA(cudaEventSynchronize(E.done));
+        tr_time[0] += std::chrono::duration<double>(std::chrono::steady_clock::now() - tr_t0).count();
+        const int total = E.total;
+        for (int k = 0; k < total; k++) {
+            Node* nd = E.nodes[k];
+            nd->evaluated = true;
+            nd->lp_status = E.h_stat[k];
+            nd->n_pivots = E.h_stat[total + k];
+            nd->silent = E.h_stat[2 * total + k];
+            nd->flags = E.h_stat[4 * total + k];
+            nd->branch = E.h_stat[5 * total + k];
+            nd->z = E.h_z[k];
+            nd->x.assign(E.h_x + (size_t)k * n, E.h_x + (size_t)(k + 1) * n);
+            tr_piv[k < E.c0 ? 0 : 1] += nd->n_pivots;
+        }
+        E.active = false;
+        return LPX_OK;
+    }
+
     // ---- commit logic -------------------------------------------------------------------------
     void emit(Instance& I, const Node& nd, int outcome, int branch_var, int floor_val, int ceil_val, int rec_index) {
         if (!on_node) return;
@@ -471,6 +623,69 @@ struct Driver {
         I.stack.push_back(std::move(again));
     }
 
+    // SolveNode bodies of the evaluated nodes of instances [lo, hi), on a few host threads (independent trees).
+    void commit_range(int lo, int hi) {
+        auto commit_instance = [&](Instance& I) {
+            while (!I.finished && !I.stack.empty() && I.stack.back()->evaluated) {
+                std::unique_ptr<Node> nd = std::move(I.stack.back());
+                I.stack.pop_back();
+                if (nd->is_root_lp) commit_root_lp(I, std::move(nd));
+                else commit_node(I, std::move(nd));
+            }
+            if (I.stack.empty()) I.finished = true;
+        };
+        const int nthreads = host_threads();
+        if (nthreads <= 1 || hi - lo < 16) {
+            for (int k = lo; k < hi; k++) commit_instance(inst[k]);
+            return;
+        }
+        std::atomic<int> next(lo);
+        auto worker = [&]() {
+            for (;;) {
+                const int a = next.fetch_add(8);
+                if (a >= hi) break;
+                for (int k = a; k < std::min(hi, a + 8); k++) commit_instance(inst[k]);
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nthreads; t++) pool.emplace_back(worker);
+        worker();
+        for (std::thread& th : pool) th.join();
+    }
+
+    // Two halves of the batch alternate: while the GPU solves the open nodes of one half, the host commits
+    // the other half's round and stages its next one.
+    int run_pipelined() {
+        const int half = count / 2;
+        const int lo[2] = {0, half}, hi[2] = {half, count};
+        auto enqueue = [&](int g) -> int {
+            std::vector<Node*> todo;
+            for (int k = lo[g]; k < hi[g]; k++)
+                if (!inst[k].finished)
+                    for (auto& nd : inst[k].stack)
+                        if (!nd->evaluated) todo.push_back(nd.get());
+            return evaluate_async(todo, g);
+        };
+        int rc;
+        for (int g = 0; g < 2; g++)
+            if ((rc = enqueue(g)) != LPX_OK) return rc;
+        while (sets[0].active || sets[1].active) {
+            for (int g = 0; g < 2; g++) {
+                if (!sets[g].active) continue;
+                if ((rc = evaluate_finish(g)) != LPX_OK) return rc;
+                commit_range(lo[g], hi[g]);
+                if ((rc = enqueue(g)) != LPX_OK) return rc;
+            }
+        }
+        for (int g = 0; g < 2; g++)
+            if (sets[g].done) cudaEventDestroy(sets[g].done);
+        if (getenv("LPX_BNB_TRACE"))
+            fprintf(stderr, "[bnb trace] pipelined: %.3f s waiting for the GPU, %.3f s staging + enqueueing; shared-memory "
+                            "kernel %ld launches / %ld nodes / %ld pivots, cluster kernel %ld / %ld / %ld\n",
+                    tr_time[0], tr_time[1], tr_launch[0], tr_nodes[0], tr_piv[0], tr_launch[1], tr_nodes[1], tr_piv[1]);
+        return LPX_OK;
+    }
+
     int run() {
         Runtime& r = rt();
         // base problems to the device once
@@ -493,6 +708,7 @@ struct Driver {
             inst[k].stack.push_back(std::move(root));
         }
         const bool want_history = (flags & LPX_BNB_WANT_HISTORY) && on_node;
+        if (!on_node && count >= 32) return run_pipelined();
         while (true) {
             std::vector<Node*> todo;
             for (Instance& I : inst)
@@ -594,8 +810,9 @@ int lpx_bnb_simplex_batched(int count, int m, int n, int sense, const double* A,
     rc = d.run();
     if (rc != LPX_OK) return rc;
     g_last_stats[0] = 0;
-    g_last_stats[1] = d.tr_time[0] + d.tr_time[1];
     g_last_stats[2] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_run).count();
+    // pipelined batches keep the GPU busy for the whole search: its seconds are the call's
+    g_last_stats[1] = (!on_node && count >= 32) ? g_last_stats[2] : d.tr_time[0] + d.tr_time[1];
     g_last_stats[3] = (double)(d.tr_launch[0] + d.tr_launch[1]);
     for (int k = 0; k < count; k++) g_last_stats[0] += d.inst[k].lp_flops;
     for (int k = 0; k < count; k++) {

@@ -233,6 +233,56 @@ __device__ __forceinline__ int warp_margin_scan_cert(int count, double margin, G
     return warp_margin_scan(count, margin, get);
 }
 
+// The same certified scan over ratios staged in shared memory (NaN = not eligible), with the candidates
+// of a lane (rows lane, lane + 32, ..) held in K registers: the loops of warp_margin_scan_cert become
+// straight-line code with K independent chains instead of K dependent round trips to shared memory —
+// on a lone control warp, where every dependent instruction costs its full latency, that is the
+// difference between ~1500 and a few hundred cycles per pivot.  count <= 32 K.
+template <int K>
+__device__ __forceinline__ int warp_margin_scan_regs(int count, double margin, const double* ratio) {
+    const int lane = threadIdx.x & 31;
+    double r[K];
+    unsigned long long k[K];
+#pragma unroll
+    for (int s = 0; s < K; s++) {
+        const int i = lane + 32 * s;
+        r[s] = i < count ? ratio[i] : __longlong_as_double(0x7ff8000000000000LL);
+    }
+    unsigned long long kl = ~0ULL;
+#pragma unroll
+    for (int s = 0; s < K; s++) {
+        k[s] = (r[s] == r[s]) ? dkey(r[s]) : ~0ULL;
+        kl = k[s] < kl ? k[s] : kl;
+    }
+    const unsigned long long KK = warp_min_u64(kl);
+    if (KK == ~0ULL) return -1;
+    const double vmin = dkey_inv(KK);
+    int il = INT_MAX, close = 0;
+#pragma unroll
+    for (int s = K - 1; s >= 0; s--) {
+        if (k[s] == KK) il = lane + 32 * s;
+        if ((r[s] == r[s]) && !(vmin < __dsub_rn(r[s], margin))) close++;
+    }
+    const int imin = __reduce_min_sync(0xffffffffu, il);
+    const int nclose = __reduce_add_sync(0xffffffffu, close);
+    if (nclose == 1 && vmin < __longlong_as_double(0x7ff0000000000000LL)) return imin;
+    return warp_margin_scan(count, margin, [&](int i, double& rr) {
+        rr = ratio[i];
+        return rr == rr;
+    });
+}
+// Dispatch on the number of candidates (a B&B node of a 60 x 120 problem has up to 186 rows).
+__device__ __forceinline__ int warp_margin_scan_staged(int count, double margin, const double* ratio) {
+    if (count <= 64) return warp_margin_scan_regs<2>(count, margin, ratio);
+    if (count <= 128) return warp_margin_scan_regs<4>(count, margin, ratio);
+    if (count <= 192) return warp_margin_scan_regs<6>(count, margin, ratio);
+    if (count <= 256) return warp_margin_scan_regs<8>(count, margin, ratio);
+    return warp_margin_scan_cert(count, margin, [&](int i, double& rr) {
+        rr = ratio[i];
+        return rr == rr;
+    });
+}
+
 __device__ __forceinline__ double neg_if(double v, bool flip) {
     // "v *= -1" of the reference (PrimalSimplex.cs:170-171, DualSimplex.cs:135,144-152)
     return flip ? __dmul_rn(v, -1.0) : v;

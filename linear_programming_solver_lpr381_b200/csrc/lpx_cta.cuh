@@ -595,10 +595,7 @@ __global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) 
                 cta_stage_ratios<THREADS>(T, ld, m, e, rhs, prow);
                 CTA_TICK(0)
                 if (warp == 0) {
-                    const int lv = warp_margin_scan_cert(m, margin, [&](int i, double& r) {
-                        r = prow[i];
-                        return r == r;
-                    });
+                    const int lv = warp_margin_scan_staged(m, margin, prow);
                     if (lane == 0) ctl[2] = lv;
                 }
                 __syncthreads();

@@ -259,10 +259,7 @@ __global__ void __launch_bounds__(THREADS) cta_cluster_simplex_kernel(const CtaB
                 }
                 cluster.sync();
                 if (warp == 0) {
-                    const int lv = warp_margin_scan_cert(m, margin, [&](int i, double& r) {
-                        r = ratio[i];
-                        return r == r;
-                    });
+                    const int lv = warp_margin_scan_staged(m, margin, ratio);
                     if (lane == 0) ctl[2] = lv;
                 }
                 __syncthreads();
