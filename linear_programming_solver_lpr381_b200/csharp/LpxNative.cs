@@ -32,6 +32,33 @@ namespace Linear_Programming_Solver.Models
     [UnmanagedFunctionPointer(CallingConvention.Cdecl)]
     internal delegate void LpxBnbNodeFn(ref LpxBnbNode node, IntPtr user);
 
+    // lpx_knap_eval (include/lpx.h): one ComputeRelaxation of a child, or of the popped node itself.
+    // Natural C layout: the two doubles after three ints force 4 bytes of padding, likewise before `frac`.
+    [StructLayout(LayoutKind.Sequential)]
+    internal struct LpxKnapEval
+    {
+        public int pop_index, child, var;
+        public double bound, weight;
+        public int frac_rank;
+        public double frac;
+        public int break_rank, decision;
+        public IntPtr assigned;      // n signed bytes: -1 undecided, 0, 1
+    }
+
+    // lpx_knap_pop: one node taken from the heap (the embedded relax is an LpxKnapEval by value)
+    [StructLayout(LayoutKind.Sequential)]
+    internal struct LpxKnapPop
+    {
+        public int pop_index, label_len;
+        public IntPtr label;         // label_len ints, e.g. {1,2,1} = "1.2.1"; root = {0}
+        public LpxKnapEval relax;
+        public int closed;           // 0 expanded; 1 BEST CANDIDATE; 2 CANDIDATE; 3 INFEASIBLE
+    }
+
+    // left / right are null (IntPtr.Zero) for a closed pop
+    [UnmanagedFunctionPointer(CallingConvention.Cdecl)]
+    internal delegate void LpxKnapPopFn(ref LpxKnapPop pop, IntPtr left, IntPtr right, IntPtr user);
+
     internal static class LpxNative
     {
         const string Lib = "lpx";   // liblpx.so on Linux
@@ -73,7 +100,7 @@ namespace Linear_Programming_Solver.Models
         [DllImport(Lib)]
         public static extern int lpx_bnb_knapsack(int n, double[] profit, double[] weight, double capacity,
             ref LpxOptions opt, out int found, out double best_value, int[] best_x, out long n_evals, out long n_pops,
-            int[] rank_order, IntPtr on_pop, IntPtr user);
+            int[] rank_order, LpxKnapPopFn on_pop, IntPtr user);
 
         public static string LastError() => Marshal.PtrToStringUTF8(lpx_last_error()) ?? "";
         public static string StatusMessage(int s) => Marshal.PtrToStringUTF8(lpx_status_message(s)) ?? "";

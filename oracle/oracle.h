@@ -60,6 +60,13 @@ int orc_bnb_simplex(int m, int n, int sense, const double* A, const int* rel, co
                     int* node_depth);
 
 /* BranchAndBoundKnapsack.Solve.  Eval arrays: one entry per ComputeRelaxation of root/children. */
+/* Mode B, the "pooled tree" — NOT the reference's tree (oracle/orc_pooled.cpp): both children honoured, warm
+ * started from the parent's tableau, best-bound rounds of `batch` nodes.  Per evaluated node, in commit order:
+ * id, outcome (BNB_* as above), dual pivots, z. */
+int orc_bnb_pooled(int m, int n, int sense, const double* A, const int* rel, const double* b, const double* c, int batch,
+                   int* found, double* best_z, double* best_x, long* n_nodes, long* total_pivots, long* rounds,
+                   long* skipped, long node_cap, int* node_id, int* node_outcome, int* node_pivots, double* node_z);
+
 int orc_knapsack(int n, const double* profit, const double* weight, double capacity, int* found, double* best,
                  int* best_x, long* n_evals, long* n_pops, long eval_cap, int* ev_parent, int* ev_child,
                  int* ev_var, double* ev_bound, double* ev_weight, int* ev_frac, int* ev_decision);

@@ -251,6 +251,34 @@ int orc_bnb_simplex(int m, int n, int sense, const double* A, const int* rel, co
     return 0;
 }
 
+int orc_bnb_pooled(int m, int n, int sense, const double* A, const int* rel, const double* b, const double* c, int batch,
+                   int* found, double* best_z, double* best_x, long* n_nodes, long* total_pivots, long* rounds,
+                   long* skipped, long node_cap, int* node_id, int* node_outcome, int* node_pivots, double* node_z) {
+    Problem p = make_problem(m, n, sense, A, rel, b, c);
+    PooledTrace t;
+    try {
+        bnb_pooled(p, batch, 1L << 22, &t);
+    } catch (const SolveError& e) {
+        t_err = e.what();
+        return e.code;
+    }
+    *found = t.found ? 1 : 0;
+    *best_z = t.best_z;
+    if (t.found && best_x)
+        for (int j = 0; j < n; j++) best_x[j] = t.best_x[j];
+    *n_nodes = (long)t.node_id.size();
+    if (total_pivots) *total_pivots = t.pivots;
+    if (rounds) *rounds = t.rounds;
+    if (skipped) *skipped = t.skipped;
+    for (long k = 0; k < *n_nodes && k < node_cap; k++) {
+        if (node_id) node_id[k] = t.node_id[k];
+        if (node_outcome) node_outcome[k] = t.node_outcome[k];
+        if (node_pivots) node_pivots[k] = t.node_pivots[k];
+        if (node_z) node_z[k] = t.node_z[k];
+    }
+    return 0;
+}
+
 int orc_knapsack(int n, const double* profit, const double* weight, double capacity, int* found, double* best,
                  int* best_x, long* n_evals, long* n_pops, long eval_cap, int* ev_parent, int* ev_child,
                  int* ev_var, double* ev_bound, double* ev_weight, int* ev_frac, int* ev_decision) {

@@ -219,6 +219,29 @@ def bnb_simplex(A, b, c, rel=None, sense=0, node_cap=4096):
                 depth=dp[:k])
 
 
+def bnb_pooled(A, b, c, rel=None, sense=0, batch=64, node_cap=1 << 20):
+    """Mode B, the pooled tree (NOT the reference's tree; see oracle/orc_pooled.cpp)."""
+    A, rel, b, c, m, n = _prep(A, rel, b, c)
+    found = C.c_int()
+    best_z = C.c_double()
+    nn, tp, rounds, skipped = C.c_long(), C.c_long(), C.c_long(), C.c_long()
+    best_x = np.zeros(n)
+    nid = np.zeros(node_cap, dtype=np.int32)
+    oc = np.zeros(node_cap, dtype=np.int32)
+    pv = np.zeros(node_cap, dtype=np.int32)
+    nz = np.zeros(node_cap)
+    L = lib()
+    L.orc_bnb_pooled.argtypes = [C.c_int, C.c_int, C.c_int, c_dp, c_ip, c_dp, c_dp, C.c_int, c_ip, c_dp, c_dp, c_lp, c_lp,
+                                 c_lp, c_lp, C.c_long, c_ip, c_ip, c_ip, c_dp]
+    rc = L.orc_bnb_pooled(m, n, sense, _d(A), _i(rel), _d(b), _d(c), batch, C.byref(found), C.byref(best_z), _d(best_x),
+                          C.byref(nn), C.byref(tp), C.byref(rounds), C.byref(skipped), node_cap, _i(nid), _i(oc), _i(pv),
+                          _d(nz))
+    k = min(nn.value, node_cap)
+    return dict(rc=rc, found=bool(found.value), best_z=best_z.value, best_x=best_x, n_nodes=nn.value,
+                total_pivots=tp.value, rounds=rounds.value, skipped=skipped.value, node_id=nid[:k], outcome=oc[:k],
+                pivots=pv[:k], z=nz[:k])
+
+
 def knapsack(profit, weight, capacity, eval_cap=1 << 22):
     p = np.ascontiguousarray(profit, dtype=np.float64)
     w = np.ascontiguousarray(weight, dtype=np.float64)

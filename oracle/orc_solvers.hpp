@@ -50,6 +50,18 @@ struct BnbTrace {
 // R/Models/Branch&Bound.cs:30-123
 Outcome branch_and_bound(const Problem& p, const Sink& sink, BnbTrace* trace, bool format_every_iteration = true);
 
+// Mode B, the "pooled tree" (NOT the reference's tree: see orc_pooled.cpp).  One entry per evaluated node,
+// in commit order (node 0 = root).
+struct PooledTrace {
+    std::vector<int> node_id, node_status, node_pivots, node_outcome;
+    std::vector<double> node_z;
+    bool found = false;
+    double best_z = 0;
+    std::vector<double> best_x;
+    long pivots = 0, rounds = 0, skipped = 0;
+};
+int bnb_pooled(const Problem& p, int batch, long max_nodes, PooledTrace* t);
+
 struct KnapEval {           // one ComputeRelaxation call for the root or a child
     int parent_pop = -1;    // index of the expanding pop (-1 root)
     int child = 0;          // 0 left (x=0), 1 right (x=1)
