@@ -752,8 +752,11 @@ static lpx_session* session_create(int m, int n, int sense, const double* dA, co
     // stream_protocol 0: pipelined when the cluster look-ahead is available and the block size allows it
     // (<= 8 pivots per block); 4 forces the non-pipelined blocked protocol.
     const bool want_pipe = s->opt.stream_protocol == 0 && s->la_cluster && P.kblock > 0 && P.kblock <= LPX_PIPE_K;
-    P.Fbuf = (double*)sess_alloc(s, (size_t)LPX_BLOCK_KMAX * P.colstride * 8);
-    P.Pbuf = (double*)sess_alloc(s, (size_t)LPX_BLOCK_KMAX * P.ld * 8);
+    // factor columns and pivot rows of the blocks in flight, in ONE allocation: the look-ahead re-reads all
+    // pending entries for every pivot it decides, so they are pinned in L2 (access policy window below)
+    const size_t fbytes = (size_t)LPX_BLOCK_KMAX * P.colstride * 8, pbytes = (size_t)LPX_BLOCK_KMAX * P.ld * 8;
+    P.Fbuf = (double*)sess_alloc(s, fbytes + pbytes);
+    P.Pbuf = P.Fbuf ? P.Fbuf + (size_t)LPX_BLOCK_KMAX * P.colstride : nullptr;
     P.Lbuf = (int*)sess_alloc(s, (size_t)LPX_BLOCK_KMAX * 4);
     P.dbg = (unsigned long long*)sess_alloc(s, 16 * 8);
     P.T1 = nullptr;
@@ -771,6 +774,22 @@ static lpx_session* session_create(int m, int n, int sense, const double* dA, co
             ok = cudaEventCreateWithFlags(&s->evL[k], cudaEventDisableTiming) == cudaSuccess &&
                  cudaEventCreateWithFlags(&s->evP[k], cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&s->evStart, cudaEventDisableTiming) == cudaSuccess;
+        if (ok && !getenv("LPX_NO_L2_PIN")) {
+            // The pass streams 800 MB through L2 per block and would evict the 2 MB of pending factor columns /
+            // pivot rows the concurrent look-ahead needs again for each of its 8 pivots (16 dependent round
+            // trips per block, each queueing behind a saturated HBM).  Keep them resident: a persisting-L2
+            // carve-out and an access-policy window on both streams.  Best effort: failures are ignored.
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)8 << 20);
+            cudaStreamAttrValue av;
+            std::memset(&av, 0, sizeof av);
+            av.accessPolicyWindow.base_ptr = P.Fbuf;
+            av.accessPolicyWindow.num_bytes = fbytes + pbytes;
+            av.accessPolicyWindow.hitRatio = 1.0f;
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaStreamSetAttribute(s->streamL, cudaStreamAttributeAccessPolicyWindow, &av);
+            cudaStreamSetAttribute(s->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+        }
         cudaGetLastError();
         s->pipe = ok;
         if (!ok) P.zbuf = nullptr;  // fall back to the non-pipelined blocked protocol
