@@ -34,6 +34,7 @@ C3 = dict(m=4096, n=8192)
 BNB_INSTANCES = 512             # C4 instances per GPU in the bnb_simplex section ("e.g. 512")
 KNAP_INSTANCES = 592            # C5 instances per GPU in the bnb_knapsack section (4 per SM: one warp each)
 KNAP_INSTANCES_FRACTIONAL = 148
+POOLED = dict(seed=12, batch=4096)  # Mode B: one hard 60 x 120 instance (2.2e5 nodes), rounds of 4096 open nodes
 
 
 def load_peaks():
@@ -228,6 +229,17 @@ def run_ours(args):
             os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     F.check(F.lib().lpx_init(local_rank))
+    if world > 1:
+        # the engine's own communicator (one tree over all ranks in the bnb_simplex_pooled section): rank 0
+        # creates the id, torch.distributed ships the 128 bytes
+        import ctypes as C
+        uid = (C.c_byte * 128)()
+        if rank == 0:
+            F.check(F.lib().lpx_comm_unique_id(uid))
+        obj = [bytes(uid)]
+        dist.broadcast_object_list(obj, src=0)
+        uid = (C.c_byte * 128).from_buffer_copy(obj[0])
+        F.check(F.lib().lpx_comm_init(world, rank, uid))
     hbm_peak, peak_kind = load_peaks()
     stream = torch.cuda.current_stream()
 
@@ -509,6 +521,35 @@ def run_ours(args):
                                    "note": port_note}
         return out
 
+    def bench_pooled():
+        """Mode B (NOT the reference's tree): ONE 60 x 120 IP, both children honoured, warm starts, the nodes of
+        every round dealt over all ranks (strong scaling: the tree is the same for any N)."""
+        A, b, c = workloads.ip_c4(seed=POOLED["seed"])
+        api.bnb_pooled(A, b, c, batch=POOLED["batch"])  # warm-up: node pools allocated and mapped into the peers
+        barrier()
+        l0 = F.lib().lpx_kernel_launches()
+        t0 = time.perf_counter()
+        r = api.bnb_pooled(A, b, c, batch=POOLED["batch"])
+        dt = max_over_ranks(time.perf_counter() - t0)
+        out = {"metric": "B&B simplex nodes/sec, pooled tree (Mode B: both children, warm-started, one tree over all GPUs)",
+               "value": r["n_nodes"] / dt, "unit": "nodes/s", "scaling": "strong", "nodes": int(r["n_nodes"]),
+               "rounds": int(r["rounds"]), "dual_pivots": int(r["total_pivots"]), "best_z": r["best_z"], "seconds": dt,
+               "gpu_launches": F.lib().lpx_kernel_launches() - l0, "n_gpus": world,
+               "config": {"workload": "C4 one general IP 60 x 120 (seed %d), rounds of %d open nodes" %
+                                      (POOLED["seed"], POOLED["batch"]), **POOLED},
+               "note": "NOT the reference's tree (its '>=' children are never explored, SURVEY F5); checked node for "
+                       "node against oracle/orc_pooled.cpp and against an independent MILP solver (tests/test_gpu_pooled.py); "
+                       "every rank returns the same tree for any number of GPUs (tests/pooled_shard_check.py)"}
+        if with_cpu:
+            orc = oracle()
+            t1 = time.perf_counter()
+            ro = orc.bnb_pooled(A, b, c, batch=POOLED["batch"], max_nodes=40000, node_cap=1)
+            d1 = time.perf_counter() - t1
+            out["cpu_baseline"] = {"value": ro["n_nodes"] / d1, "unit": "nodes/s", "cores": 1, "kind": "port",
+                                   "sample": f"the first {ro['n_nodes']} nodes of the same tree, one thread",
+                                   "note": "oracle/orc_pooled.cpp: the same search on the CPU (there is no upstream code for this tree)"}
+        return out
+
     def cpu_baseline_large():
         """The oracle's arithmetic loop on the same 4096 x 8192 tableau, one thread (a single tableau is one
         thread upstream)."""
@@ -589,6 +630,10 @@ def run_ours(args):
                 extras["bnb_knapsack"] = bench_knap(KNAP_INSTANCES)
             except Exception as e:
                 extras["bnb_knapsack"] = {"error": str(e)}
+            try:
+                extras["bnb_simplex_pooled"] = bench_pooled()
+            except Exception as e:
+                extras["bnb_simplex_pooled"] = {"error": str(e)}
             try:  # non-integer data: every sum in the reference's order (the ordered-summation path)
                 extras["bnb_knapsack_fractional"] = bench_knap(KNAP_INSTANCES_FRACTIONAL, kind="fractional",
                                                                label="ordered-summation path (non-integer data)")
@@ -607,6 +652,7 @@ def run_ours(args):
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
+        F.lib().lpx_comm_destroy()
         dist.destroy_process_group()
 
 

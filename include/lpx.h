@@ -201,6 +201,21 @@ int lpx_bnb_simplex(int m, int n, int sense, const double* A, const int* rel, co
                     long long* n_lp_pivots, int* root_status, lpx_bnb_node_fn on_node, void* user);
 int lpx_bnb_instance(void);  /* inside on_node: which instance of the batch the record belongs to */
 
+/* ---- Mode B: the pooled tree — NOT the reference's tree ------------------------------------------------ */
+/* The reference's BranchAndBound never explores a '>=' child (R/Models/Branch&Bound.cs:157-161 rejects every
+ * Dual Simplex result), so the tree lpx_bnb_simplex reproduces is one floor path.  lpx_bnb_pooled is the tree
+ * the class's doc comment describes (R/Models/Branch&Bound.cs:9-19) with both children honoured: children are
+ * warm-started from the parent's final tableau (bound row + Dual Simplex pivots with the reference's rules),
+ * each round evaluates the `batch` open nodes with the largest bound, and after lpx_comm_init the nodes of a
+ * round are dealt over the ranks (every rank makes the same call and returns the same result; children read
+ * their parent's tableau from the owning GPU's memory over NVLink).  All rows must be '<=' with b >= 0.
+ * Per evaluated node, in commit order (node 0 = root): id, outcome (LPX_BNB_*), dual pivots, z.
+ * Checked against oracle/orc_pooled.cpp node for node and against an independent MILP solver. */
+int lpx_bnb_pooled(int m, int n, int sense, const double* A, const int* rel, const double* b, const double* c,
+                   const lpx_options* opt, int batch, int* found, double* best_z, double* best_x,
+                   long long* n_nodes, long long* n_pivots, long long* n_rounds, long long node_cap, int* node_id,
+                   int* node_outcome, int* node_pivots, double* node_z);
+
 /* ---- Branch & Bound Knapsack: BranchAndBoundKnapsack.Solve, R/Models/BranchAndBoundKnapsack.cs:58-407 */
 typedef struct lpx_knap_eval {   /* one ComputeRelaxation of the root or of a child (:108,209,269) */
     int pop_index;        /* index of the expanded pop this evaluation belongs to, -1 = root */

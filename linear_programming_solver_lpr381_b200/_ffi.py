@@ -30,7 +30,7 @@ EXPORTS = [
     "lpx_bnb_knapsack_batched", "lpx_comm_unique_id", "lpx_comm_init", "lpx_comm_allreduce_max",
     "lpx_comm_allgather", "lpx_comm_destroy", "lpx_comm_world", "lpx_comm_rank", "lpx_kernel_launches",
     "lpx_reset_counters", "lpx_revised_solve", "lpx_revised_history_stride", "lpx_measure_fp64_rate", "lpx_measure_latencies", "lpx_session_profile", "lpx_session_debug_stamps",
-    "lpx_bnb_last_stats",
+    "lpx_bnb_last_stats", "lpx_bnb_pooled",
 ]
 
 

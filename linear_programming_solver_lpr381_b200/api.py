@@ -258,6 +258,34 @@ def bnb_simplex(A, b, c, rel=None, sense=0, trace=False, want_history=False, **k
     return out
 
 
+def bnb_pooled(A, b, c, rel=None, sense=0, batch=64, node_cap=1 << 20):
+    """Mode B, the pooled tree (lpx_bnb_pooled) — NOT the reference's tree.  After lpx_comm_init every rank must
+    make the same call; every rank returns the same result."""
+    A, b, c, rel = _prep(A, b, c, rel)
+    m, n = A.shape
+    opt = F.make_options()
+    found = C.c_int()
+    best_z = C.c_double()
+    best_x = np.zeros(n)
+    nn, npiv, nr = C.c_longlong(), C.c_longlong(), C.c_longlong()
+    nid = np.zeros(node_cap, dtype=np.int32)
+    oc = np.zeros(node_cap, dtype=np.int32)
+    pv = np.zeros(node_cap, dtype=np.int32)
+    nz = np.zeros(node_cap)
+    L = F.lib()
+    L.lpx_bnb_pooled.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = L.lpx_bnb_pooled(m, n, sense, F.ptr(A), F.ptr(rel), F.ptr(b), F.ptr(c), C.cast(C.byref(opt), C.c_void_p), batch,
+                          C.cast(C.byref(found), C.c_void_p), C.cast(C.byref(best_z), C.c_void_p), F.ptr(best_x),
+                          C.cast(C.byref(nn), C.c_void_p), C.cast(C.byref(npiv), C.c_void_p),
+                          C.cast(C.byref(nr), C.c_void_p), node_cap, F.ptr(nid), F.ptr(oc), F.ptr(pv), F.ptr(nz))
+    F.check(rc)
+    k = min(nn.value, node_cap)
+    return dict(found=bool(found.value), best_z=best_z.value, best_x=best_x, n_nodes=nn.value, total_pivots=npiv.value,
+                rounds=nr.value, node_id=nid[:k], outcome=oc[:k], pivots=pv[:k], z=nz[:k])
+
+
 def bnb_knapsack(profit, weight, capacity, trace=False, spec_nodes=0, spec_depth=0, sequential=False,
                  shard_tree=False):
     p = np.ascontiguousarray(profit, dtype=np.float64)

@@ -180,6 +180,7 @@ void lpx_shutdown(void) {
     if (!r.ready) return;
     cudaDeviceSynchronize();
     knapsack_release_cache();
+    pooled_release_cache();
     for (int s = 0; s < WS_COUNT; s++) {
         if (r.dev[s]) cudaFree(r.dev[s]);
         if (r.pin[s]) cudaFreeHost(r.pin[s]);

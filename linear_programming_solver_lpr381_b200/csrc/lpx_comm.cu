@@ -79,6 +79,16 @@ int comm_merge_u64(unsigned long long* dev, size_t words, cudaStream_t s) {
     if (r != ncclSuccess) return nccl_fail(r, "ncclAllReduce(u64 sum)");
     return LPX_OK;
 }
+// All-gather of device buffers on stream s (bytes per rank; recv holds world * bytes).  One rank: a copy.
+int comm_allgather_dev(const void* send, void* recv, size_t bytes, cudaStream_t s) {
+    if (!g_comm) {
+        LPX_CUDA(cudaMemcpyAsync(recv, send, bytes, cudaMemcpyDeviceToDevice, s));
+        return LPX_OK;
+    }
+    ncclResult_t r = g_api.AllGather(send, recv, bytes, ncclChar, g_comm, s);
+    if (r != ncclSuccess) return nccl_fail(r, "ncclAllGather");
+    return LPX_OK;
+}
 int comm_world() { return g_world; }
 int comm_rank() { return g_rank; }
 }  // namespace lpx

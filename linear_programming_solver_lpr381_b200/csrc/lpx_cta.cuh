@@ -15,6 +15,20 @@
 
 namespace lpx {
 
+// Warm start of a pooled-tree B&B node (lpx_pooled.cu, Mode B — not the reference's tree): the node's tableau
+// is its parent's FINAL tableau plus one bound row on variable `var` (x_var <= val for side 0, x_var >= val for
+// side 1, written in the parent's non-basic variables) plus one slack column; Dual Simplex pivots follow.
+// T / basis may point into ANOTHER GPU's node pool (peer memory over NVLink); out_T / out_basis are local.
+struct WarmNode {
+    const double* T;     // parent's compact tableau, rows x (n + rows)
+    const int* basis;    // parent's basis, rows - 1 entries
+    double* out_T;       // this node's final tableau, (rows + 1) x (n + rows + 1), compact
+    int* out_basis;      // rows entries
+    double val;
+    int rows;            // of the PARENT's tableau (constraint rows + objective row)
+    int var, side, pad;
+};
+
 struct CtaBatch {
     // base problems: instance k at A + k*strideA etc.; rel (nullable = all LE) is shared
     const double* A;
@@ -58,6 +72,7 @@ struct CtaBatch {
     // (R/Models/Branch&Bound.cs:268-294), and the branching variable (:198-213), -1 if none
     int* node_flags;
     int* node_branch;
+    const WarmNode* warm;  // nullable: problem p is built from warm[p] instead of (A, b, c) and runs the dual loop
     long long* dbg;  // LPX_CTA_PROF=1: clock64() sums per phase of the LAST problem of the batch (8 slots)
 };
 
@@ -488,9 +503,10 @@ __global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) 
     const int inst = B.node_inst ? B.node_inst[p] : p;
     const int nex = B.node_extra_cnt ? B.node_extra_cnt[p] : 0;
     const int exo = B.node_extra_off ? B.node_extra_off[p] : 0;
-    const int mode = B.node_mode ? B.node_mode[p] : B.mode;
+    const bool warm = B.warm != nullptr;
+    const int mode = warm ? 1 : (B.node_mode ? B.node_mode[p] : B.mode);
     const int n = B.n;
-    const int m = B.m_base + nex;
+    const int m = warm ? B.warm[p].rows : B.m_base + nex;  // a warm node has one constraint row more than its parent
     const int rows = m + 1, width = n + m + 1, ld = SMEM_T ? ((width + 1) & ~1) : width;
     const int rhs = width - 1;
 
@@ -504,23 +520,65 @@ __global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) 
     int* ctl = reinterpret_cast<int*>(smem_raw + cv.ctl);
     double* T;
     if (SMEM_T) T = reinterpret_cast<double*>(smem_raw + cv.T);
+    else if (warm) T = B.warm[p].out_T;  // the node's pool slot doubles as working storage (compact: ld == width)
     else T = B.tableau ? B.tableau + (size_t)p * B.tableau_stride : B.scratch + (size_t)p * B.scratch_stride;
 
     const double* Ai = B.A + (size_t)inst * B.strideA;
     const double* bi = B.b + (size_t)inst * B.strideB;
     const double* ci = B.c + (size_t)inst * B.strideC;
 
-    // ---- row map + the reference's up-front checks (PrimalSimplex.cs:66-77) -------------------
-    cta_row_map<THREADS>(B, bi, nex, exo, mode, rsrc, rsgn, ctl);
-    __syncthreads();
-    int status = ctl[0];
+    int status = LPX_RUNNING;
+    if (!warm) {
+        // ---- row map + the reference's up-front checks (PrimalSimplex.cs:66-77) -------------------
+        cta_row_map<THREADS>(B, bi, nex, exo, mode, rsrc, rsgn, ctl);
+        __syncthreads();
+        status = ctl[0];
+    }
 
     int n_piv = 0, n_silent = 0, n_hist = 0;
     int* plog = B.pivots ? B.pivots + (size_t)p * B.pivots_cap * 2 : nullptr;
     double* hist = B.history ? B.history + (size_t)p * B.history_stride : nullptr;
     const size_t tsize = (size_t)rows * width;
 
-    if (status == LPX_RUNNING) {
+    if (warm) {
+        // ---- parent's final tableau + bound row + slack column (lpx_pooled.cu; oracle/orc_pooled.cpp) -----
+        const WarmNode wn = B.warm[p];
+        const int mp = wn.rows - 1, wp = n + wn.rows, rhs_p = wp - 1;  // parent: constraint rows, width, RHS column
+        if (tid == 0) ctl[5] = -1;
+        __syncthreads();
+        for (int i = tid; i < mp; i += THREADS) {
+            const int bv = wn.basis[i];
+            sbasis[i] = bv;
+            if (bv == wn.var) ctl[5] = i;  // the row in which the branching variable is basic (exactly one)
+        }
+        if (tid == 0) sbasis[mp] = rhs_p;   // the new slack is basic in the new row
+        __syncthreads();
+        const int r = ctl[5];
+        const double* Tr = wn.T + (size_t)r * wp;
+        for (int i = warp; i < rows; i += NW) {
+            double* Ti = T + (size_t)i * ld;
+            // child row i <- parent row (i < mp: same row; i == mp: the bound row, built from parent row r;
+            // i == mp + 1: the objective row)
+            const double* Ts = i < mp ? wn.T + (size_t)i * wp : (i == mp ? Tr : wn.T + (size_t)mp * wp);
+            for (int j = lane; j < width; j += 32) {
+                double v;
+                if (i != mp) {
+                    v = j < rhs_p ? Ts[j] : (j == rhs_p ? 0.0 : Ts[rhs_p]);
+                } else if (j < rhs_p) {
+                    const double unit = j == wn.var ? 1.0 : 0.0;
+                    v = wn.side == 0 ? __dsub_rn(unit, Ts[j]) : __dsub_rn(Ts[j], unit);
+                } else if (j == rhs_p) {
+                    v = 1.0;
+                } else {
+                    v = wn.side == 0 ? __dsub_rn(wn.val, Ts[rhs_p]) : __dsub_rn(Ts[rhs_p], wn.val);
+                }
+                Ti[j] = v;
+            }
+        }
+        if (ld > width)
+            for (int i = tid; i < rows; i += THREADS) T[(size_t)i * ld + width] = 0.0;  // pad column
+        __syncthreads();
+    } else if (status == LPX_RUNNING) {
         // ---- BuildTableau -------------------------------------------------------------------
         for (int i = warp; i < rows; i += NW) {
             double* Ti = T + (size_t)i * ld;
@@ -558,7 +616,8 @@ __global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) 
             for (int i = tid; i < rows; i += THREADS) T[(size_t)i * ld + width] = 0.0;  // pad column
         for (int i = tid; i < m; i += THREADS) sbasis[i] = n + i;
         __syncthreads();
-
+    }
+    if (status == LPX_RUNNING) {
         const double* zrow = T + (size_t)m * ld;
         double* zc = reinterpret_cast<double*>(smem_raw + cv.zc);
         long long pc[4] = {0, 0, 0, 0}, c0 = 0;
@@ -639,7 +698,8 @@ __global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) 
             }
         };
 
-        if (mode == 1) primal_steps(LPX_MARGIN_DUAL, 100, true);  // <= 100 silent pivots, ratio margin 1e-12
+        // <= 100 silent pivots, ratio margin 1e-12 (a warm node starts from an optimal, hence dual feasible, tableau)
+        if (mode == 1 && !warm) primal_steps(LPX_MARGIN_DUAL, 100, true);
 
         if (hist && n_hist < B.history_cap) {
             cta_copy_out<THREADS>(hist + (size_t)n_hist * tsize, T, ld, rows, width);
@@ -715,6 +775,10 @@ __global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) 
         // ---- FinalizeReport's numeric part (PrimalSimplex.cs:132-138) -------------------------
         if (B.basis)
             for (int i = tid; i < m; i += THREADS) B.basis[(size_t)p * B.basis_stride + i] = sbasis[i];
+        if (warm) {  // the final tableau and basis stay in the node pool for the node's own children
+            for (int i = tid; i < m; i += THREADS) B.warm[p].out_basis[i] = sbasis[i];
+            if (SMEM_T) cta_copy_out<THREADS>(B.warm[p].out_T, T, ld, rows, width);
+        }
         if (B.x) {
             double* xo = B.x + (size_t)p * n;
             for (int j = tid; j < n; j += THREADS) xo[j] = 0.0;
@@ -725,7 +789,7 @@ __global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) 
         if (B.z && tid == 0) B.z[p] = T[(size_t)m * ld + rhs];
         if (B.tableau && (SMEM_T || T != B.tableau + (size_t)p * B.tableau_stride))
             cta_copy_out<THREADS>(B.tableau + (size_t)p * B.tableau_stride, T, ld, rows, width);
-        if (B.node_flags && B.x && mode == 0) {  // prow (width > n doubles) is free now
+        if (B.node_flags && B.x && (mode == 0 || warm)) {  // prow (width > n doubles) is free now
             __syncthreads();
             cta_node_epilogue<THREADS>(B, p, inst, nex, exo, B.x + (size_t)p * n, prow, red);
         }

@@ -15,6 +15,7 @@ enum Slot {
     WS_A = 0, WS_B, WS_C, WS_REL, WS_STATUS, WS_NPIV, WS_SILENT, WS_PIVOTS, WS_BASIS, WS_X, WS_Z, WS_TABLEAU,
     WS_HISTORY, WS_NHIST, WS_SCRATCH, WS_TOTAL, WS_NODE_INST, WS_NODE_OFF, WS_NODE_CNT, WS_NODE_MODE, WS_EX_VAR,
     WS_EX_REL, WS_EX_RHS, WS_KN_ITEMS, WS_KN_ASSIGN, WS_KN_OUT, WS_KN_AUX, WS_KN_EXACT, WS_MISC0, WS_MISC1, WS_MISC2,
+    WS_PL_IN, WS_PL_OUT, WS_PL_ALL,  // pooled-tree B&B: node descriptors, own results, everybody's results
     WS_BB_IN0, WS_BB_OUT0, WS_BB_SCR0, WS_BB_IN1, WS_BB_OUT1, WS_BB_SCR1,  // pipelined B&B: two evaluation sets
     WS_COUNT
 };
@@ -38,7 +39,9 @@ Runtime& rt();
 void* ws_dev(Slot s, size_t bytes);
 void* ws_pin(Slot s, size_t bytes);
 void knapsack_release_cache();  // lpx_knapsack.cu
+void pooled_release_cache();    // lpx_pooled.cu
 int comm_merge_u64(unsigned long long* dev, size_t words, cudaStream_t s);  // lpx_comm.cu
+int comm_allgather_dev(const void* send, void* recv, size_t bytes, cudaStream_t s);  // lpx_comm.cu
 int comm_world();
 int comm_rank();
 

@@ -64,7 +64,7 @@ int orc_bnb_simplex(int m, int n, int sense, const double* A, const int* rel, co
  * started from the parent's tableau, best-bound rounds of `batch` nodes.  Per evaluated node, in commit order:
  * id, outcome (BNB_* as above), dual pivots, z. */
 int orc_bnb_pooled(int m, int n, int sense, const double* A, const int* rel, const double* b, const double* c, int batch,
-                   int* found, double* best_z, double* best_x, long* n_nodes, long* total_pivots, long* rounds,
+                   long max_nodes /* stop after the round that passes this many nodes; 0 = none */, int* found, double* best_z, double* best_x, long* n_nodes, long* total_pivots, long* rounds,
                    long* skipped, long node_cap, int* node_id, int* node_outcome, int* node_pivots, double* node_z);
 
 int orc_knapsack(int n, const double* profit, const double* weight, double capacity, int* found, double* best,

@@ -252,12 +252,12 @@ int orc_bnb_simplex(int m, int n, int sense, const double* A, const int* rel, co
 }
 
 int orc_bnb_pooled(int m, int n, int sense, const double* A, const int* rel, const double* b, const double* c, int batch,
-                   int* found, double* best_z, double* best_x, long* n_nodes, long* total_pivots, long* rounds,
+                   long max_nodes, int* found, double* best_z, double* best_x, long* n_nodes, long* total_pivots, long* rounds,
                    long* skipped, long node_cap, int* node_id, int* node_outcome, int* node_pivots, double* node_z) {
     Problem p = make_problem(m, n, sense, A, rel, b, c);
     PooledTrace t;
     try {
-        bnb_pooled(p, batch, 1L << 22, &t);
+        bnb_pooled(p, batch, max_nodes > 0 ? max_nodes : (1L << 30), &t);
     } catch (const SolveError& e) {
         t_err = e.what();
         return e.code;

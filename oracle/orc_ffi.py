@@ -219,7 +219,7 @@ def bnb_simplex(A, b, c, rel=None, sense=0, node_cap=4096):
                 depth=dp[:k])
 
 
-def bnb_pooled(A, b, c, rel=None, sense=0, batch=64, node_cap=1 << 20):
+def bnb_pooled(A, b, c, rel=None, sense=0, batch=64, node_cap=1 << 20, max_nodes=0):
     """Mode B, the pooled tree (NOT the reference's tree; see oracle/orc_pooled.cpp)."""
     A, rel, b, c, m, n = _prep(A, rel, b, c)
     found = C.c_int()
@@ -231,9 +231,9 @@ def bnb_pooled(A, b, c, rel=None, sense=0, batch=64, node_cap=1 << 20):
     pv = np.zeros(node_cap, dtype=np.int32)
     nz = np.zeros(node_cap)
     L = lib()
-    L.orc_bnb_pooled.argtypes = [C.c_int, C.c_int, C.c_int, c_dp, c_ip, c_dp, c_dp, C.c_int, c_ip, c_dp, c_dp, c_lp, c_lp,
+    L.orc_bnb_pooled.argtypes = [C.c_int, C.c_int, C.c_int, c_dp, c_ip, c_dp, c_dp, C.c_int, C.c_long, c_ip, c_dp, c_dp, c_lp, c_lp,
                                  c_lp, c_lp, C.c_long, c_ip, c_ip, c_ip, c_dp]
-    rc = L.orc_bnb_pooled(m, n, sense, _d(A), _i(rel), _d(b), _d(c), batch, C.byref(found), C.byref(best_z), _d(best_x),
+    rc = L.orc_bnb_pooled(m, n, sense, _d(A), _i(rel), _d(b), _d(c), batch, max_nodes, C.byref(found), C.byref(best_z), _d(best_x),
                           C.byref(nn), C.byref(tp), C.byref(rounds), C.byref(skipped), node_cap, _i(nid), _i(oc), _i(pv),
                           _d(nz))
     k = min(nn.value, node_cap)
