@@ -156,7 +156,7 @@ def dist_env():
 def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
-        return
+        return None
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import orc_ffi
     from linear_programming_solver_lpr381_b200 import workloads
@@ -206,7 +206,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "pivots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    return line
 
 
 # ------------------------------------------------------------------------------------------------
@@ -649,11 +649,28 @@ def run_ours(args):
                 "roofline": Bm["roofline"], "e2e": Bm["e2e"], "gpu_launches": Bm["launches"], "clocks": Bm["clocks"],
                 "cpu_baseline": cpu_baseline(host) if (rank == 0 and world == 1) else None}
         line.update(extras)
-    if rank == 0:
-        print(json.dumps(line))
     if world > 1:
         F.lib().lpx_comm_destroy()
         dist.destroy_process_group()
+    return line if rank == 0 else None
+
+
+class OneJsonLine:
+    """The driver parses stdout as ONE JSON line.  Libraries below us write there too (NCCL prints its version
+    line to stdout when a communicator is created under NCCL_DEBUG=VERSION/WARN), so file descriptor 1 points at
+    stderr while the benchmark runs and is restored only for the final print."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
 
 
 def main():
@@ -666,10 +683,10 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the configs 3-5 sections")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    with OneJsonLine() as guard:
+        line = run_reference(args) if args.impl == "reference" else run_ours(args)
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

@@ -585,7 +585,13 @@ struct KnDriver {
                 int ch_pending = -1, ch_level = it.level;
                 if (ch < 0) {
                     const int slot = alloc_slot();
-                    if (slot < 0) return;  // pool exhausted: plan what we have
+                    if (slot < 0) {
+                        // Pool exhausted: plan what we have — except in the sharded-tree mode, where every rank must
+                        // build the SAME plan (the merge is an all-reduce of total * 5 words): there it is a hard
+                        // error, raised identically on whichever ranks see it, never a silently shorter plan.
+                        if (shard_world > 1) plan_failed = true;
+                        return;
+                    }
                     ch = alloc_rec();
                     EvalRec& c = recs[ch];
                     c.slot = slot;
@@ -618,6 +624,7 @@ struct KnDriver {
     }
 
     int coop_ctas = 1;
+    bool plan_failed = false;
     int shard_world = 1, shard_rank = 0;  // > 1: one tree over all ranks of the communicator
     double tr_stage = 0, tr_launch = 0, tr_sync = 0, tr_unpack = 0;  // LPX_KNAP_TRACE: inside the device rounds
     long tr_evals = 0;
@@ -1014,6 +1021,16 @@ struct KnDriver {
                 break;
             }
             const auto t1 = now();
+            if (shard_world > 1) {
+                // agree on the plan before any collective is sized by it
+                double bad = plan_failed ? 1.0 : 0.0;
+                int rcb = lpx_comm_allreduce_max(&bad, 1);
+                if (rcb != LPX_OK) return rcb;
+                if (bad != 0.0) {
+                    set_error("knapsack (sharded tree): node pool exhausted on a rank; the plans would differ");
+                    return LPX_E_CAPACITY;
+                }
+            }
             int rc = run_plan(pl);
             if (rc != LPX_OK) return rc;
             const auto t2 = now();
