@@ -48,7 +48,7 @@ def load_peaks():
 def measured_traffic(kernel):
     """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/), or None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             return json.load(f)[kernel]["dram_bytes_per_launch"]
     except Exception:
         return None
