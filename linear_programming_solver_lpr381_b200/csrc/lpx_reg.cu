@@ -56,7 +56,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, OCC) reg_simplex_kernel(const R
     constexpr int C = CR + CS;
     constexpr int ROWS = NW * R;   // padded constraint rows (>= m)
     constexpr int COLS = 32 * C;   // padded non-RHS columns (>= n + m)
-    __shared__ double s_t[(CS ? CS : 1) * (ROWS + 1) * 32];  // [slot][row][lane]; row ROWS = objective row
+    extern __shared__ __align__(16) double s_t[];  // (CS ? CS : 1) * (ROWS + 1) * 32: [slot][row][lane]; row ROWS = objective row
     constexpr int NT = (NW + 1) * 32;
     static_assert(ROWS >= 64 && ROWS <= 96, "the control warp holds the RHS of rows lane and lane+32");
     __shared__ double s_f[ROWS];     // entering column = update factors
@@ -86,9 +86,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, OCC) reg_simplex_kernel(const R
     } while (0)
     // control-warp state lives in the row slots it does not use (t[1..][*]), so that it costs the
     // row warps no registers: RHS of rows lane / lane+32, objective value, and per-pivot scratch
-    static_assert(R >= 3 && CR >= 4, "control-warp aliases need t[1][0..3] and t[2][0..2]");
-    double &rhs0 = t[1][0], &rhs1 = t[1][1], &zrhs = t[1][2], &a0 = t[1][3], &a1 = t[2][0], &fz = t[2][1],
-           &prhs = t[2][2];
+    static_assert((R - 1) * CR >= 7, "control-warp aliases need seven slots in t[1..][*]");
+#define CTL_ALIAS(k) t[1 + (k) / CR][(k) % CR]
+    double &rhs0 = CTL_ALIAS(0), &rhs1 = CTL_ALIAS(1), &zrhs = CTL_ALIAS(2), &a0 = CTL_ALIAS(3), &a1 = CTL_ALIAS(4),
+           &fz = CTL_ALIAS(5), &prhs = CTL_ALIAS(6);
+#undef CTL_ALIAS
 #pragma unroll
     for (int r = 0; r < R; r++) {
         const int i = w * R + r;
@@ -339,6 +341,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, OCC) reg_simplex_kernel(const R
     }
 }
 
+// dynamic shared memory of an instance: the CS column slots kept out of the register file
+static size_t reg_smem(int nw, int r, int cs) { return (size_t)(cs ? cs : 1) * (nw * r + 1) * 32 * 8; }
+
 // Shapes served by the <13, 5, 6> instance: m + 1 <= 65 rows, n + m <= 192 columns, all '<='.
 bool reg_kernel_supports(int m, int n, int m_expanded, bool has_rel) {
     if (has_rel || m_expanded != m) return false;
@@ -380,8 +385,8 @@ int reg_launch_batched(int count, int m, int n, int sense, const double* A, cons
         LPX_CUDA(cudaMalloc(&d, nslots * sizeof(long long)));
         LPX_CUDA(cudaMemsetAsync(d, 0, nslots * sizeof(long long), stream));
         B.dbg = d;
-        if (opt.reg_variant == 1) reg_simplex_kernel<13, 5, 6, 0, 1, true><<<count, 14 * 32, 0, stream>>>(B);
-        else reg_simplex_kernel<13, 5, 4, 2, 2, true><<<count, 14 * 32, 0, stream>>>(B);
+        if (opt.reg_variant == 1) reg_simplex_kernel<13, 5, 6, 0, 1, true><<<count, 14 * 32, reg_smem(13, 5, 0), stream>>>(B);
+        else reg_simplex_kernel<13, 5, 4, 2, 2, true><<<count, 14 * 32, reg_smem(13, 5, 2), stream>>>(B);
         long long h[nslots];
         LPX_CUDA(cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, stream));
         LPX_CUDA(cudaStreamSynchronize(stream));
@@ -399,8 +404,18 @@ int reg_launch_batched(int count, int m, int n, int sense, const double* A, cons
         count_launch();
         return LPX_OK;
     }
-    if (opt.reg_variant == 1) reg_simplex_kernel<13, 5, 6, 0, 1><<<count, 14 * 32, 0, stream>>>(B);
-    else reg_simplex_kernel<13, 5, 4, 2, 2><<<count, 14 * 32, 0, stream>>>(B);
+    if (opt.reg_variant == 1) {
+        reg_simplex_kernel<13, 5, 6, 0, 1><<<count, 14 * 32, reg_smem(13, 5, 0), stream>>>(B);
+    } else if (opt.reg_variant == 3) {
+        // three CTAs per SM: 11 row warps x 6 rows, two of the six column slots in registers (56 registers), four
+        // in shared memory (67 KB per CTA)
+        static const bool ok3 = cudaFuncSetAttribute(reg_simplex_kernel<11, 6, 2, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)reg_smem(11, 6, 4)) == cudaSuccess;
+        if (!ok3) return cuda_fail(cudaGetLastError(), "cudaFuncSetAttribute(reg_simplex_kernel<11,6,2,4,3>)", __FILE__, __LINE__);
+        reg_simplex_kernel<11, 6, 2, 4, 3><<<count, 12 * 32, reg_smem(11, 6, 4), stream>>>(B);
+    } else {
+        reg_simplex_kernel<13, 5, 4, 2, 2><<<count, 14 * 32, reg_smem(13, 5, 2), stream>>>(B);
+    }
     LPX_CUDA(cudaGetLastError());
     count_launch();
     return LPX_OK;

@@ -737,6 +737,11 @@ static lpx_session* session_create(int m, int n, int sense, const double* dA, co
     if (blocked_wanted) {
         const int kb = s->opt.stream_block > 0 ? std::min(s->opt.stream_block, LPX_BLOCK_KMAX) : 8;
         if (s->opt.stream_protocol != 3 && lookahead_cluster_smem(P) + 24 * 1024 <= (size_t)max_smem_optin() &&
+            (LPX_LA_CLUSTER <= 8 ||
+             (cudaFuncSetAttribute(stream_lookahead_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) ==
+                  cudaSuccess &&
+              cudaFuncSetAttribute(stream_lookahead_pipe_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) ==
+                  cudaSuccess)) &&
             cudaFuncSetAttribute(stream_lookahead_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)lookahead_cluster_smem(P)) == cudaSuccess) {
             P.kblock = kb;
