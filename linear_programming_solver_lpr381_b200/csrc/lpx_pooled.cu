@@ -28,7 +28,10 @@
 // NCCL all-gather of the small result records (status, pivots, flags, branching variable, z, x), from
 // which every rank commits identically: the incumbent is global by construction.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <deque>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
@@ -54,10 +57,14 @@ struct PNode {
     int open_children = 0;
 };
 
+struct OpenRef {  // entry of the open-node queue: 16 bytes, no pointer chasing in the heap's compares
+    double bound;
+    int id;
+};
 struct ByBound {
-    bool operator()(const PNode* a, const PNode* b) const {
-        if (a->bound != b->bound) return a->bound < b->bound;
-        return a->id > b->id;
+    bool operator()(const OpenRef& a, const OpenRef& b) const {
+        if (a.bound != b.bound) return a.bound < b.bound;
+        return a.id > b.id;
     }
 };
 
@@ -212,9 +219,9 @@ extern "C" int lpx_bnb_pooled(int m, int n, int sense, const double* A, const in
         B.scratch_stride = 0;
     };
 
-    std::vector<std::unique_ptr<PNode>> nodes;
+    std::deque<PNode> nodes;  // stable addresses, chunked allocation: no malloc per node
     std::vector<Pool> pools(world);
-    std::priority_queue<PNode*, std::vector<PNode*>, ByBound> open;
+    std::priority_queue<OpenRef, std::vector<OpenRef>, ByBound> open;
     double best = -std::numeric_limits<double>::infinity();
     bool have_best = false;
     std::vector<double> bx(n, 0.0);
@@ -222,7 +229,7 @@ extern "C" int lpx_bnb_pooled(int m, int n, int sense, const double* A, const in
 
     auto release_parent = [&](int id) {
         if (id < 0) return;
-        PNode& p = *nodes[id];
+        PNode& p = nodes[id];
         if (--p.open_children == 0 && p.slot >= 0 && p.parent >= 0) {  // the root keeps slot 0 of every pool
             pools[p.owner].release(p.cls, p.slot);
             p.slot = -1;
@@ -242,19 +249,20 @@ extern "C" int lpx_bnb_pooled(int m, int n, int sense, const double* A, const in
         } else if (branch < 0) outcome = LPX_BNB_NOFRAC;
         else {
             outcome = LPX_BNB_BRANCHED;
-            for (int side = 1; side >= 0; side--) {  // ceil child first
-                std::unique_ptr<PNode> ch(new PNode());
-                ch->id = (int)nodes.size();
-                ch->parent = nd.id;
-                ch->var = branch;
-                ch->side = side;
-                ch->bound_val = (int)(side ? std::ceil(x[branch]) : std::floor(x[branch]));
-                ch->depth = nd.depth + 1;
-                ch->bound = z;
-                open.push(ch.get());
-                nodes.push_back(std::move(ch));
-            }
+            const int nd_id = nd.id, nd_depth = nd.depth;
             nd.open_children = 2;
+            for (int side = 1; side >= 0; side--) {  // ceil child first
+                PNode ch;
+                ch.id = (int)nodes.size();
+                ch.parent = nd_id;
+                ch.var = branch;
+                ch.side = side;
+                ch.bound_val = (int)(side ? std::ceil(x[branch]) : std::floor(x[branch]));
+                ch.depth = nd_depth + 1;
+                ch.bound = z;
+                open.push(OpenRef{z, ch.id});
+                nodes.push_back(ch);  // (a deque never moves existing elements: `nd` stays valid)
+            }
         }
         if (evaluated < node_cap) {
             if (node_id) node_id[evaluated] = nd.id;
@@ -271,7 +279,8 @@ extern "C" int lpx_bnb_pooled(int m, int n, int sense, const double* A, const in
 
     // ---- root: every rank solves it into slot 0 of its own pool (replicated, deterministic) ----------------
     {
-        std::unique_ptr<PNode> root(new PNode());
+        nodes.emplace_back();
+        PNode* root = &nodes[0];
         root->bound = std::numeric_limits<double>::infinity();
         root->rows = m + 1;
         for (int q = 0; q < world; q++) {
@@ -300,25 +309,31 @@ extern "C" int lpx_bnb_pooled(int m, int n, int sense, const double* A, const in
         if (rc != LPX_OK) return rc;
         LPX_CUDA(cudaMemcpyAsync(h_all, d_own, rank_bytes, cudaMemcpyDeviceToHost, s));
         LPX_CUDA(cudaStreamSynchronize(s));
-        nodes.push_back(std::move(root));
         const int st = own_int(h_all, 0)[0];
         if (st == LPX_UNBOUNDED || st < 0) {
             // the relaxation is unbounded or threw: no tree (the caller sees found = 0 and one node)
-            commit(*nodes[0], LPX_INFEASIBLE, own_int(h_all, 1)[0], 0, -1, 0.0, own_x(h_all));
+            commit(nodes[0], LPX_INFEASIBLE, own_int(h_all, 1)[0], 0, -1, 0.0, own_x(h_all));
         } else {
-            commit(*nodes[0], st, own_int(h_all, 1)[0], own_int(h_all, 2)[0], own_int(h_all, 3)[0], own_z(h_all)[0],
+            commit(nodes[0], st, own_int(h_all, 1)[0], own_int(h_all, 2)[0], own_int(h_all, 3)[0], own_z(h_all)[0],
                    own_x(h_all));
         }
         // the root is "owned" by everybody: children anywhere read their local copy
     }
 
     std::vector<PNode*> sel;
+    double tr[3] = {0, 0, 0};  // LPX_POOLED_TRACE=1: seconds selecting + staging | launch .. results on the host | committing
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double>(b - a).count();
+    };
     while (!open.empty()) {
+        const auto t0 = now();
         sel.clear();
         while (!open.empty() && (int)sel.size() < batch) {
-            PNode* nd = open.top();
+            const OpenRef top = open.top();
             open.pop();
-            if (nd->bound <= best + PL_EPS) {  // cannot beat the incumbent any more: no LP
+            PNode* nd = &nodes[top.id];
+            if (top.bound <= best + PL_EPS) {  // cannot beat the incumbent any more: no LP
                 release_parent(nd->parent);
                 continue;
             }
@@ -332,7 +347,7 @@ extern "C" int lpx_bnb_pooled(int m, int n, int sense, const double* A, const in
         bool any_big = false;
         for (int j = 0; j < nsel; j++) {
             PNode* nd = sel[j];
-            const PNode& par = *nodes[nd->parent];
+            const PNode& par = nodes[nd->parent];
             nd->owner = j % world;
             nd->rows = par.rows + 1;
             if (nd->rows > max_rows) {
@@ -360,6 +375,7 @@ extern "C" int lpx_bnb_pooled(int m, int n, int sense, const double* A, const in
             my_max_rows = std::max(my_max_rows, nd->rows);
             any_big = any_big || !cta_fits_smem(nd->rows, n + nd->rows);
         }
+        const auto t1 = now();
         if (mine > 0) {
             LPX_CUDA(cudaMemcpyAsync(d_warm, h_warm, (size_t)mine * sizeof(WarmNode), cudaMemcpyHostToDevice, s));
             CtaBatch B;
@@ -381,6 +397,7 @@ extern "C" int lpx_bnb_pooled(int m, int n, int sense, const double* A, const in
         if ((rc = comm_allgather_dev(d_own, d_all, rank_bytes, s)) != LPX_OK) return rc;
         LPX_CUDA(cudaMemcpyAsync(h_all, d_all, rank_bytes * world, cudaMemcpyDeviceToHost, s));
         LPX_CUDA(cudaStreamSynchronize(s));
+        const auto t2 = now();
         for (int j = 0; j < nsel; j++) {
             PNode* nd = sel[j];
             unsigned char* rb = h_all + (size_t)(j % world) * rank_bytes;
@@ -389,7 +406,13 @@ extern "C" int lpx_bnb_pooled(int m, int n, int sense, const double* A, const in
                    own_x(rb) + (size_t)q * n);
             release_parent(nd->parent);
         }
+        tr[0] += secs(t0, t1);
+        tr[1] += secs(t1, t2);
+        tr[2] += secs(t2, now());
     }
+    if (getenv("LPX_POOLED_TRACE"))
+        fprintf(stderr, "[pooled trace] rank %d of %d: %lld rounds, %lld nodes: select + stage %.3f s, launch .. results on the host "
+                        "%.3f s, commit %.3f s\n", rank, world, rounds, evaluated, tr[0], tr[1], tr[2]);
     if (found) *found = have_best ? 1 : 0;
     if (best_z) *best_z = best;
     if (best_x && have_best)
