@@ -209,7 +209,9 @@ __device__ __forceinline__ KsEval ks_eval_chain(const KsInst& I, int sfw, unsign
     double wn, pn;
     fetch(b, wn, pn);
     ((b & 1) ? I.st_out : I.st_in)[lane] = make_double2(wn, pn);
+    unsigned neg_cur = __ballot_sync(0xffffffffu, wn < 0.0);  // lanes of the block with a negative weight
     fetch(b + 1, wn, pn);
+    unsigned neg_next = __ballot_sync(0xffffffffu, wn < 0.0);
     __syncwarp();
     const bool int_cmp = I.limit >= 0.0;
     const long long lim_bits = __double_as_longlong(I.limit);
@@ -219,7 +221,30 @@ __device__ __forceinline__ KsEval ks_eval_chain(const KsInst& I, int sfw, unsign
         fetch(b + 2, wn, pn);
         double Wc = weight, Pc = profit;
         unsigned fail = 0u;  // bit j: the sum through item j does not fit (zeros never flip it first)
-        if (int_cmp) {
+        // Non-negative weights in the block (the usual case): the partial sums are monotone (fl(a + b) >= a for
+        // b >= 0), so the block's LAST sum decides whether anything in it fails and the chain carries no compare
+        // at all; only the block that holds the break item is run again with the per-item test.
+        const bool monotone = neg_cur == 0u;
+        bool per_item = !monotone;
+        if (monotone) {
+#pragma unroll
+            for (int j0 = 0; j0 < 32; j0 += 8) {
+                double2 v[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) v[j] = cur[j0 + j];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    Wc = __dadd_rn(Wc, v[j].x);
+                    Pc = __dadd_rn(Pc, v[j].y);
+                }
+            }
+            if (!(Wc <= I.limit)) {
+                per_item = true;
+                Wc = weight;
+                Pc = profit;
+            }
+        }
+        if (per_item && int_cmp) {
             // limit >= 0: "!(W <= limit)" is a signed compare of the bit patterns (a negative W fits, +NaN does
             // not), which keeps the FP64 pipe for the two add chains alone
 #pragma unroll
@@ -234,7 +259,7 @@ __device__ __forceinline__ KsEval ks_eval_chain(const KsInst& I, int sfw, unsign
                     if (__double_as_longlong(Wc) > lim_bits) fail |= 1u << (j0 + j);
                 }
             }
-        } else {
+        } else if (per_item) {
 #pragma unroll
             for (int j0 = 0; j0 < 32; j0 += 8) {
                 double2 v[8];
@@ -261,6 +286,8 @@ __device__ __forceinline__ KsEval ks_eval_chain(const KsInst& I, int sfw, unsign
         }
         weight = Wc;
         profit = Pc;
+        neg_cur = neg_next;
+        neg_next = __ballot_sync(0xffffffffu, wn < 0.0);  // block b + 2's operands have long arrived
         __syncwarp();
     }
     return ks_finish(I, w1, p1, weight, profit, n);
@@ -502,52 +529,126 @@ constexpr int KS_MAX_WARPS = 16;  // warps (instances in flight) per CTA, one CT
 __host__ __device__ inline size_t ks_warp_smem(int HS, int MS, int n_staged = 0) {
     return (((size_t)HS * 12 + 15) & ~(size_t)15) + (size_t)MS * 4 + 1024 + (size_t)n_staged * 16;
 }
+// A PAIR of warps per instance (few instances: latency matters) adds the helper warp's chain staging, the job
+// the main warp posts and the result the helper returns.
+struct KsJob {
+    int kind;  // 0: no more instances, 1: evaluate the right child, 2: a new instance (k)
+    int k, sf, kv;
+    double w1, p1, wb, pb;
+};
+constexpr size_t KS_PAIR_EXTRA = 1024 + 64 + 128;
+__host__ __device__ inline size_t ks_unit_smem(int HS, int MS, int n_staged, bool paired) {
+    return ks_warp_smem(HS, MS, n_staged) + (paired ? KS_PAIR_EXTRA : 0);
+}
 
-template <int MAXW>
+// The instance as a warp sees it (pointers into the item tables, the staged masks, its own chain buffers).
+__device__ __forceinline__ KsInst ks_inst(const KsParams& P, int k, const unsigned* sm_mask, double2* st_in, double2* st_out,
+                                          const double* sm_items, int n_staged) {
+    const int n = P.n;
+    KsInst I;
+    I.w_s = n_staged ? sm_items : P.w_s + (size_t)k * n;
+    I.p_s = n_staged ? sm_items + n : P.p_s + (size_t)k * n;
+    I.w_o = P.w_o + (size_t)k * n;
+    I.p_o = P.p_o + (size_t)k * n;
+    I.orig_s = P.orig_s + (size_t)k * n;
+    I.capacity = P.cap[k];
+    I.limit = __dadd_rn(I.capacity, KS_EPS);
+    I.n = n;
+    I.W = P.W;
+    I.exact = P.exact[k];
+    I.one = sm_mask;
+    I.dec = sm_mask + P.W;
+    I.st_in = st_in;
+    I.st_out = st_out;
+    return I;
+}
+
+// Right child (x_k = 1) of the node whose masks are staged: the fixed sums grow by item kv (:266-269).
+__device__ __forceinline__ KsEval ks_right_child(const KsInst& I, int sf, int kv, double w1, double p1, double wb, double pb) {
+    const int sfw = sf >> 5, kw = kv >> 5;
+    const unsigned sfbit = 1u << (sf & 31), kbit = 1u << (kv & 31);
+    double w1r, p1r;
+    if (I.exact) {
+        w1r = w1 + I.w_o[kv];
+        p1r = p1 + I.p_o[kv];
+    } else {
+        ks_phase1_ordered(I, kw, kbit, w1r, p1r);
+    }
+    if (w1r > I.limit) return ks_early(w1r, p1r, I.n);
+    return I.exact ? ks_right_exact(I, sf, sfbit, w1r, p1r, wb - w1, pb - p1)
+                   : ks_eval_chain(I, sfw, sfbit, 0, w1r, p1r, w1r, p1r);
+}
+
+// PAIRED: two warps per instance.  The MAIN warp runs the search loop; for every node it expands it posts the
+// right child (the long evaluation: all fixed items and the whole greedy pass again) to the HELPER warp and
+// meanwhile sinks the heap and evaluates the left child itself; the two meet at a named barrier of their own
+// (bar.sync 1 + pair, 64) before the commit.
+template <int MAXW, bool PAIRED>
 __global__ void __launch_bounds__(MAXW * 32, 1) knap_search_kernel(const KsParams P) {
     extern __shared__ __align__(16) unsigned char ks_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int unit = PAIRED ? warp >> 1 : warp;
+    const bool helper = PAIRED && (warp & 1);
     const int HS = P.HS, MS = P.MS;
     const int n_staged = P.stage_items ? P.n : 0;
-    unsigned char* mine_smem = ks_smem + (size_t)warp * ks_warp_smem(HS, MS, n_staged);
-    double2* st_in = reinterpret_cast<double2*>(mine_smem);
+    unsigned char* mine_smem = ks_smem + (size_t)unit * ks_unit_smem(HS, MS, n_staged, PAIRED);
+    unsigned char* pair_smem = mine_smem + ks_warp_smem(HS, MS, n_staged);  // PAIRED only
+    double2* st_in = reinterpret_cast<double2*>(helper ? pair_smem : mine_smem);
     double2* st_out = st_in + 32;
     unsigned* sm_mask = reinterpret_cast<unsigned*>(mine_smem + 1024);
     unsigned long long* sk = reinterpret_cast<unsigned long long*>(mine_smem + 1024 + (size_t)MS * 4);
     int* sn = reinterpret_cast<int*>(sk + HS);
     double* sm_items = reinterpret_cast<double*>(mine_smem + ks_warp_smem(HS, MS));  // [w_s | p_s] when staged
+    KsJob* job = reinterpret_cast<KsJob*>(pair_smem + 1024);
+    KsEval* res = reinterpret_cast<KsEval*>(pair_smem + 1024 + 64);
     const int W = P.W, n = P.n, cap_nodes = P.node_cap;
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + unit) : "memory"); };
+
+    if (helper) {
+        KsInst I = ks_inst(P, 0, sm_mask, st_in, st_out, sm_items, n_staged);
+        for (;;) {
+            pair_sync();  // a job is posted
+            const KsJob j = *job;
+            if (j.kind == 0) return;
+            if (j.kind == 2) {
+                I = ks_inst(P, j.k, sm_mask, st_in, st_out, sm_items, n_staged);
+                continue;
+            }
+            const KsEval e = ks_right_child(I, j.sf, j.kv, j.w1, j.p1, j.wb, j.pb);
+            if (lane == 0) *res = e;
+            pair_sync();  // the result is in place
+        }
+    }
 
     for (;;) {
         int q = 0;
         if (lane == 0) q = atomicAdd(P.next, 1);
         q = __shfl_sync(0xffffffffu, q, 0);
-        if (q >= P.n_todo) break;
+        if (q >= P.n_todo) {
+            if (PAIRED) {
+                if (lane == 0) job->kind = 0;
+                pair_sync();
+            }
+            break;
+        }
         const int k = P.todo[q];
 
-        KsInst I;
-        I.w_s = P.w_s + (size_t)k * n;
-        I.p_s = P.p_s + (size_t)k * n;
-        I.w_o = P.w_o + (size_t)k * n;
-        I.p_o = P.p_o + (size_t)k * n;
-        I.orig_s = P.orig_s + (size_t)k * n;
-        I.capacity = P.cap[k];
-        I.limit = __dadd_rn(I.capacity, KS_EPS);
-        I.n = n;
-        I.W = W;
-        I.exact = P.exact[k];
-        I.one = sm_mask;
-        I.dec = sm_mask + W;
-        I.st_in = st_in;
-        I.st_out = st_out;
         if (n_staged) {  // the greedy pass reads these 2 n doubles over and over: keep them next to the ALUs
+            const double* gw = P.w_s + (size_t)k * n;
+            const double* gp = P.p_s + (size_t)k * n;
             for (int i = lane; i < n; i += 32) {
-                sm_items[i] = I.w_s[i];
-                sm_items[n + i] = I.p_s[i];
+                sm_items[i] = gw[i];
+                sm_items[n + i] = gp[i];
             }
-            I.w_s = sm_items;
-            I.p_s = sm_items + n;
             __syncwarp();
+        }
+        const KsInst I = ks_inst(P, k, sm_mask, st_in, st_out, sm_items, n_staged);
+        if (PAIRED) {
+            if (lane == 0) {
+                job->kind = 2;
+                job->k = k;
+            }
+            pair_sync();
         }
 
         KsState* S = P.state + k;
@@ -662,10 +763,27 @@ __global__ void __launch_bounds__(MAXW * 32, 1) knap_search_kernel(const KsParam
             const int li = size - 1;
             H.get(li, xk, xn);
             size = li;
-            if (li > 0) ks_heap_sink(H, li - 1, xk, xn);
+            if (!PAIRED && li > 0) ks_heap_sink(H, li - 1, xk, xn);
             pops++;
             __pipeline_wait_prior(0);
             __syncwarp();
+            if (PAIRED) {
+                // the right child goes to the helper as soon as the node's record and masks are here; the heap
+                // sinks (and the left child is evaluated) while it works
+                if (!(M.bound <= best + KS_EPS) && M.frac_rank >= 0) {
+                    if (lane == 0) {
+                        job->kind = 1;
+                        job->sf = M.frac_rank;
+                        job->kv = I.orig_s[M.frac_rank];
+                        job->w1 = M.w1;
+                        job->p1 = M.p1;
+                        job->wb = M.wb;
+                        job->pb = M.pb;
+                    }
+                    pair_sync();
+                }
+                if (li > 0) ks_heap_sink(H, li - 1, xk, xn);
+            }
             KS_TICK(0)
             if (M.bound <= best + KS_EPS) {  // :124 (node.Bound is the stored relaxation's)
                 free_node(tn);
@@ -711,18 +829,11 @@ __global__ void __launch_bounds__(MAXW * 32, 1) knap_search_kernel(const KsParam
                             : ks_eval_chain(I, sfw, sfbit, sf + 1, M.wb, M.pb, M.w1, M.p1);
             KS_TICK(2)
             // right child, x_k = 1
-            {
-                double w1r, p1r;
-                if (I.exact) {
-                    w1r = M.w1 + I.w_o[kv];
-                    p1r = M.p1 + I.p_o[kv];
-                } else {
-                    ks_phase1_ordered(I, kw, kbit, w1r, p1r);
-                    KS_TICK(6)
-                }
-                if (w1r > I.limit) ev[1] = ks_early(w1r, p1r, n);
-                else ev[1] = I.exact ? ks_right_exact(I, sf, sfbit, w1r, p1r, M.wb - M.w1, M.pb - M.p1)
-                                     : ks_eval_chain(I, sfw, sfbit, 0, w1r, p1r, w1r, p1r);
+            if (PAIRED) {
+                pair_sync();  // the helper's result
+                ev[1] = *res;
+            } else {
+                ev[1] = ks_right_child(I, sf, kv, M.w1, M.p1, M.wb, M.pb);
             }
             KS_TICK(3)
             bool overflow = false;
@@ -934,17 +1045,23 @@ int knapsack_search_device(int count, int n, const double* profit, const double*
     // One CTA per SM; its warps (one instance each) share the SM's shared memory: few instances get one
     // SM and a deep heap cache each, a large batch 16 warps per SM with 1023 cached entries each.
     const int max_dyn = r.smem_optin;
-    auto shape_for = [&](int nt, int& wpb, int& HS, bool& stage) {
+    // units per CTA (a unit = one instance in flight: one warp, or a main + helper pair of warps when there are
+    // at most four instances per SM and a single instance's latency is what the caller waits for)
+    static const bool no_pairs = getenv("LPX_KNAP_NO_PAIRS") != nullptr;
+    auto shape_for = [&](int nt, int& wpb, int& HS, bool& stage, bool& paired) {
         wpb = std::max(1, std::min(KS_MAX_WARPS, (nt + r.sms - 1) / r.sms));
+        paired = wpb <= 4 && !no_pairs;
         // one or two instances per SM: at most ~128 KB of the SM's 256 KB, so that their item tables (72 KB per
         // instance at 2000 items) stay in L1; more instances than that do not fit L1 anyway
         const size_t budget = wpb <= 2 ? (size_t)128 * 1024 : (size_t)max_dyn;
         stage = wpb <= 2 && (size_t)n * 16 <= (size_t)48 * 1024;
         HS = 8191;
-        while (HS > 31 && (size_t)wpb * ks_warp_smem(HS, MS, stage ? n : 0) > budget) HS >>= 1;
+        while (HS > 31 && (size_t)wpb * ks_unit_smem(HS, MS, stage ? n : 0, paired) > budget) HS >>= 1;
     };
-    LPX_CUDA(cudaFuncSetAttribute(knap_search_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
-    LPX_CUDA(cudaFuncSetAttribute(knap_search_kernel<KS_MAX_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+    LPX_CUDA(cudaFuncSetAttribute(knap_search_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+    LPX_CUDA(cudaFuncSetAttribute(knap_search_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+    LPX_CUDA(cudaFuncSetAttribute(knap_search_kernel<KS_MAX_WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  max_dyn));
 
     for (int pass = 0; pass < 2 && !todo.empty(); pass++) {
         // pass 0: every instance with an equal share of the budget; pass 1: the few whose pool overflowed,
@@ -999,10 +1116,11 @@ int knapsack_search_device(int count, int n, const double* profit, const double*
         P.trace_cap = trace_cap;
         int wpb = 1, HS = 31;
         bool stage = false;
-        shape_for(nt, wpb, HS, stage);
+        bool paired = false;
+        shape_for(nt, wpb, HS, stage, paired);
         P.HS = HS;
         P.stage_items = stage ? 1 : 0;
-        const size_t smem = (size_t)wpb * ks_warp_smem(HS, MS, stage ? n : 0);
+        const size_t smem = (size_t)wpb * ks_unit_smem(HS, MS, stage ? n : 0, paired);
         DevBuf b_prof;
         static const bool want_prof = getenv("LPX_KNAP_PROF") != nullptr;
         if (want_prof) {
@@ -1031,9 +1149,10 @@ int knapsack_search_device(int count, int n, const double* profit, const double*
         std::vector<KsRec> h_trace;
         while (true) {
             LPX_CUDA(cudaMemsetAsync(d_next, 0, 4, s));
-            const int threads = wpb * 32, grid = std::max(1, std::min((nt + wpb - 1) / wpb, r.sms));
-            if (wpb <= 8) knap_search_kernel<8><<<grid, threads, smem, s>>>(P);  // up to 255 registers per thread
-            else knap_search_kernel<KS_MAX_WARPS><<<grid, threads, smem, s>>>(P);
+            const int threads = wpb * (paired ? 64 : 32), grid = std::max(1, std::min((nt + wpb - 1) / wpb, r.sms));
+            if (paired) knap_search_kernel<8, true><<<grid, threads, smem, s>>>(P);            // <= 4 pairs per CTA
+            else if (wpb <= 8) knap_search_kernel<8, false><<<grid, threads, smem, s>>>(P);    // up to 255 registers
+            else knap_search_kernel<KS_MAX_WARPS, false><<<grid, threads, smem, s>>>(P);
             LPX_CUDA(cudaGetLastError());
             count_launch();
             LPX_CUDA(cudaMemcpyAsync(h_state.data(), d_state, (size_t)count * sizeof(KsState), cudaMemcpyDeviceToHost, s));
