@@ -76,7 +76,9 @@ typedef struct lpx_options {
     int knap_shard_tree;   /* knapsack: 1 = ONE search tree evaluated by all ranks of lpx_comm_init: every rank
                               plans and commits identically, evaluates the speculative subtrees it owns
                               (round robin), and the relaxations are merged by an NCCL all-reduce per round */
-    int reserved[5];
+    int knap_warps;        /* knapsack, warps per instance: 0 auto (2 = a main + helper pair when there are at most four
+                              instances per SM, else 1), 1 or 2 to force */
+    int reserved[4];
 } lpx_options;
 
 #define LPX_KERNEL_AUTO        0

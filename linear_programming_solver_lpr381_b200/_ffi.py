@@ -44,7 +44,7 @@ class Options(C.Structure):
     _fields_ = [("max_iterations", C.c_int), ("kernel", C.c_int), ("threads", C.c_int), ("knap_spec_nodes", C.c_int),
                 ("knap_spec_depth", C.c_int), ("stream_protocol", C.c_int), ("reg_variant", C.c_int),
                 ("stream_block", C.c_int), ("stream_pass_variant", C.c_int), ("knap_ordered_sums", C.c_int),
-                ("knap_shard_tree", C.c_int), ("reserved", C.c_int * 5)]
+                ("knap_shard_tree", C.c_int), ("knap_warps", C.c_int), ("reserved", C.c_int * 4)]
 
 
 class BnbNode(C.Structure):
@@ -152,7 +152,7 @@ def check(rc):
         raise LpxError(rc, last_error())
 
 
-def make_options(max_iterations=10000, kernel=KERNEL_AUTO, threads=0, spec_nodes=0, spec_depth=0, single_cta_select=0, reg_variant=0, kblock=0, pass_variant=0, ordered_sums=0, shard_tree=0):
+def make_options(max_iterations=10000, kernel=KERNEL_AUTO, threads=0, spec_nodes=0, spec_depth=0, single_cta_select=0, reg_variant=0, kblock=0, pass_variant=0, ordered_sums=0, shard_tree=0, knap_warps=0):
     o = Options()
     lib().lpx_default_options(C.byref(o))
     o.max_iterations = max_iterations
@@ -166,6 +166,7 @@ def make_options(max_iterations=10000, kernel=KERNEL_AUTO, threads=0, spec_nodes
     o.stream_pass_variant = pass_variant
     o.knap_ordered_sums = ordered_sums
     o.knap_shard_tree = shard_tree
+    o.knap_warps = knap_warps
     return o
 
 

@@ -287,14 +287,15 @@ def bnb_pooled(A, b, c, rel=None, sense=0, batch=64, node_cap=1 << 20):
 
 
 def bnb_knapsack(profit, weight, capacity, trace=False, spec_nodes=0, spec_depth=0, sequential=False,
-                 shard_tree=False):
+                 shard_tree=False, warps=0):
     p = np.ascontiguousarray(profit, dtype=np.float64)
     w = np.ascontiguousarray(weight, dtype=np.float64)
     n = p.shape[0]
     # sequential=True forces the ordered-summation kernel path even for exactly summable integer data
     # shard_tree=True: all ranks of lpx_comm_init work on this ONE tree (see lpx_options.knap_shard_tree)
+    # warps: 0 auto, 1 one warp per instance, 2 a main + helper pair (lpx_options.knap_warps)
     opt = F.make_options(spec_nodes=spec_nodes, spec_depth=spec_depth, ordered_sums=1 if sequential else 0,
-                         shard_tree=1 if shard_tree else 0)
+                         shard_tree=1 if shard_tree else 0, knap_warps=warps)
     found = C.c_int()
     best = C.c_double()
     bx = np.zeros(n, dtype=np.int32)
@@ -325,12 +326,12 @@ def bnb_knapsack(profit, weight, capacity, trace=False, spec_nodes=0, spec_depth
     return out
 
 
-def bnb_knapsack_batched(profit, weight, capacity, spec_nodes=0, spec_depth=0):
+def bnb_knapsack_batched(profit, weight, capacity, spec_nodes=0, spec_depth=0, warps=0):
     p = np.ascontiguousarray(profit, dtype=np.float64)
     w = np.ascontiguousarray(weight, dtype=np.float64)
     cap = np.ascontiguousarray(capacity, dtype=np.float64)
     count, n = p.shape
-    opt = F.make_options(spec_nodes=spec_nodes, spec_depth=spec_depth)
+    opt = F.make_options(spec_nodes=spec_nodes, spec_depth=spec_depth, knap_warps=warps)
     found = np.zeros(count, dtype=np.int32)
     best = np.zeros(count)
     bx = np.zeros((count, n), dtype=np.int32)

@@ -11,8 +11,8 @@ namespace Linear_Programming_Solver.Models
     {
         public int max_iterations, kernel, threads;
         public int knap_spec_nodes, knap_spec_depth, stream_protocol, reg_variant, stream_block, stream_pass_variant;
-        public int knap_ordered_sums, knap_shard_tree;
-        public int r0, r1, r2, r3, r4;
+        public int knap_ordered_sums, knap_shard_tree, knap_warps;
+        public int r0, r1, r2, r3;
     }
 
     [StructLayout(LayoutKind.Sequential)]

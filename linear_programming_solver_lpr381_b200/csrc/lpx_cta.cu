@@ -35,6 +35,8 @@ bool cta_cluster_fits(int max_rows, int max_width, int cl) {
 int cta_cluster_size_for(int max_rows, int max_width) {
     // (4 CTAs where 2 would do was measured slower, also at 64 registers for two CTAs per SM: 0.34-0.44 s
     // against 0.27 s on the deep levels of the C4 batch — the cluster barrier grows with the cluster.)
+    static const bool prefer4 = getenv("LPX_CLUSTER4") != nullptr;  // experiment switch
+    if (prefer4 && cta_cluster_fits(max_rows, max_width, 4)) return 4;
     if (cta_cluster_fits(max_rows, max_width, 2)) return 2;
     if (cta_cluster_fits(max_rows, max_width, 4)) return 4;
     return 0;

@@ -1047,9 +1047,10 @@ int knapsack_search_device(int count, int n, const double* profit, const double*
     const int max_dyn = r.smem_optin;
     // units per CTA (a unit = one instance in flight: one warp, or a main + helper pair of warps when there are
     // at most four instances per SM and a single instance's latency is what the caller waits for)
-    static const bool no_pairs = getenv("LPX_KNAP_NO_PAIRS") != nullptr;
+    const bool no_pairs = getenv("LPX_KNAP_NO_PAIRS") != nullptr || opt.knap_warps == 1;
     auto shape_for = [&](int nt, int& wpb, int& HS, bool& stage, bool& paired) {
         wpb = std::max(1, std::min(KS_MAX_WARPS, (nt + r.sms - 1) / r.sms));
+        if (opt.knap_warps == 2) wpb = std::min(wpb, 4);  // forced pairs: at most four per CTA (the queue does the rest)
         paired = wpb <= 4 && !no_pairs;
         // one or two instances per SM: at most ~128 KB of the SM's 256 KB, so that their item tables (72 KB per
         // instance at 2000 items) stay in L1; more instances than that do not fit L1 anyway

@@ -193,6 +193,23 @@ def test_knapsack_c5(lpx, orc, kind, sequential):
     compare_knap(got, want, kind)
 
 
+@pytest.mark.parametrize("warps", [1, 2])
+@pytest.mark.parametrize("kind", ["uncorrelated", "fractional"])
+def test_knapsack_one_and_two_warps_per_instance(lpx, orc, kind, warps):
+    """The search kernel's two builds — one warp per instance (large batches) and a main + helper pair (the
+    helper evaluates the right child while the main warp sinks the heap and evaluates the left one) — on a
+    single traced instance and on a batch, against the oracle."""
+    p, w, cap = workloads.knapsack_c5(n=500, seed=21, kind=kind)
+    compare_knap(lpx.bnb_knapsack(p, w, cap, trace=True, warps=warps), orc.knapsack(p, w, cap), f"{kind} warps={warps}")
+    ps, ws, caps = zip(*[workloads.knapsack_c5(n=300, seed=200 + k, kind=kind) for k in range(9)])
+    got = lpx.bnb_knapsack_batched(np.stack(ps), np.stack(ws), np.array(caps), warps=warps)
+    for k in range(9):
+        want = orc.knapsack(ps[k], ws[k], caps[k])
+        assert got["n_evals"][k] == want["n_evals"] and got["n_pops"][k] == want["n_pops"], (kind, warps, k)
+        assert_bits_equal([got["best"][k]], [want["best"]], f"best {k}")
+        assert got["best_x"][k].tolist() == want["best_x"].tolist()
+
+
 def test_knapsack_integer_edge_values(lpx, orc):
     """Zero and repeated weights, zero profits, capacity hit exactly: the exact-sum path."""
     rng = np.random.default_rng(91)
