@@ -1141,9 +1141,7 @@ int knapsack_search_device(int count, int n, const double* profit, const double*
             std::fill(pop_index.begin(), pop_index.end(), 0);
         }
 
-        std::vector<int> running = todo;  // slot q <-> todo[q] stays fixed while the pass resumes paused instances
-        std::vector<int> slot_of(count, -1);
-        for (int q = 0; q < nt; q++) slot_of[todo[q]] = q;
+        // Slot q <-> todo[q] stays fixed while the pass resumes paused instances.
         // Paused instances keep their slot: the kernel is relaunched over the same todo list and instances
         // that are already done return at once.
         LPX_CUDA(cudaMemcpyAsync(d_todo, todo.data(), (size_t)nt * 4, cudaMemcpyHostToDevice, s));
@@ -1167,8 +1165,6 @@ int knapsack_search_device(int count, int n, const double* profit, const double*
                     h_trace.resize(st.trace_count);
                     LPX_CUDA(cudaMemcpy(h_trace.data(), P.trace + (size_t)q * trace_cap,
                                         (size_t)st.trace_count * sizeof(KsRec), cudaMemcpyDeviceToHost));
-                    const int* ord = h_orig.data() + (size_t)k * n;
-                    (void)ord;
                     if (tnodes.empty() && pop_index[k] == 0) {
                         TraceNode root;
                         root.assigned.assign(n, -1);
