@@ -32,7 +32,7 @@ sys.path.insert(0, ROOT)
 C2 = dict(count=4096, m=64, n=128)
 C3 = dict(m=4096, n=8192)
 BNB_INSTANCES = 512             # C4 instances per GPU in the bnb_simplex section ("e.g. 512")
-KNAP_INSTANCES = 592            # C5 instances per GPU in the bnb_knapsack section (4 per SM: one warp each)
+KNAP_INSTANCES = 2368           # C5 instances per GPU in the bnb_knapsack section (16 per SM: one warp each)
 KNAP_INSTANCES_FRACTIONAL = 148
 POOLED = dict(seed=12, batch=4096)  # Mode B: one hard 60 x 120 instance (2.2e5 nodes), rounds of 4096 open nodes
 

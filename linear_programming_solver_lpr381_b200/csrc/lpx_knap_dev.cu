@@ -90,7 +90,10 @@ struct KsParams {
     int n, W, MS, count;  // W mask words per set; MS words per node (ONE then DEC), a multiple of 4
     // per-slot arenas: slot q serves instance todo[q]
     const int* todo;
+    const int* slots;   // arena slot of queue entry q (an instance keeps its slot when it is resumed in a shorter queue)
     int n_todo;
+    int pop_budget;     // > 0: an instance pauses after this many pops in one launch (stragglers of a large batch
+                        // are resumed with a pair of warps and an SM's heap cache each)
     int* next;          // work-queue head
     int node_cap;       // nodes (= heap entries = free-stack entries) per slot
     KsHeapEntry* heap;  // [slot][node_cap]
@@ -634,6 +637,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) knap_search_kernel(const KsParam
             break;
         }
         const int k = P.todo[q];
+        const int slot = P.slots[q];
 
         if (n_staged) {  // the greedy pass reads these 2 n doubles over and over: keep them next to the ALUs
             const double* gw = P.w_s + (size_t)k * n;
@@ -657,16 +661,17 @@ __global__ void __launch_bounds__(MAXW * 32, 1) knap_search_kernel(const KsParam
         KsHeap H;
         H.sk = sk;
         H.sn = sn;
-        H.g = P.heap + (size_t)q * cap_nodes;
+        H.g = P.heap + (size_t)slot * cap_nodes;
         H.HS = HS;
-        int* fstack = P.free_stack + (size_t)q * cap_nodes;
-        KsMeta* meta = P.meta + (size_t)q * cap_nodes;
-        unsigned* masks = P.masks + (size_t)q * cap_nodes * MS;
+        int* fstack = P.free_stack + (size_t)slot * cap_nodes;
+        KsMeta* meta = P.meta + (size_t)slot * cap_nodes;
+        unsigned* masks = P.masks + (size_t)slot * cap_nodes * MS;
         unsigned* bmask = P.best_masks + (size_t)k * 2 * W;
-        KsRec* trace = P.trace ? P.trace + (size_t)q * P.trace_cap : nullptr;
+        KsRec* trace = P.trace ? P.trace + (size_t)slot * P.trace_cap : nullptr;
 
         double best = S->best;
         long long evals = S->evals, pops = S->pops;
+        const long long pops_at_start = pops;
         int size = S->heap_size, free_top = S->free_top, next_fresh = S->next_fresh;
         int status = KS_RUNNING, tcount = 0;
         __syncwarp();
@@ -745,7 +750,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) knap_search_kernel(const KsParam
         c0 = c1;                           \
     }
         while (size > 0) {
-            if (trace && tcount + 3 > P.trace_cap) {
+            if ((trace && tcount + 3 > P.trace_cap) || (P.pop_budget > 0 && pops - pops_at_start >= P.pop_budget)) {
                 status = KS_PAUSED;
                 break;
             }
@@ -1042,9 +1047,10 @@ int knapsack_search_device(int count, int n, const double* profit, const double*
     int rc;
     KsState* d_state = ws_dev_as<KsState>(WS_KN_OUT, count);
     unsigned* d_best = ws_dev_as<unsigned>(WS_KN_AUX, (size_t)count * 2 * W);
-    int* d_todo = ws_dev_as<int>(WS_KN_EXACT, (size_t)count + 1);
+    int* d_todo = ws_dev_as<int>(WS_KN_EXACT, (size_t)2 * count + 1);  // queue (instances), their arena slots, head
     if (!d_state || !d_best || !d_todo) return LPX_E_CUDA;
-    int* d_next = d_todo + count;
+    int* d_slots = d_todo + count;
+    int* d_next = d_todo + 2 * count;
 
     const bool tracing = on_pop != nullptr;
     if (tracing && count != 1) {
@@ -1123,6 +1129,7 @@ int knapsack_search_device(int count, int n, const double* profit, const double*
         P.MS = MS;
         P.count = count;
         P.todo = d_todo;
+        P.slots = d_slots;
         P.n_todo = nt;
         P.next = d_next;
         P.node_cap = (int)cap_nodes;
@@ -1140,13 +1147,9 @@ int knapsack_search_device(int count, int n, const double* profit, const double*
         P.best_masks = d_best;
         P.state = d_state;
         P.trace_cap = trace_cap;
-        int wpb = 1, HS = 31;
-        bool stage = false;
-        bool paired = false;
-        shape_for(nt, wpb, HS, stage, paired);
-        P.HS = HS;
-        P.stage_items = stage ? 1 : 0;
-        const size_t smem = (size_t)wpb * ks_unit_smem(HS, MS, stage ? n : 0, paired);
+        // the queue of one launch: `queue[q]` = instance, `qslot[q]` = its arena slot (fixed for the pass)
+        std::vector<int> queue = todo, qslot(nt);
+        for (int q = 0; q < nt; q++) qslot[q] = q;
         DevBuf b_prof;
         static const bool want_prof = getenv("LPX_KNAP_PROF") != nullptr;
         if (want_prof) {
@@ -1169,11 +1172,24 @@ int knapsack_search_device(int count, int n, const double* profit, const double*
         // Slot q <-> todo[q] stays fixed while the pass resumes paused instances.
         // Paused instances keep their slot: the kernel is relaunched over the same todo list and instances
         // that are already done return at once.
-        LPX_CUDA(cudaMemcpyAsync(d_todo, todo.data(), (size_t)nt * 4, cudaMemcpyHostToDevice, s));
         std::vector<KsRec> h_trace;
         while (true) {
+            // One launch over the current queue.  A large batch runs one warp per instance, 16 per SM, with a pop
+            // budget: the few long searches that outlive it are paused and resumed in a short queue — a pair of
+            // warps and an SM's heap cache each — instead of crawling on as lone warps after everybody else is done.
+            const int nq = (int)queue.size();
+            int wpb = 1, HS = 31;
+            bool stage = false, paired = false;
+            shape_for(nq, wpb, HS, stage, paired);
+            P.HS = HS;
+            P.stage_items = stage ? 1 : 0;
+            P.n_todo = nq;
+            P.pop_budget = (!paired && !tracing) ? 16384 : 0;
+            const size_t smem = (size_t)wpb * ks_unit_smem(HS, MS, stage ? n : 0, paired);
+            LPX_CUDA(cudaMemcpyAsync(d_todo, queue.data(), (size_t)nq * 4, cudaMemcpyHostToDevice, s));
+            LPX_CUDA(cudaMemcpyAsync(d_slots, qslot.data(), (size_t)nq * 4, cudaMemcpyHostToDevice, s));
             LPX_CUDA(cudaMemsetAsync(d_next, 0, 4, s));
-            const int threads = wpb * (paired ? 64 : 32), grid = std::max(1, std::min((nt + wpb - 1) / wpb, r.sms));
+            const int threads = wpb * (paired ? 64 : 32), grid = std::max(1, std::min((nq + wpb - 1) / wpb, r.sms));
             if (paired) knap_search_kernel<8, true><<<grid, threads, smem, s>>>(P);            // <= 4 pairs per CTA
             else if (wpb <= 8) knap_search_kernel<8, false><<<grid, threads, smem, s>>>(P);    // up to 255 registers
             else knap_search_kernel<KS_MAX_WARPS, false><<<grid, threads, smem, s>>>(P);
@@ -1181,14 +1197,14 @@ int knapsack_search_device(int count, int n, const double* profit, const double*
             count_launch();
             LPX_CUDA(cudaMemcpyAsync(h_state.data(), d_state, (size_t)count * sizeof(KsState), cudaMemcpyDeviceToHost, s));
             LPX_CUDA(cudaStreamSynchronize(s));
-            bool paused = false;
-            for (int q = 0; q < nt; q++) {
-                const int k = todo[q];
+            std::vector<int> nqueue, nslot;
+            for (int q = 0; q < nq; q++) {
+                const int k = queue[q];
                 KsState& st = h_state[k];
                 if (tracing && st.trace_count > 0) {
                     // replay the records: rebuild assignment vectors and labels, call back in order
                     h_trace.resize(st.trace_count);
-                    LPX_CUDA(cudaMemcpy(h_trace.data(), P.trace + (size_t)q * trace_cap,
+                    LPX_CUDA(cudaMemcpy(h_trace.data(), P.trace + (size_t)qslot[q] * trace_cap,
                                         (size_t)st.trace_count * sizeof(KsRec), cudaMemcpyDeviceToHost));
                     if (tnodes.empty() && pop_index[k] == 0) {
                         TraceNode root;
@@ -1247,9 +1263,14 @@ int knapsack_search_device(int count, int n, const double* profit, const double*
                         t += 3;
                     }
                 }
-                if (st.status == KS_PAUSED) paused = true;
+                if (st.status == KS_PAUSED) {
+                    nqueue.push_back(k);
+                    nslot.push_back(qslot[q]);
+                }
             }
-            if (!paused) break;
+            if (nqueue.empty()) break;
+            queue.swap(nqueue);
+            qslot.swap(nslot);
         }
         if (want_prof) {
             long long h[8];
