@@ -332,6 +332,7 @@ struct Driver {
     // one upload, one launch per kernel family (nodes that fit one SM's shared memory | cluster / global-
     // memory nodes), one download, one event.  Two sets alternate on the stream, so the host commits one
     // half's round while the GPU solves the other half's.
+    bool use_condensed = true;  // run(): opt.kernel == AUTO and LPX_BNB_FULL_TABLEAU unset
     struct EvalSet {
         std::vector<Node*> nodes;  // kind 0 first, then kind 1
         int c0 = 0, total = 0;
@@ -351,9 +352,16 @@ struct Driver {
         std::vector<Node*> big;
         size_t total_extra = 0;
         int max_extra[2] = {0, 0};
+        // no callback on this path, so nobody reads a node's tableau: when the deepest node's CONDENSED tableau
+        // (non-basic columns + RHS, lpx_cta_cond.cuh) fits one SM, every node runs on the condensed kernel —
+        // in two launches, so that the shallow nodes (two CTAs' worth of shared memory per SM) are not held
+        // to the occupancy of the deepest one
+        int deepest = 0;
+        for (Node* nd : todo) deepest = std::max(deepest, (int)nd->extras.size());
+        const bool cond = use_condensed && cta_condensed_fits(mm + deepest + 1, n);
         for (Node* nd : todo) {
             const int rows = mm + (int)nd->extras.size() + 1, width = n + rows;
-            const bool fits = cta_fits_smem(rows, width);
+            const bool fits = cond ? cta_condensed_ctas_per_sm(rows, n) >= 2 : cta_fits_smem(rows, width);
             (fits ? E.nodes : big).push_back(nd);
             max_extra[fits ? 0 : 1] = std::max(max_extra[fits ? 0 : 1], (int)nd->extras.size());
             total_extra += nd->extras.size();
@@ -425,7 +433,7 @@ struct Driver {
             B.max_iter = opt.max_iterations;
             B.max_rows = max_rows;
             B.max_width = max_width;
-            if (kind == 1 && cta_cluster_size_for(max_rows, max_width) == 0) {  // beyond a 4-CTA cluster: global memory
+            if (!cond && kind == 1 && cta_cluster_size_for(max_rows, max_width) == 0) {  // beyond a 4-CTA cluster: global memory
                 double* sc = (double*)ws_dev(s_scr, (size_t)cnt * tsize * 8);
                 if (!sc) return LPX_E_CUDA;
                 B.scratch = sc;
@@ -439,8 +447,9 @@ struct Driver {
             B.node_branch = d_stat + 5 * total + lo;
             B.x = d_x + (size_t)lo * n;
             B.z = d_z + lo;
-            int rc = cta_launch(B, cnt, opt.kernel == LPX_KERNEL_CTA_GLOBAL ? LPX_KERNEL_CTA_GLOBAL : LPX_KERNEL_AUTO,
-                                opt.threads, s, nullptr);
+            int rc = cond ? cta_condensed_launch(B, cnt, s)
+                          : cta_launch(B, cnt, opt.kernel == LPX_KERNEL_CTA_GLOBAL ? LPX_KERNEL_CTA_GLOBAL : LPX_KERNEL_AUTO,
+                                       opt.threads, s, nullptr);
             if (rc != LPX_OK) return rc;
             tr_launch[kind]++;
             tr_nodes[kind] += cnt;
@@ -708,6 +717,7 @@ struct Driver {
             inst[k].stack.push_back(std::move(root));
         }
         const bool want_history = (flags & LPX_BNB_WANT_HISTORY) && on_node;
+        use_condensed = opt.kernel == LPX_KERNEL_AUTO && !std::getenv("LPX_BNB_FULL_TABLEAU");
         if (!on_node && count >= 32) return run_pipelined();
         while (true) {
             std::vector<Node*> todo;

@@ -8,6 +8,7 @@
 
 #include "lpx_cta.cuh"
 #include "lpx_cta_cluster.cuh"
+#include "lpx_cta_cond.cuh"
 #include "lpx_runtime.hpp"
 #include "lpx_stream.hpp"
 
@@ -112,6 +113,28 @@ int cta_launch(const CtaBatch& B, int count, int kernel_pref, int threads_pref, 
     if (threads == 128) return launch_variant<128, false>(B, count, smem, stream);
     if (threads == 256) return launch_variant<256, false>(B, count, smem, stream);
     return launch_variant<512, false>(B, count, smem, stream);
+}
+
+// condensed-tableau node kernel (lpx_cta_cond.cuh)
+bool cta_condensed_fits(int max_rows, int n) { return cond_carve(max_rows, n).total <= (size_t)max_smem_optin(); }
+int cta_condensed_ctas_per_sm(int rows, int n) {
+    // 227 KB usable per SM, 1 KB reserved per resident CTA; 58 registers x 512 threads allow two CTAs
+    const size_t per = cond_carve(rows, n).total + 1024 + 1024;  // + the kernel's static shared memory
+    return (int)std::min<size_t>(2, ((size_t)228 * 1024) / per);
+}
+int cta_condensed_launch(const CtaBatch& B, int count, cudaStream_t stream) {
+    if (count <= 0) return LPX_OK;
+    const size_t smem = cond_carve(B.max_rows, B.n).total;
+    if (smem > (size_t)max_smem_optin()) {
+        set_error("internal: condensed tableau does not fit in shared memory");
+        return LPX_E_CAPACITY;
+    }
+    auto kfn = cta_condensed_kernel<512>;
+    LPX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kfn<<<count, 512, smem, stream>>>(B);
+    LPX_CUDA(cudaGetLastError());
+    count_launch();
+    return LPX_OK;
 }
 
 static int expanded_rows(int m, const int* rel) {

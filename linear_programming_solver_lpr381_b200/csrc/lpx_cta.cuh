@@ -811,6 +811,10 @@ __global__ void __launch_bounds__(THREADS) cta_simplex_kernel(const CtaBatch B) 
 // not fit in shared memory and B.tableau is null.
 int cta_launch(const CtaBatch& B, int count, int kernel_pref, int threads_pref, cudaStream_t stream, bool* used_smem);
 bool cta_fits_smem(int max_rows, int max_width);
+// condensed-tableau node kernel (lpx_cta_cond.cuh)
+bool cta_condensed_fits(int max_rows, int n);
+int cta_condensed_ctas_per_sm(int rows, int n);  // by shared memory
+int cta_condensed_launch(const CtaBatch& B, int count, cudaStream_t stream);
 int cta_cluster_size_for(int max_rows, int max_width);
 
 }  // namespace lpx
