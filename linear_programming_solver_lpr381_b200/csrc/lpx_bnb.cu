@@ -15,6 +15,9 @@
 // iteration log) but never branches.
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <cstdio>
 #include <cstdlib>
@@ -55,6 +58,8 @@ struct Node {
     int flags = 0, branch = -1;  // node epilogue of the kernel: bit 0 IsFeasible, bit 1 IsIntegral; branching variable
     double z = 0;
     std::vector<double> x;
+    const double* xp = nullptr;  // pipelined batches: x stays in the evaluation set's pinned result block
+    int slot = -1;               // ... at this index
     std::vector<int> pivots;
     std::vector<double> history;
     int n_history = 0;
@@ -71,6 +76,7 @@ struct Instance {
     double lp_flops = 0;  // sum over node LPs of pivots x flops per pivot at that node's shape
     int root_status = 0;
     bool finished = false;
+    std::vector<Node*> open;  // pipelined batches: this instance's nodes in the evaluation set in flight
 };
 
 // Math.Round(double): ties to even
@@ -327,55 +333,136 @@ struct Driver {
         return LPX_OK;
     }
 
-    // ---- asynchronous evaluation (batches without a callback) -------------------------------------
-    // One evaluation SET = all open nodes of half of the instances: descriptors staged in one pinned blob,
-    // one upload, one launch per kernel family (nodes that fit one SM's shared memory | cluster / global-
-    // memory nodes), one download, one event.  Two sets alternate on the stream, so the host commits one
-    // half's round while the GPU solves the other half's.
+    // ---- pipelined evaluation (batches without a callback) ---------------------------------------
+    // The batch is cut into 2-4 evaluation SETS of instances.  One round of a set = all its open nodes:
+    // descriptors staged in one pinned blob, one upload, one launch per occupancy class, one download, one
+    // event — on the set's own stream, so that the tail of one set's kernel overlaps the next set's.  While
+    // the GPU solves the other sets the host commits this set's round (SolveNode bodies, independent per
+    // instance) and stages its next one on a few persistent worker threads.
+    struct HostPool {
+        std::vector<std::thread> th;
+        std::mutex mu;
+        std::condition_variable cv;
+        std::atomic<unsigned> gen{0};
+        std::atomic<int> next{0}, pending{0};
+        std::atomic<bool> stop{false};
+        int hi = 0, chunk = 1;
+        const std::function<void(int, int)>* fn = nullptr;
+
+        explicit HostPool(int workers) {
+            for (int t = 0; t < workers; t++) th.emplace_back([this] { loop(); });
+        }
+        ~HostPool() {
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                stop.store(true);
+                gen.fetch_add(1, std::memory_order_release);
+            }
+            cv.notify_all();
+            for (std::thread& t : th) t.join();
+        }
+        void work() {
+            for (;;) {
+                const int a = next.fetch_add(chunk);
+                if (a >= hi) break;
+                (*fn)(a, std::min(hi, a + chunk));
+            }
+        }
+        void loop() {
+            unsigned seen = 0;
+            for (;;) {
+                int spins = 0;
+                while (gen.load(std::memory_order_acquire) == seen) {
+                    if (++spins < 4000) {
+                        std::this_thread::yield();
+                        continue;
+                    }
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return gen.load(std::memory_order_acquire) != seen; });
+                }
+                if (stop.load()) return;
+                seen = gen.load(std::memory_order_acquire);
+                work();
+                pending.fetch_sub(1, std::memory_order_release);
+            }
+        }
+        // f(a, b) over [lo, hi_) in chunks, on the workers and the calling thread
+        void run(int lo, int hi_, int chunk_, const std::function<void(int, int)>& f) {
+            if (th.empty() || hi_ - lo <= chunk_) {
+                if (hi_ > lo) f(lo, hi_);
+                return;
+            }
+            fn = &f;
+            hi = hi_;
+            chunk = chunk_;
+            next.store(lo);
+            pending.store((int)th.size());
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                gen.fetch_add(1, std::memory_order_release);
+            }
+            cv.notify_all();
+            work();
+            while (pending.load(std::memory_order_acquire) != 0) std::this_thread::yield();
+        }
+    };
+
     bool use_condensed = true;  // run(): opt.kernel == AUTO and LPX_BNB_FULL_TABLEAU unset
     struct EvalSet {
-        std::vector<Node*> nodes;  // kind 0 first, then kind 1
-        int c0 = 0, total = 0;
-        cudaEvent_t done = nullptr;
+        int lo = 0, hi = 0;         // instances [lo, hi)
+        std::vector<Node*> nodes;   // occupancy class 0 first, then class 1
+        std::vector<int> offs;      // first extra row of each node in the blob
+        int total = 0;
+        cudaStream_t stream = nullptr;
+        cudaEvent_t done = nullptr, began = nullptr;
         bool active = false;
-        int *h_stat = nullptr;
+        int* h_stat = nullptr;
         double *h_x = nullptr, *h_z = nullptr;
-    } sets[2];
+    };
+    std::vector<EvalSet> sets;
+    bool trace_gpu = false;
+    double gpu_ms = 0;
 
-    int evaluate_async(std::vector<Node*>& todo, int set) {
-        EvalSet& E = sets[set];
+    // stage and launch the open nodes (Instance::open) of set g
+    int enqueue(int g, HostPool& pool) {
+        EvalSet& E = sets[g];
         E.active = false;
-        if (todo.empty()) return LPX_OK;
-        Runtime& r = rt();
         const auto tr_t0 = std::chrono::steady_clock::now();
-        E.nodes.clear();
-        std::vector<Node*> big;
-        size_t total_extra = 0;
-        int max_extra[2] = {0, 0};
         // no callback on this path, so nobody reads a node's tableau: when the deepest node's CONDENSED tableau
         // (non-basic columns + RHS, lpx_cta_cond.cuh) fits one SM, every node runs on the condensed kernel —
-        // in two launches, so that the shallow nodes (two CTAs' worth of shared memory per SM) are not held
-        // to the occupancy of the deepest one
-        int deepest = 0;
-        for (Node* nd : todo) deepest = std::max(deepest, (int)nd->extras.size());
+        // in two launches, so that the shallow nodes (two CTAs per SM) are not held to the occupancy of the
+        // deepest one.  Otherwise: nodes that fit one SM's shared memory | cluster / global-memory nodes.
+        int deepest = -1;
+        for (int k = E.lo; k < E.hi; k++)
+            for (Node* nd : inst[k].open) deepest = std::max(deepest, (int)nd->extras.size());
+        if (deepest < 0) return LPX_OK;
         const bool cond = use_condensed && cta_condensed_fits(mm + deepest + 1, n);
-        for (Node* nd : todo) {
-            const int rows = mm + (int)nd->extras.size() + 1, width = n + rows;
-            const bool fits = cond ? cta_condensed_ctas_per_sm(rows, n) >= 2 : cta_fits_smem(rows, width);
-            (fits ? E.nodes : big).push_back(nd);
-            max_extra[fits ? 0 : 1] = std::max(max_extra[fits ? 0 : 1], (int)nd->extras.size());
-            total_extra += nd->extras.size();
-        }
-        E.c0 = (int)E.nodes.size();
+        E.nodes.clear();
+        std::vector<Node*> big;
+        int max_extra[2] = {0, 0};
+        for (int k = E.lo; k < E.hi; k++)
+            for (Node* nd : inst[k].open) {
+                const int rows = mm + (int)nd->extras.size() + 1, width = n + rows;
+                const int kind = (cond ? cta_condensed_ctas_per_sm(rows, n) >= 2 : cta_fits_smem(rows, width)) ? 0 : 1;
+                (kind ? big : E.nodes).push_back(nd);
+                max_extra[kind] = std::max(max_extra[kind], (int)nd->extras.size());
+            }
+        const int c0 = (int)E.nodes.size();
         E.nodes.insert(E.nodes.end(), big.begin(), big.end());
         const int total = E.total = (int)E.nodes.size();
+        E.offs.resize((size_t)total + 1);
+        size_t total_extra = 0;
+        for (int k = 0; k < total; k++) {
+            E.offs[k] = (int)total_extra;
+            total_extra += E.nodes[k]->extras.size();
+        }
         // input blob: inst, off, cnt, mode (ints per node), var, rel (ints per extra), rhs (doubles per extra)
         const size_t in_ints = (size_t)4 * total + 2 * (total_extra + 1);
         const size_t in_bytes = ((in_ints * 4 + 7) & ~(size_t)7) + (total_extra + 1) * 8;
         // output blob: status, n_pivots, silent, n_history, flags, branch (ints), z, x (doubles)
         const size_t out_bytes = (size_t)total * 6 * 4 + (size_t)total * 8 + (size_t)total * n * 8;
-        const Slot s_in = set ? WS_BB_IN1 : WS_BB_IN0, s_out = set ? WS_BB_OUT1 : WS_BB_OUT0,
-                   s_scr = set ? WS_BB_SCR1 : WS_BB_SCR0;
+        const Slot s_in = (Slot)(WS_BB_SET0 + 3 * g), s_out = (Slot)(WS_BB_SET0 + 3 * g + 1),
+                   s_scr = (Slot)(WS_BB_SET0 + 3 * g + 2);
         unsigned char* h_in = (unsigned char*)ws_pin(s_in, in_bytes);
         unsigned char* d_in = (unsigned char*)ws_dev(s_in, in_bytes);
         unsigned char* h_out = (unsigned char*)ws_pin(s_out, out_bytes);
@@ -385,28 +472,32 @@ struct Driver {
         int *h_inst = hi, *h_off = hi + total, *h_cnt = hi + 2 * total, *h_mode = hi + 3 * total;
         int *h_var = hi + 4 * total, *h_rel = h_var + total_extra + 1;
         double* h_rhs = (double*)(h_in + ((in_ints * 4 + 7) & ~(size_t)7));
-        size_t off = 0;
-        for (int k = 0; k < total; k++) {
-            Node* nd = E.nodes[k];
-            h_inst[k] = nd->inst;
-            h_off[k] = (int)off;
-            h_cnt[k] = (int)nd->extras.size();
-            h_mode[k] = nd->mode;
-            for (const Extra& e : nd->extras) {
-                h_var[off] = e.var;
-                h_rel[off] = e.rel;
-                h_rhs[off] = e.rhs;
-                off++;
+        pool.run(0, total, 32, [&](int a, int b) {
+            for (int k = a; k < b; k++) {
+                Node* nd = E.nodes[k];
+                nd->slot = k;
+                size_t off = (size_t)E.offs[k];
+                h_inst[k] = nd->inst;
+                h_off[k] = (int)off;
+                h_cnt[k] = (int)nd->extras.size();
+                h_mode[k] = nd->mode;
+                for (const Extra& e : nd->extras) {
+                    h_var[off] = e.var;
+                    h_rel[off] = e.rel;
+                    h_rhs[off] = e.rhs;
+                    off++;
+                }
             }
-        }
-        cudaStream_t s = r.stream;
+        });
+        cudaStream_t s = E.stream;
+        if (trace_gpu) LPX_CUDA(cudaEventRecord(E.began, s));
         LPX_CUDA(cudaMemcpyAsync(d_in, h_in, in_bytes, cudaMemcpyHostToDevice, s));
         int* di = (int*)d_in;
         int* d_stat = (int*)d_out;
         double* d_z = (double*)(d_out + (size_t)total * 24);
         double* d_x = d_z + total;
         for (int kind = 0; kind < 2; kind++) {
-            const int lo = kind ? E.c0 : 0, cnt = kind ? total - E.c0 : E.c0;
+            const int lo = kind ? c0 : 0, cnt = kind ? total - c0 : c0;
             if (cnt == 0) continue;
             const int max_rows = mm + max_extra[kind] + 1, max_width = n + max_rows;
             const size_t tsize = (size_t)max_rows * max_width;
@@ -433,7 +524,7 @@ struct Driver {
             B.max_iter = opt.max_iterations;
             B.max_rows = max_rows;
             B.max_width = max_width;
-            if (!cond && kind == 1 && cta_cluster_size_for(max_rows, max_width) == 0) {  // beyond a 4-CTA cluster: global memory
+            if (!cond && kind == 1 && cta_cluster_size_for(max_rows, max_width) == 0) {  // beyond a 4-CTA cluster
                 double* sc = (double*)ws_dev(s_scr, (size_t)cnt * tsize * 8);
                 if (!sc) return LPX_E_CUDA;
                 B.scratch = sc;
@@ -455,7 +546,6 @@ struct Driver {
             tr_nodes[kind] += cnt;
         }
         LPX_CUDA(cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, s));
-        if (!E.done) LPX_CUDA(cudaEventCreateWithFlags(&E.done, cudaEventDisableTiming));
         LPX_CUDA(cudaEventRecord(E.done, s));
         E.h_stat = (int*)h_out;
         E.h_z = (double*)(h_out + (size_t)total * 24);
@@ -465,26 +555,95 @@ struct Driver {
         return LPX_OK;
     }
 
-    int evaluate_finish(int set) {
-        EvalSet& E = sets[set];
-        if (!E.active) return LPX_OK;
-        const auto tr_t0 = std::chrono::steady_clock::now();
-        LPX_CUDA(cudaEventSynchronize(E.done));
-        tr_time[0] += std::chrono::duration<double>(std::chrono::steady_clock::now() - tr_t0).count();
-        const int total = E.total;
-        for (int k = 0; k < total; k++) {
-            Node* nd = E.nodes[k];
-            nd->evaluated = true;
-            nd->lp_status = E.h_stat[k];
-            nd->n_pivots = E.h_stat[total + k];
-            nd->silent = E.h_stat[2 * total + k];
-            nd->flags = E.h_stat[4 * total + k];
-            nd->branch = E.h_stat[5 * total + k];
-            nd->z = E.h_z[k];
-            nd->x.assign(E.h_x + (size_t)k * n, E.h_x + (size_t)(k + 1) * n);
-            tr_piv[k < E.c0 ? 0 : 1] += nd->n_pivots;
+    // results of set g's round -> its nodes, SolveNode bodies in the reference's order, next round's open nodes
+    int finish_and_commit(int g, HostPool& pool) {
+        EvalSet& E = sets[g];
+        if (E.active) {
+            const auto tr_t0 = std::chrono::steady_clock::now();
+            LPX_CUDA(cudaEventSynchronize(E.done));
+            tr_time[0] += std::chrono::duration<double>(std::chrono::steady_clock::now() - tr_t0).count();
+            if (trace_gpu) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, E.began, E.done);
+                gpu_ms += ms;
+            }
         }
+        const int total = E.total;
+        pool.run(E.lo, E.hi, 4, [&](int a, int b) {
+            for (int k = a; k < b; k++) {
+                Instance& I = inst[k];
+                for (Node* nd : I.open) {
+                    const int q = nd->slot;
+                    nd->evaluated = true;
+                    nd->lp_status = E.h_stat[q];
+                    nd->n_pivots = E.h_stat[total + q];
+                    nd->silent = E.h_stat[2 * total + q];
+                    nd->flags = E.h_stat[4 * total + q];
+                    nd->branch = E.h_stat[5 * total + q];
+                    nd->z = E.h_z[q];
+                    nd->xp = E.h_x + (size_t)q * n;
+                }
+                I.open.clear();
+                while (!I.finished && !I.stack.empty() && I.stack.back()->evaluated) {
+                    std::unique_ptr<Node> nd = std::move(I.stack.back());
+                    I.stack.pop_back();
+                    if (nd->is_root_lp) commit_root_lp(I, std::move(nd));
+                    else commit_node(I, std::move(nd));
+                }
+                if (I.stack.empty()) I.finished = true;
+                if (!I.finished)  // the nodes without a relaxation yet are the top of the stack
+                    for (size_t i = I.stack.size(); i-- > 0 && !I.stack[i]->evaluated;) I.open.push_back(I.stack[i].get());
+            }
+        });
         E.active = false;
+        return LPX_OK;
+    }
+
+    int run_pipelined() {
+        const int nsets = std::max(2, std::min(LPX_BB_SETS, count / 64));
+        sets.resize(nsets);
+        int rc = LPX_OK;
+        LPX_CUDA(cudaStreamSynchronize(rt().stream));  // the base problems are on the device
+        trace_gpu = getenv("LPX_BNB_TRACE") != nullptr;
+        for (int g = 0; g < nsets; g++) {
+            EvalSet& E = sets[g];
+            E.lo = (int)((long long)count * g / nsets);
+            E.hi = (int)((long long)count * (g + 1) / nsets);
+            if (cudaStreamCreateWithFlags(&E.stream, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&E.done, trace_gpu ? cudaEventDefault : cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&E.began, cudaEventDefault) != cudaSuccess)
+                rc = LPX_E_CUDA;
+        }
+        if (rc == LPX_OK) {
+            HostPool pool(host_threads() - 1);
+            for (int g = 0; g < nsets && rc == LPX_OK; g++)
+                if ((rc = finish_and_commit(g, pool)) == LPX_OK) rc = enqueue(g, pool);  // nothing to commit yet: the roots
+            bool any = true;
+            while (rc == LPX_OK && any) {
+                any = false;
+                for (int g = 0; g < nsets && rc == LPX_OK; g++) {
+                    if (!sets[g].active) continue;
+                    any = true;
+                    if ((rc = finish_and_commit(g, pool)) == LPX_OK) rc = enqueue(g, pool);
+                }
+            }
+        }
+        for (EvalSet& E : sets) {
+            if (E.stream) {
+                cudaStreamSynchronize(E.stream);
+                cudaStreamDestroy(E.stream);
+            }
+            if (E.done) cudaEventDestroy(E.done);
+            if (E.began) cudaEventDestroy(E.began);
+        }
+        if (rc != LPX_OK) {
+            if (rc == LPX_E_CUDA) set_error("lpx_bnb_simplex: CUDA error in the pipelined node evaluation");
+            return rc;
+        }
+        if (trace_gpu)
+            fprintf(stderr, "[bnb trace] pipelined, %d sets: %.3f s waiting for the GPU, %.3f s staging + enqueueing, GPU busy "
+                            "(sum over sets, upload to download) %.3f s; class 0: %ld launches / %ld nodes, class 1: %ld / %ld\n",
+                    nsets, tr_time[0], tr_time[1], gpu_ms * 1e-3, tr_launch[0], tr_nodes[0], tr_launch[1], tr_nodes[1]);
         return LPX_OK;
     }
 
@@ -545,7 +704,7 @@ struct Driver {
             emit(I, nd, LPX_BNB_INVALID, -1, 0, 0, rec);
             return;
         }
-        const std::vector<double>& x = nd.x;
+        const double* x = nd.xp ? nd.xp : nd.x.data();
         const double z = nd.z;
         const BaseProblem bp = base(nd.inst);
         // IsFeasible, IsIntegral and the branching variable were computed by the node's kernel (cta_node_epilogue)
@@ -580,8 +739,10 @@ struct Driver {
             ch->depth = nd.depth + 1;
             ch->parent_rec = rec;
             ch->ceil_child = ceil_side;
-            ch->id_path = nd.id_path;
-            ch->id_path.push_back(id);
+            if (on_node) {  // only the callback's records carry the id path
+                ch->id_path = nd.id_path;
+                ch->id_path.push_back(id);
+            }
             ch->extras = nd.extras;
             ch->extras.push_back(Extra{frac_index, ceil_side ? 1 : 0, (double)(ceil_side ? ceil_val : floor_val)});
             ch->mode = choose_mode(bp, ch->extras);
@@ -617,7 +778,8 @@ struct Driver {
             I.best = nd.z;
             I.have_best = true;
             I.best_x.resize(n);
-            for (int i = 0; i < n; i++) I.best_x[i] = round_even(nd.x[i]);
+            const double* xr = nd.xp ? nd.xp : nd.x.data();
+            for (int i = 0; i < n; i++) I.best_x[i] = round_even(xr[i]);
             emit(I, nd, LPX_BNB_INCUMBENT, -1, 0, 0, rec);
             I.finished = true;
             return;
@@ -630,69 +792,6 @@ struct Driver {
         again->parent_rec = rec;
         again->mode = nd.mode;
         I.stack.push_back(std::move(again));
-    }
-
-    // SolveNode bodies of the evaluated nodes of instances [lo, hi), on a few host threads (independent trees).
-    void commit_range(int lo, int hi) {
-        auto commit_instance = [&](Instance& I) {
-            while (!I.finished && !I.stack.empty() && I.stack.back()->evaluated) {
-                std::unique_ptr<Node> nd = std::move(I.stack.back());
-                I.stack.pop_back();
-                if (nd->is_root_lp) commit_root_lp(I, std::move(nd));
-                else commit_node(I, std::move(nd));
-            }
-            if (I.stack.empty()) I.finished = true;
-        };
-        const int nthreads = host_threads();
-        if (nthreads <= 1 || hi - lo < 16) {
-            for (int k = lo; k < hi; k++) commit_instance(inst[k]);
-            return;
-        }
-        std::atomic<int> next(lo);
-        auto worker = [&]() {
-            for (;;) {
-                const int a = next.fetch_add(8);
-                if (a >= hi) break;
-                for (int k = a; k < std::min(hi, a + 8); k++) commit_instance(inst[k]);
-            }
-        };
-        std::vector<std::thread> pool;
-        for (int t = 1; t < nthreads; t++) pool.emplace_back(worker);
-        worker();
-        for (std::thread& th : pool) th.join();
-    }
-
-    // Two halves of the batch alternate: while the GPU solves the open nodes of one half, the host commits
-    // the other half's round and stages its next one.
-    int run_pipelined() {
-        const int half = count / 2;
-        const int lo[2] = {0, half}, hi[2] = {half, count};
-        auto enqueue = [&](int g) -> int {
-            std::vector<Node*> todo;
-            for (int k = lo[g]; k < hi[g]; k++)
-                if (!inst[k].finished)
-                    for (auto& nd : inst[k].stack)
-                        if (!nd->evaluated) todo.push_back(nd.get());
-            return evaluate_async(todo, g);
-        };
-        int rc;
-        for (int g = 0; g < 2; g++)
-            if ((rc = enqueue(g)) != LPX_OK) return rc;
-        while (sets[0].active || sets[1].active) {
-            for (int g = 0; g < 2; g++) {
-                if (!sets[g].active) continue;
-                if ((rc = evaluate_finish(g)) != LPX_OK) return rc;
-                commit_range(lo[g], hi[g]);
-                if ((rc = enqueue(g)) != LPX_OK) return rc;
-            }
-        }
-        for (int g = 0; g < 2; g++)
-            if (sets[g].done) cudaEventDestroy(sets[g].done);
-        if (getenv("LPX_BNB_TRACE"))
-            fprintf(stderr, "[bnb trace] pipelined: %.3f s waiting for the GPU, %.3f s staging + enqueueing; shared-memory "
-                            "kernel %ld launches / %ld nodes / %ld pivots, cluster kernel %ld / %ld / %ld\n",
-                    tr_time[0], tr_time[1], tr_launch[0], tr_nodes[0], tr_piv[0], tr_launch[1], tr_nodes[1], tr_piv[1]);
-        return LPX_OK;
     }
 
     int run() {

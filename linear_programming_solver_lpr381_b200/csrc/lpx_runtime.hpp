@@ -11,13 +11,14 @@ namespace lpx {
 
 // Grow-only cached buffers, keyed by a small slot id, so that repeated solves do not pay
 // cudaMalloc / cudaHostAlloc every call.  Freed by lpx_shutdown().
+#define LPX_BB_SETS 4
 enum Slot {
     WS_A = 0, WS_B, WS_C, WS_REL, WS_STATUS, WS_NPIV, WS_SILENT, WS_PIVOTS, WS_BASIS, WS_X, WS_Z, WS_TABLEAU,
     WS_HISTORY, WS_NHIST, WS_SCRATCH, WS_TOTAL, WS_NODE_INST, WS_NODE_OFF, WS_NODE_CNT, WS_NODE_MODE, WS_EX_VAR,
     WS_EX_REL, WS_EX_RHS, WS_KN_ITEMS, WS_KN_ASSIGN, WS_KN_OUT, WS_KN_AUX, WS_KN_EXACT, WS_MISC0, WS_MISC1, WS_MISC2,
     WS_PL_IN, WS_PL_OUT, WS_PL_ALL,  // pooled-tree B&B: node descriptors, own results, everybody's results
-    WS_BB_IN0, WS_BB_OUT0, WS_BB_SCR0, WS_BB_IN1, WS_BB_OUT1, WS_BB_SCR1,  // pipelined B&B: two evaluation sets
-    WS_COUNT
+    WS_BB_SET0,  // pipelined B&B: descriptors, results, scratch of each of LPX_BB_SETS evaluation sets
+    WS_COUNT = WS_BB_SET0 + 3 * 4
 };
 
 struct Runtime {
