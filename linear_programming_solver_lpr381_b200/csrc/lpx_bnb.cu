@@ -422,6 +422,7 @@ struct Driver {
     std::vector<EvalSet> sets;
     bool trace_gpu = false;
     double gpu_ms = 0;
+    long long* d_prof = nullptr;  // LPX_BNB_TRACE: phase cycles of the condensed kernel, two occupancy classes x 14 slots
 
     // stage and launch the open nodes (Instance::open) of set g
     int enqueue(int g, HostPool& pool) {
@@ -437,18 +438,23 @@ struct Driver {
             for (Node* nd : inst[k].open) deepest = std::max(deepest, (int)nd->extras.size());
         if (deepest < 0) return LPX_OK;
         const bool cond = use_condensed && cta_condensed_fits(mm + deepest + 1, n);
-        E.nodes.clear();
-        std::vector<Node*> big;
+        // evaluation classes, one launch each.  Condensed: 0 / 1 = two / one CTA per SM.  Otherwise: 0 = the
+        // node's full tableau fits one SM's shared memory, 1 = cluster / global memory.
+        std::vector<Node*> cls[2];
         int max_extra[2] = {0, 0};
         for (int k = E.lo; k < E.hi; k++)
             for (Node* nd : inst[k].open) {
                 const int rows = mm + (int)nd->extras.size() + 1, width = n + rows;
                 const int kind = (cond ? cta_condensed_ctas_per_sm(rows, n) >= 2 : cta_fits_smem(rows, width)) ? 0 : 1;
-                (kind ? big : E.nodes).push_back(nd);
+                cls[kind].push_back(nd);
                 max_extra[kind] = std::max(max_extra[kind], (int)nd->extras.size());
             }
-        const int c0 = (int)E.nodes.size();
-        E.nodes.insert(E.nodes.end(), big.begin(), big.end());
+        E.nodes.clear();
+        int first[3] = {0, 0, 0};
+        for (int kind = 0; kind < 2; kind++) {
+            E.nodes.insert(E.nodes.end(), cls[kind].begin(), cls[kind].end());
+            first[kind + 1] = (int)E.nodes.size();
+        }
         const int total = E.total = (int)E.nodes.size();
         E.offs.resize((size_t)total + 1);
         size_t total_extra = 0;
@@ -497,7 +503,7 @@ struct Driver {
         double* d_z = (double*)(d_out + (size_t)total * 24);
         double* d_x = d_z + total;
         for (int kind = 0; kind < 2; kind++) {
-            const int lo = kind ? c0 : 0, cnt = kind ? total - c0 : c0;
+            const int lo = first[kind], cnt = first[kind + 1] - first[kind];
             if (cnt == 0) continue;
             const int max_rows = mm + max_extra[kind] + 1, max_width = n + max_rows;
             const size_t tsize = (size_t)max_rows * max_width;
@@ -538,6 +544,7 @@ struct Driver {
             B.node_branch = d_stat + 5 * total + lo;
             B.x = d_x + (size_t)lo * n;
             B.z = d_z + lo;
+            if (d_prof) B.dbg = d_prof + 14 * kind;
             int rc = cond ? cta_condensed_launch(B, cnt, s)
                           : cta_launch(B, cnt, opt.kernel == LPX_KERNEL_CTA_GLOBAL ? LPX_KERNEL_CTA_GLOBAL : LPX_KERNEL_AUTO,
                                        opt.threads, s, nullptr);
@@ -605,6 +612,7 @@ struct Driver {
         int rc = LPX_OK;
         LPX_CUDA(cudaStreamSynchronize(rt().stream));  // the base problems are on the device
         trace_gpu = getenv("LPX_BNB_TRACE") != nullptr;
+        if (trace_gpu && cudaMalloc(&d_prof, 28 * 8) == cudaSuccess) cudaMemset(d_prof, 0, 28 * 8);
         for (int g = 0; g < nsets; g++) {
             EvalSet& E = sets[g];
             E.lo = (int)((long long)count * g / nsets);
@@ -636,10 +644,27 @@ struct Driver {
             if (E.done) cudaEventDestroy(E.done);
             if (E.began) cudaEventDestroy(E.began);
         }
+        long long hp[28] = {0};
+        if (d_prof) {
+            cudaMemcpy(hp, d_prof, sizeof hp, cudaMemcpyDeviceToHost);
+            cudaFree(d_prof);
+            d_prof = nullptr;
+        }
         if (rc != LPX_OK) {
             if (rc == LPX_E_CUDA) set_error("lpx_bnb_simplex: CUDA error in the pipelined node evaluation");
             return rc;
         }
+        if (trace_gpu)
+            for (int kind = 0; kind < 2; kind++) {
+                const long long* h = hp + 14 * kind;
+                if (!h[13]) continue;
+                const double pp = (double)std::max(1LL, h[10]), dp = (double)std::max(1LL, h[11]), nc = (double)h[13];
+                fprintf(stderr, "[bnb trace] condensed kernel, class %d: %lld nodes, %.0f cycles each (build %.0f, between/after "
+                                "the loops %.0f); %lld primal pivots: ratios %.0f, scan %.0f, staging %.0f, update %.0f cycles; "
+                                "%lld dual pivots: leaving %.0f, entering %.0f, staging %.0f, update %.0f\n",
+                        kind, h[13], h[12] / nc, h[8] / nc, h[9] / nc, h[10], h[0] / pp, h[1] / pp, h[2] / pp, h[3] / pp,
+                        h[11], h[4] / dp, h[5] / dp, h[6] / dp, h[7] / dp);
+            }
         if (trace_gpu)
             fprintf(stderr, "[bnb trace] pipelined, %d sets: %.3f s waiting for the GPU, %.3f s staging + enqueueing, GPU busy "
                             "(sum over sets, upload to download) %.3f s; class 0: %ld launches / %ld nodes, class 1: %ld / %ld\n",

@@ -203,6 +203,23 @@ __device__ __forceinline__ int warp_margin_scan64(int count, double margin, doub
     });
 }
 
+// Wider certificate for ties.  C = the eligible ratios r with !(vmin < r - margin) — the minimum, its exact
+// ties, anything within the margin of it.  If every eligible ratio OUTSIDE C clears all of C by the margin,
+//     max(C) < min over j not in C of (r_j - margin),
+// the sequential answer is the FIRST row of C: whatever record b stands when that row c1 comes up (+inf, or a
+// ratio outside C) has r_c1 < b - margin, so c1 is accepted; after it a row k would need
+// r_k < r_c1 - margin <= vmin, which nothing satisfies.  B&B node LPs on integer data tie all the time (equal
+// bound rows, zero right-hand sides); only a ratio strictly between "tied" and "clear" falls through to the
+// replay.  Each lane passes the largest key of its C members (0 if none), the smallest key of r - margin over
+// its other eligible rows (~0 if none) and its first row in C (INT_MAX if none); returns the row, or -1.
+__device__ __forceinline__ int warp_tie_certificate(unsigned long long cmax_key, unsigned long long dmin_key, int first_in_c) {
+    const unsigned long long CM = ~warp_min_u64(~cmax_key);
+    const unsigned long long DM = warp_min_u64(dmin_key);
+    const int first = __reduce_min_sync(0xffffffffu, first_in_c);
+    if (DM == ~0ULL || dkey_inv(CM) < dkey_inv(DM)) return first;
+    return -1;
+}
+
 // Any number of candidates, read through get(i, r) -> eligible (cheap, called up to three times per
 // candidate).  Must be called by all 32 lanes of the warp.
 template <class Get>
@@ -230,6 +247,26 @@ __device__ __forceinline__ int warp_margin_scan_cert(int count, double margin, G
     const int imin = __reduce_min_sync(0xffffffffu, il);
     const int nclose = __reduce_add_sync(0xffffffffu, close);
     if (nclose == 1 && vmin < __longlong_as_double(0x7ff0000000000000LL)) return imin;
+    if (vmin < __longlong_as_double(0x7ff0000000000000LL)) {  // ties: the wider certificate
+        unsigned long long cm = 0ULL, dm = ~0ULL;
+        int ic = INT_MAX;
+        for (int i = lane; i < count; i += 32) {
+            double r;
+            if (get(i, r)) {
+                const double d = __dsub_rn(r, margin);
+                if (!(vmin < d)) {
+                    const unsigned long long k = dkey(r);
+                    cm = k > cm ? k : cm;
+                    if (i < ic) ic = i;
+                } else {
+                    const unsigned long long kd = dkey(d);
+                    dm = kd < dm ? kd : dm;
+                }
+            }
+        }
+        const int first = warp_tie_certificate(cm, dm, ic);
+        if (first >= 0) return first;
+    }
     return warp_margin_scan(count, margin, get);
 }
 
@@ -266,6 +303,24 @@ __device__ __forceinline__ int warp_margin_scan_regs(int count, double margin, c
     const int imin = __reduce_min_sync(0xffffffffu, il);
     const int nclose = __reduce_add_sync(0xffffffffu, close);
     if (nclose == 1 && vmin < __longlong_as_double(0x7ff0000000000000LL)) return imin;
+    if (vmin < __longlong_as_double(0x7ff0000000000000LL)) {  // ties: the wider certificate (see warp_tie_certificate)
+        unsigned long long cm = 0ULL, dm = ~0ULL;
+        int ic = INT_MAX;
+#pragma unroll
+        for (int s = K - 1; s >= 0; s--)
+            if (r[s] == r[s]) {
+                const double d = __dsub_rn(r[s], margin);
+                if (!(vmin < d)) {
+                    cm = k[s] > cm ? k[s] : cm;
+                    ic = lane + 32 * s;
+                } else {
+                    const unsigned long long kd = dkey(d);
+                    dm = kd < dm ? kd : dm;
+                }
+            }
+        const int first = warp_tie_certificate(cm, dm, ic);
+        if (first >= 0) return first;
+    }
     return warp_margin_scan(count, margin, [&](int i, double& rr) {
         rr = ratio[i];
         return rr == rr;

@@ -129,7 +129,7 @@ int cta_condensed_launch(const CtaBatch& B, int count, cudaStream_t stream) {
         set_error("internal: condensed tableau does not fit in shared memory");
         return LPX_E_CAPACITY;
     }
-    auto kfn = cta_condensed_kernel<512>;
+    auto kfn = B.dbg ? cta_condensed_kernel<512, true> : cta_condensed_kernel<512, false>;
     LPX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kfn<<<count, 512, smem, stream>>>(B);
     LPX_CUDA(cudaGetLastError());

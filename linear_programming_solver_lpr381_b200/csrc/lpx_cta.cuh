@@ -183,6 +183,39 @@ __device__ __forceinline__ void cta_pivot(double* T, int ld, int rows, int width
     __syncthreads();
 }
 
+// Rows i = g, g + G, .. of one pair of adjacent columns: T[i,.] -= fcol[i] * pj, row l <- pj.  The loads of four
+// rows are issued before the first store — the compiler cannot hoist a shared-memory load above the previous
+// row's store on its own, and a one-row-at-a-time loop pays the load latency once per row.  UNIT: the column
+// `which` (0 / 1, -1: neither) of the pair enters the update as the unit vector of row l (lpx_cta_cond.cuh).
+template <bool UNIT>
+__device__ __forceinline__ void cta_update_pair_column(double* t, size_t step, int g, int G, int rows, int l,
+                                                       const double2 pj, const double* fcol, int which) {
+    auto one = [&](double2 cur, double f, int i) -> double2 {
+        if (UNIT) {
+            if (which == 0) cur.x = i == l ? 1.0 : 0.0;
+            if (which == 1) cur.y = i == l ? 1.0 : 0.0;
+        }
+        if (i == l) return pj;
+        cur.x = __dsub_rn(cur.x, __dmul_rn(f, pj.x));
+        cur.y = __dsub_rn(cur.y, __dmul_rn(f, pj.y));
+        return cur;
+    };
+    int i = g;
+    for (; i + 3 * G < rows; i += 4 * G, t += 4 * step) {
+        double2 c[4];
+        double f[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            c[u] = *reinterpret_cast<const double2*>(t + u * step);
+            f[u] = fcol[i + u * G];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) *reinterpret_cast<double2*>(t + u * step) = one(c[u], f[u], i + u * G);
+    }
+    for (; i < rows; i += G, t += step)
+        *reinterpret_cast<double2*>(t) = one(*reinterpret_cast<const double2*>(t), fcol[i], i);
+}
+
 // The update alone, by the UT threads utid = 0 .. UT-1 (the control warp does not take part): prow and
 // fcol are staged already.  Same arithmetic and element order as cta_pivot.
 template <bool PAIR>
@@ -197,20 +230,7 @@ __device__ __forceinline__ void cta_update(double* T, int ld, int rows, int widt
             const int q = cw2 >= UT ? q0 + utid : utid - g * cw2;
             if (g < G && q < pairs) {
                 const double2 pj = *reinterpret_cast<const double2*>(prow + 2 * q);
-                double* t = T + (size_t)g * ld + 2 * q;
-                const size_t step = (size_t)G * ld;
-#pragma unroll 4
-                for (int i = g; i < rows; i += G, t += step) {
-                    double2 cur = *reinterpret_cast<double2*>(t);
-                    const double f = fcol[i];
-                    if (i == l) {
-                        cur = pj;
-                    } else {
-                        cur.x = __dsub_rn(cur.x, __dmul_rn(f, pj.x));
-                        cur.y = __dsub_rn(cur.y, __dmul_rn(f, pj.y));
-                    }
-                    *reinterpret_cast<double2*>(t) = cur;
-                }
+                cta_update_pair_column<false>(T + (size_t)g * ld + 2 * q, (size_t)G * ld, g, G, rows, l, pj, fcol, -1);
             }
             if (cw2 < UT) break;
         }

@@ -63,8 +63,8 @@ __host__ __device__ inline CondCarve cond_carve(int max_rows, int n) {
     return c;
 }
 
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) cta_condensed_kernel(const CtaBatch B) {
+template <int THREADS, bool PROF>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) cta_condensed_kernel(const CtaBatch B) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = THREADS / 32;
@@ -101,6 +101,20 @@ __global__ void __launch_bounds__(THREADS) cta_condensed_kernel(const CtaBatch B
     __syncthreads();
     int status = ctl[0];
     int n_piv = 0, n_silent = 0;
+    // LPX_BNB_TRACE: thread 0's clock64() per phase, summed over the launch's CTAs into B.dbg (14 slots)
+    const bool prof = PROF && B.dbg != nullptr && tid == 0;
+    __shared__ long long pc[PROF ? 10 : 1];
+    if (prof)
+        for (int k = 0; k < 10; k++) pc[k] = 0;
+    long long c0 = prof ? clock64() : 0;
+    const long long c_begin = c0;
+    int tick_base = 0, n_dual = 0;
+#define COND_TICK(slot)                 \
+    if (prof) {                         \
+        const long long c1 = clock64(); \
+        pc[slot] += c1 - c0;            \
+        c0 = c1;                        \
+    }
 
     if (status == LPX_RUNNING) {
         // ---- BuildTableau, non-basic columns only: the slack basis starts basic -----------------------
@@ -138,6 +152,7 @@ __global__ void __launch_bounds__(THREADS) cta_condensed_kernel(const CtaBatch B
             slotof[j] = j;
         }
         __syncthreads();
+        COND_TICK(8)
 
         const double* zrow = T + (size_t)m * ld;
 
@@ -174,6 +189,7 @@ __global__ void __launch_bounds__(THREADS) cta_condensed_kernel(const CtaBatch B
                 prow[j] = ddiv_by_pivot(j == e ? 1.0 : T[(size_t)l * ld + j], piv);
             if (tid == 0 && (cols & 1)) prow[cols] = 0.0;
             __syncthreads();
+            COND_TICK(tick_base + 2)
             if (warp == 0) {
                 if (with_zc) {
                     const double fz = fcol[m];
@@ -209,27 +225,13 @@ __global__ void __launch_bounds__(THREADS) cta_condensed_kernel(const CtaBatch B
                     if (g < G && q < pairs) {
                         const double2 pj = *reinterpret_cast<const double2*>(prow + 2 * q);
                         const int which = (e >> 1) == q ? (e & 1) : -1;  // this thread's pair holds slot e?
-                        double* t = T + (size_t)g * ld + 2 * q;
-                        const size_t step = (size_t)G * ld;
-#pragma unroll 4
-                        for (int i = g; i < rows; i += G, t += step) {
-                            double2 cur = *reinterpret_cast<double2*>(t);
-                            if (which == 0) cur.x = i == l ? 1.0 : 0.0;
-                            if (which == 1) cur.y = i == l ? 1.0 : 0.0;
-                            const double f = fcol[i];
-                            if (i == l) {
-                                cur = pj;
-                            } else {
-                                cur.x = __dsub_rn(cur.x, __dmul_rn(f, pj.x));
-                                cur.y = __dsub_rn(cur.y, __dmul_rn(f, pj.y));
-                            }
-                            *reinterpret_cast<double2*>(t) = cur;
-                        }
+                        cta_update_pair_column<true>(T + (size_t)g * ld + 2 * q, (size_t)G * ld, g, G, rows, l, pj, fcol, which);
                     }
                     if (cw2 < UT) break;
                 }
             }
             __syncthreads();
+            COND_TICK(tick_base + 3)
         };
 
         // primal pivots (PrimalSimplex.cs:92-124; ForceDualFeasibility, DualSimplex.cs:195-228):
@@ -248,11 +250,13 @@ __global__ void __launch_bounds__(THREADS) cta_condensed_kernel(const CtaBatch B
                 const int e = ctl[3];
                 if (e < 0) return 1;
                 cta_stage_ratios<THREADS>(T, ld, m, e, rhs, rbuf);
+                COND_TICK(0)
                 if (warp == 0) {
                     const int lv = warp_margin_scan_staged(m, margin, rbuf);
                     if (lane == 0) ctl[2] = lv;
                 }
                 __syncthreads();
+                COND_TICK(1)
                 const int l = ctl[2];
                 if (l < 0) return 2;
                 pivot(l, e, true);
@@ -268,6 +272,8 @@ __global__ void __launch_bounds__(THREADS) cta_condensed_kernel(const CtaBatch B
             status = why == 0 ? LPX_S_ITER_LIMIT : (why == 1 ? LPX_OPTIMAL : LPX_UNBOUNDED);
         }
         int iter = 1;
+        tick_base = 4;
+        COND_TICK(9)
         while (mode == 1) {
             if (iter > LPX_DUAL_MAX_ITER) {
                 status = LPX_S_ITER_LIMIT;
@@ -275,6 +281,7 @@ __global__ void __launch_bounds__(THREADS) cta_condensed_kernel(const CtaBatch B
             }
             // dual: leaving row = most negative RHS below -1e-9 (DualSimplex.cs:45-55)
             const int l = block_argmin_below_strided<THREADS>(T + rhs, (size_t)ld, m, -LPX_EPS, red);
+            COND_TICK(4)
             if (l < 0) {
                 status = LPX_OPTIMAL;
                 break;
@@ -300,12 +307,14 @@ __global__ void __launch_bounds__(THREADS) cta_condensed_kernel(const CtaBatch B
             }
             __syncthreads();
             const int e = ctl[2];
+            COND_TICK(5)
             if (e < 0) {
                 status = LPX_INFEASIBLE;
                 break;
             }
             pivot(l, e, false);
             n_piv++;
+            n_dual++;
             iter++;
         }
         __syncthreads();
@@ -328,6 +337,15 @@ __global__ void __launch_bounds__(THREADS) cta_condensed_kernel(const CtaBatch B
         if (B.z && tid == 0) B.z[p] = 0.0;
     }
 
+    if (prof) {
+        COND_TICK(9)
+        for (int k = 0; k < 10; k++) atomicAdd((unsigned long long*)B.dbg + k, (unsigned long long)pc[k]);
+        atomicAdd((unsigned long long*)B.dbg + 10, (unsigned long long)(n_piv - n_dual));
+        atomicAdd((unsigned long long*)B.dbg + 11, (unsigned long long)n_dual);
+        atomicAdd((unsigned long long*)B.dbg + 12, (unsigned long long)(clock64() - c_begin));
+        atomicAdd((unsigned long long*)B.dbg + 13, 1ULL);
+    }
+#undef COND_TICK
     if (tid == 0) {
         B.status[p] = status;
         if (B.n_pivots) B.n_pivots[p] = n_piv;
