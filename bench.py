@@ -465,12 +465,14 @@ def run_ours(args):
                "roofline": {"bound": "fp64", "achieved": ach, "peak": rate, "unit": "TFLOP/s",
                             "frac": ach / rate if rate else None, "traffic": None,
                             "peak_source": "measured in this run: unfused DMUL+DADD issue rate",
-                            "kernel": "cta_simplex_kernel / cta_cluster_simplex_kernel (all node LPs of a round in one "
-                                      "launch per kernel family)",
+                            "kernel": "cta_condensed_kernel (condensed tableau: non-basic columns + RHS; the open nodes of "
+                                      "a quarter of the instances per round, one launch per occupancy class, four "
+                                      "rounds in flight on four streams)",
                             "algorithmic_flops": flops, "gpu_seconds": gpu_s, "evaluation_rounds": rounds,
                             "note": "flops = sum over node LPs of pivots x (2 m_d (n+m_d+1) + (n+m_d+1)) at each node's "
-                                    "own shape (rank 0's instances); gpu_seconds = host wall inside the evaluation calls "
-                                    "(descriptor upload, kernels, result download, sync), rank 0"}}
+                                    "own FULL-tableau shape, SURVEY 8d's count (rank 0's instances) — the condensed kernel "
+                                    "does n+1 of those n+m+1 columns; gpu_seconds = the whole call: the GPU is busy "
+                                    "throughout, the host commits one set's round while the others run"}}
         if with_cpu:
             orc = oracle()
             k1 = min(4, count)

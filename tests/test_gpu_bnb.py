@@ -93,6 +93,43 @@ def test_bnb_batched_c4_shape(lpx, orc):
             assert_bits_equal(got["best_x"][k], want["best_x"], f"best_x {k}")
 
 
+def _check_batch(got, wants, label):
+    for k, want in enumerate(wants):
+        assert bool(got["found"][k]) == want["found"], (label, k)
+        assert got["n_nodes"][k] == want["n_nodes"], (label, k)
+        assert got["lp_pivots"][k] == want["total_pivots"], (label, k)
+        if want["found"]:
+            assert_bits_equal([got["best_z"][k]], [want["best_z"]], f"{label} best_z {k}")
+            assert_bits_equal(got["best_x"][k], want["best_x"], f"{label} best_x {k}")
+
+
+def test_bnb_batched_relations_and_sense(lpx, orc):
+    """Batches of >= 32 instances (the pipelined driver, condensed-tableau node kernel) whose root is NOT an
+    all-'<=' Max problem: '>=' and '=' rows send the root LP through Dual Simplex — silent primal pivots, then
+    the dual loop, equality rows expanded to two (DualSimplex.cs:117-158) — and Branch & Bound rejects its
+    result (Branch&Bound.cs:60-70); a Min objective negates c (PrimalSimplex.cs:62-63)."""
+    rng = np.random.Generator(np.random.PCG64(77))
+    count, m, n = 40, 6, 9
+    for rel, sense in (([0, 1, 0, 0, 0, 0], 0), ([0, 0, 2, 0, 0, 0], 0), ([1, 1, 2, 0, 0, 1], 1), ([0] * 6, 1)):
+        A = rng.integers(1, 12, size=(count, m, n)).astype(float)
+        b = rng.integers(3 * n, 12 * n, size=(count, m)).astype(float)
+        c = rng.integers(1, 15, size=(count, n)).astype(float)
+        got = lpx.bnb_simplex_batched(A, b, c, rel, sense)
+        wants = [orc.bnb_simplex(A[k], b[k], c[k], rel, sense, node_cap=1 << 16) for k in range(count)]
+        _check_batch(got, wants, f"rel {rel} sense {sense}")
+
+
+def test_bnb_batched_full_tableau_kernels(lpx, orc, monkeypatch):
+    """LPX_BNB_FULL_TABLEAU=1 keeps the pipelined driver on the full-tableau node kernels (what it uses when a
+    node's condensed tableau does not fit one SM): same trees, bit for bit."""
+    count = 32
+    As, bs, cs = zip(*[workloads.ip_c4(m=30, n=50, seed=500 + k) for k in range(count)])
+    wants = [orc.bnb_simplex(As[k], bs[k], cs[k], node_cap=1 << 16) for k in range(count)]
+    _check_batch(lpx.bnb_simplex_batched(np.stack(As), np.stack(bs), np.stack(cs)), wants, "condensed")
+    monkeypatch.setenv("LPX_BNB_FULL_TABLEAU", "1")
+    _check_batch(lpx.bnb_simplex_batched(np.stack(As), np.stack(bs), np.stack(cs)), wants, "full tableau")
+
+
 def test_bnb_node_history(lpx, orc, kat):
     case = kat["ip"]["ip_floor_path"]
     A, b, c, rel = case_arrays(case)

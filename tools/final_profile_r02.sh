@@ -16,10 +16,9 @@ ncu --set full --clock-control none --import-source on -k regex:reg_simplex -s 2
 # C3: pass and look-ahead
 python bench.py --workload large --no-extras --steps 2 --warmup 3 > $O/p2.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:stream_update_pipe_tma -s 10 -c 1 -f -o $O/prof_r02_pass python bench.py --workload large --no-extras --steps 2 --warmup 3 > $O/n2.log 2>&1
-# C4: shared-memory and cluster node kernels (control-warp design)
+# C4: condensed-tableau node kernel (control-warp design), a deep-node launch (one CTA per SM)
 python tools/profile_targets.py bnb > $O/p3.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:cta_simplex_kernel -s 12 -c 1 -f -o $O/prof_r02_cta python tools/profile_targets.py bnb > $O/n3.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:cta_cluster_simplex -s 30 -c 1 -f -o $O/prof_r02_cluster python tools/profile_targets.py bnb > $O/n4.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:cta_condensed -s 150 -c 2 -f -o $O/prof_r02_cond python tools/profile_targets.py bnb > $O/n3.log 2>&1
 # C5: device-resident knapsack search (a persistent kernel: a small node pool keeps ncu's save / restore small)
 LPX_KNAP_POOL_MB=1024 python tools/profile_targets.py knap > $O/p5.log 2>&1 && \
 LPX_KNAP_POOL_MB=1024 ncu --set full --clock-control none --import-source on -k regex:knap_search -c 1 -f -o $O/prof_r02_knap python tools/profile_targets.py knap > $O/n5.log 2>&1
@@ -27,5 +26,5 @@ LPX_KNAP_POOL_MB=1024 ncu --set full --clock-control none --import-source on -k 
 python tools/profile_targets.py pooled > $O/p6.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:cta_simplex_kernel -s 40 -c 1 -f -o $O/prof_r02_pooled python tools/profile_targets.py pooled > $O/n6.log 2>&1
 cat $O/r02_pytest.log
-for f in n0 n1 n2 n3 n4 n5 n6; do tail -n 2 $O/$f.log; done
+for f in n0 n1 n2 n3 n5 n6; do tail -n 2 $O/$f.log; done
 ls -la $O/*.ncu-rep

@@ -13,7 +13,7 @@ from linear_programming_solver_lpr381_b200 import _ffi as F, api, workloads  # n
 
 F.check(F.lib().lpx_init(0))
 what = sys.argv[1]
-if what == "bnb":  # reference-exact B&B simplex, 64 instances of 60 x 120: cta_simplex_kernel<512,1>, then the cluster kernel
+if what == "bnb":  # reference-exact B&B simplex, 64 instances of 60 x 120: cta_condensed_kernel
     As, bs, cs = zip(*[workloads.ip_c4(seed=11 + k) for k in range(64)])
     r = api.bnb_simplex_batched(np.stack(As), np.stack(bs), np.stack(cs))
     print("bnb", int(r["n_nodes"].sum()), "nodes")
