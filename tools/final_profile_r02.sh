@@ -9,7 +9,7 @@ python bench.py --workload large --no-extras --steps 5 --warmup 3 > $O/r02_bench
 python bench.py --impl reference --steps 3 --warmup 1 > $O/r02_bench_reference.json 2> $O/r02_bench_reference.err
 # launch list of the default bench command (all sections)
 python bench.py --steps 2 --warmup 3 > $O/p0.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $O/r02_launches_default.csv python bench.py --steps 2 --warmup 3 > $O/n0.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file $O/r02_launches_default.csv python bench.py --steps 2 --warmup 3 > $O/n0.log 2>&1
 # C2: register-resident batched kernel
 python bench.py --steps 2 --warmup 3 --no-extras > $O/p1.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:reg_simplex -s 2 -c 1 -f -o $O/prof_r02_reg python bench.py --steps 2 --warmup 3 --no-extras > $O/n1.log 2>&1

@@ -17,7 +17,7 @@ dev = torch.device("cuda:0")
 stream = torch.cuda.current_stream()
 
 
-def time_batched(kernel, threads=0, reg_variant=0, count=4096, m=64, n=128, reps=5):
+def time_batched(kernel, threads=0, reg_variant=0, count=4096, m=64, n=128, reps=5, max_iterations=10000):
     A, b, c = workloads.batch_c2(count=count, m=m, n=n, seed=1)
     dA, db, dc = (torch.from_numpy(v).to(dev) for v in (A, b, c))
     st = torch.zeros(count, dtype=torch.int32, device=dev)
@@ -32,7 +32,7 @@ def time_batched(kernel, threads=0, reg_variant=0, count=4096, m=64, n=128, reps
         api.primal_solve_batched_dev(count, m, n, 0, dA.data_ptr(), None, db.data_ptr(), dc.data_ptr(), st.data_ptr(),
                                      npv.data_ptr(), basis.data_ptr(), x.data_ptr(), z.data_ptr(), T.data_ptr(),
                                      tot.data_ptr(), stream.cuda_stream, kernel=kernel, threads=threads,
-                                     reg_variant=reg_variant)
+                                     reg_variant=reg_variant, max_iterations=max_iterations)
     for _ in range(3):
         launch()
     torch.cuda.synchronize()
