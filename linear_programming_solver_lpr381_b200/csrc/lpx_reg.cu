@@ -51,12 +51,25 @@ struct RegBatch {
 // Column slots 0..CR-1 of every thread are registers, slots CR..CR+CS-1 live in shared memory
 // (lane-interleaved, conflict-free): CS = 0 is the all-register build (one CTA per SM), CS = 2 leaves
 // room for two CTAs per SM without spilling, so one CTA's narrow phases hide behind the other's update.
-template <int NW, int R, int CR, int CS, int OCC, bool DBG = false>
+//
+// COND = the CONDENSED tableau (see lpx_cta_cond.cuh for the argument): only the n non-basic columns are held
+// and updated — the m basic columns are exact unit vectors (+0 / 1: every primal pivot element is positive)
+// that no decision reads.  A pivot on (row l, slot e) hands slot e to the leaving variable, whose unit
+// column goes through the same update as every other column (0 - f * (1 / piv), row l <- 1 / piv); ties of
+// ChooseEntering go to the lowest VARIABLE index (s_nbvar).  A 64 x 128 problem then needs four column slots
+// instead of six, which is what lets three CTAs share an SM; the full tableau the caller gets is put back
+// together on the way out (non-basic columns scattered to their variables' places through a row buffer in
+// shared memory, basic columns written as unit vectors), bit for bit what the full-width kernel holds.
+template <int NW, int R, int CR, int CS, int OCC, bool DBG = false, bool COND = false>
 __global__ void __launch_bounds__((NW + 1) * 32, OCC) reg_simplex_kernel(const RegBatch B) {
     constexpr int C = CR + CS;
     constexpr int ROWS = NW * R;   // padded constraint rows (>= m)
-    constexpr int COLS = 32 * C;   // padded non-RHS columns (>= n + m)
+    constexpr int COLS = 32 * C;   // padded non-RHS columns (>= n + m; COND: >= n)
+    constexpr int RBW = COND ? 32 * C + ((ROWS + 31) & ~31) + 32 : 0;  // COND: one full-width row per warp
+    static_assert(!COND || COLS <= 256, "slot index packed into 8 bits");
     extern __shared__ __align__(16) double s_t[];  // (CS ? CS : 1) * (ROWS + 1) * 32: [slot][row][lane]; row ROWS = objective row
+                                                   // COND: followed by (NW + 1) * RBW doubles of row buffers
+    __shared__ int s_nbvar[COND ? COLS : 1];       // COND: the variable held by each column slot
     constexpr int NT = (NW + 1) * 32;
     static_assert(ROWS >= 64 && ROWS <= 96, "the control warp holds the RHS of rows lane and lane+32");
     __shared__ double s_f[ROWS];     // entering column = update factors
@@ -101,7 +114,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, OCC) reg_simplex_kernel(const R
             if (!ctl) {
                 if (i < m) {
                     if (j < n) v = Ap[(size_t)i * n + j];
-                    else if (j == n + i) v = 1.0;
+                    else if (!COND && j == n + i) v = 1.0;
                 }
             } else if (r == 0 && j < n) {
                 double cj = cp[j];
@@ -119,6 +132,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, OCC) reg_simplex_kernel(const R
     // the reference's up-front check (PrimalSimplex.cs:73-76); '>=' rows cannot occur here
     if (tid == 0) s_ctl[1] = LPX_RUNNING;
     for (int i = tid; i < m; i += NT) s_basis[i] = n + i;
+    if (COND)
+        for (int j = tid; j < COLS; j += NT) s_nbvar[j] = j;
     __syncthreads();
     if (ctl && (rhs0 < -1e-9 || rhs1 < -1e-9)) s_ctl[1] = LPX_S_NEG_RHS;
     __syncthreads();
@@ -141,8 +156,12 @@ __global__ void __launch_bounds__((NW + 1) * 32, OCC) reg_simplex_kernel(const R
             int jl = INT_MAX;
 #pragma unroll
             for (int c = C - 1; c >= 0; c--)
-                if (kk[c] == K) jl = lane + 32 * c;
-            const int j = __reduce_min_sync(0xffffffffu, jl);
+                if (kk[c] == K) {
+                    if (COND) jl = min(jl, (s_nbvar[lane + 32 * c] << 8) | (lane + 32 * c));  // lowest VARIABLE wins
+                    else jl = lane + 32 * c;
+                }
+            int j = __reduce_min_sync(0xffffffffu, jl);
+            if (COND) j &= 255;
             // one word tells every warp how the next pass starts: the column, -1 = optimal, -2 = the
             // reference's iteration limit, which it tests BEFORE looking for an entering column
             if (lane == 0) s_ctl[0] = next_iter > B.max_iter ? -2 : (K == ~0ULL ? -1 : j);
@@ -229,7 +248,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, OCC) reg_simplex_kernel(const R
             __syncthreads();  // (D)
             // ---- P5: one division per thread ------------------------------------------------------
             if (tid < COLS) {
-                s_p[tid] = ddiv_by_pos(s_raw[tid], piv);
+                s_p[tid] = ddiv_by_pos((COND && tid == e) ? 1.0 : s_raw[tid], piv);  // COND: the leaving variable's unit column
             } else if (ctl) {
                 const double rl_rhs = __shfl_sync(0xffffffffu, lr < 32 ? rhs0 : rhs1, lr & 31);
                 prhs = ddiv_by_pos(rl_rhs, piv);
@@ -241,14 +260,37 @@ __global__ void __launch_bounds__((NW + 1) * 32, OCC) reg_simplex_kernel(const R
             // leaving row pays for the "this row becomes the pivot row" select.
             if (ctl) {
 #pragma unroll
-                for (int c = 0; c < C; c++) T_SET(0, c, __dsub_rn(T_GET(0, c), __dmul_rn(fz, s_p[lane + 32 * c])));
+                for (int c = 0; c < C; c++) {
+                    double cur = T_GET(0, c);
+                    if (COND && c == ce && lane == le) cur = 0.0;
+                    T_SET(0, c, __dsub_rn(cur, __dmul_rn(fz, s_p[lane + 32 * c])));
+                }
+                if (COND) {  // slot e now holds the leaving variable
+                    if (lane == 0) {
+                        const int ve = s_nbvar[e];
+                        s_nbvar[e] = s_basis[lr];
+                        s_basis[lr] = ve;
+                    }
+                    __syncwarp();
+                }
                 choose_entering(iter + 1);
                 const double u0 = __dsub_rn(rhs0, __dmul_rn(a0, prhs)), u1 = __dsub_rn(rhs1, __dmul_rn(a1, prhs));
                 rhs0 = lane == lr ? prhs : u0;
                 rhs1 = lane + 32 == lr ? prhs : u1;
                 zrhs = __dsub_rn(zrhs, __dmul_rn(fz, prhs));
-                if (lane == 0) s_basis[lr] = e;
+                if (!COND && lane == 0) s_basis[lr] = e;
             } else {
+                if (COND) {  // slot e enters the update as the leaving variable's unit column: zero outside row lr
+#define REG_ZERO(K)                                                              \
+    if (K < C && ce == K) {                                                      \
+        asm volatile("" ::: "memory");                                           \
+        if (lane == le) {                                                        \
+            _Pragma("unroll") for (int r = 0; r < R; r++) T_SET(r, K, 0.0);      \
+        }                                                                        \
+    }
+                    REG_ZERO(0) else REG_ZERO(1) else REG_ZERO(2) else REG_ZERO(3) else REG_ZERO(4) else REG_ZERO(5) else REG_ZERO(6) else REG_ZERO(7)
+#undef REG_ZERO
+                }
                 if (CS != 0) {
 #pragma unroll
                     for (int r = 0; r < R; r++) f[r] = s_f[w * R + r];
@@ -282,7 +324,34 @@ __global__ void __launch_bounds__((NW + 1) * 32, OCC) reg_simplex_kernel(const R
             s_rhs[lane + 32] = rhs1;
             if (lane == 0) s_rhs[ROWS] = zrhs;
         }
-        if (B.tableau) {
+        if (B.tableau && COND) {
+            // the full-width rows, put together in this warp's row buffer: zeros, the non-basic entries at their
+            // variables' columns, the row's own basic variable = 1; then one coalesced copy
+            double* To = B.tableau + (size_t)p * (m + 1) * width;
+            double* rb = s_t + (size_t)(CS ? CS : 1) * (ROWS + 1) * 32 + (size_t)w * RBW;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int i = ctl ? m : w * R + r;
+                if (ctl ? r == 0 : i < m) {
+                    for (int k = lane; k < RBW; k += 32) rb[k] = 0.0;
+                    __syncwarp();
+#pragma unroll
+                    for (int c = 0; c < C; c++) {
+                        const int j = lane + 32 * c;
+                        if (j < n) rb[s_nbvar[j]] = T_GET(r, c);
+                    }
+                    if (!ctl && lane == 0) rb[s_basis[i]] = 1.0;
+                    __syncwarp();
+                    for (int j = lane; j < width - 1; j += 32) To[(size_t)i * width + j] = rb[j];
+                    __syncwarp();
+                }
+            }
+            if (ctl) {
+                if (lane < m) To[(size_t)lane * width + width - 1] = rhs0;
+                if (lane + 32 < m) To[(size_t)(lane + 32) * width + width - 1] = rhs1;
+                if (lane == 0) To[(size_t)m * width + width - 1] = zrhs;
+            }
+        } else if (B.tableau) {
             double* To = B.tableau + (size_t)p * (m + 1) * width;
             if (!ctl) {
 #pragma unroll
@@ -374,9 +443,9 @@ int reg_launch_batched(int count, int m, int n, int sense, const double* A, cons
     B.z = z;
     B.tableau = tableau;
     B.total_pivots = total_pivots;
-    // Two builds: all six column slots in registers, one CTA per SM (reg_variant = 1), or four in
-    // registers + two in shared memory at 72 registers without spills, two CTAs per SM (default:
-    // 1.08 ms vs 1.34 ms per 4096-LP batch).
+    // Builds: the condensed tableau at three CTAs per SM (reg_variant 4, the default for n <= 128); the full tableau
+    // with all six column slots in registers, one CTA per SM (1), four in registers + two in shared memory, two CTAs
+    // per SM (2: 1.04 ms per 4096-LP batch, against 1.34 for 1), or two + four at three CTAs per SM (3: 1.19 ms).
     B.dbg = nullptr;
     static const bool stamps = getenv("LPX_REG_STAMPS") != nullptr;  // measurement aid, prints to stderr
     if (stamps) {
@@ -404,9 +473,22 @@ int reg_launch_batched(int count, int m, int n, int sense, const double* A, cons
         count_launch();
         return LPX_OK;
     }
-    if (opt.reg_variant == 1) {
+    // Default: the condensed build, three CTAs per SM (n <= 128 columns of A; wider problems keep the six-slot build).
+    const int variant = opt.reg_variant ? opt.reg_variant : (n <= 128 ? 4 : 2);
+    if (variant == 4) {
+        if (n > 128) {
+            set_error("LPX_KERNEL_CTA_REG, reg_variant 4: the condensed build holds n <= 128 non-basic columns");
+            return LPX_E_CAPACITY;
+        }
+        // 11 row warps x 6 rows, four column slots (two in registers, two in shared memory) + one row buffer per warp
+        constexpr size_t smem4 = (size_t)2 * (11 * 6 + 1) * 32 * 8 + (size_t)12 * (128 + 96 + 32) * 8;
+        auto k4 = reg_simplex_kernel<11, 6, 2, 2, 3, false, true>;
+        static const bool ok4 = cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4) == cudaSuccess;
+        if (!ok4) return cuda_fail(cudaGetLastError(), "cudaFuncSetAttribute(reg_simplex_kernel<11,6,2,2,3,cond>)", __FILE__, __LINE__);
+        k4<<<count, 12 * 32, smem4, stream>>>(B);
+    } else if (variant == 1) {
         reg_simplex_kernel<13, 5, 6, 0, 1><<<count, 14 * 32, reg_smem(13, 5, 0), stream>>>(B);
-    } else if (opt.reg_variant == 3) {
+    } else if (variant == 3) {
         // three CTAs per SM: 11 row warps x 6 rows, two of the six column slots in registers (56 registers), four
         // in shared memory (67 KB per CTA)
         static const bool ok3 = cudaFuncSetAttribute(reg_simplex_kernel<11, 6, 2, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,

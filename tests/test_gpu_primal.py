@@ -229,12 +229,18 @@ def test_wide_and_tall_shapes(lpx, orc):
             compare_primal(got, want, f"{m}x{n} kernel={kernel}")
 
 
-@pytest.mark.parametrize("reg_variant", [1, 2])
+@pytest.mark.parametrize("reg_variant", [0, 1, 2, 3, 4])
 def test_register_resident_kernel(lpx, orc, reg_variant):
-    """LPX_KERNEL_CTA_REG on every shape class it serves, against the oracle, bit for bit."""
+    """LPX_KERNEL_CTA_REG on every shape class it serves, against the oracle, bit for bit: the full-tableau
+    builds (1, 2, 3), the condensed build (4: non-basic columns only, the full tableau put back together on the
+    way out) and the default choice between them (0)."""
     rng = np.random.default_rng(17)
-    shapes = [(64, 128), (64, 100), (60, 120), (10, 20), (1, 1), (33, 7), (64, 1), (5, 187)]
+    shapes = [(64, 128), (64, 100), (60, 120), (10, 20), (1, 1), (33, 7), (64, 1), (5, 187), (40, 128), (64, 127)]
     for (m, n) in shapes:
+        if reg_variant == 4 and n > 128:  # the condensed build holds n <= 128 columns and says so
+            with pytest.raises(F.LpxError):
+                lpx.primal_solve_batched(*workloads.batch_c2(count=2, m=m, n=n, seed=1), kernel=F.KERNEL_CTA_REG, reg_variant=4)
+            continue
         for kind, sense in (("integer", 0), ("decimal", 0), ("integer", 1)):
             A, b, c = workloads.batch_c2(count=24, m=m, n=n, seed=3 + m + n, kind=kind)
             if sense == 1:
@@ -276,7 +282,7 @@ BEALE_B = np.array([0.0, 0.0, 1.0])
 BEALE_C = np.array([0.75, -20.0, 0.5, -6.0])
 
 
-@pytest.mark.parametrize("reg_variant", [1, 2])
+@pytest.mark.parametrize("reg_variant", [1, 2, 4])
 def test_register_kernel_near_ties_and_signed_zeros(lpx, orc, reg_variant):
     """The certified shortcut of the leaving-row scan must hand ties, near-ties inside the 1e-9
     margin, zero ratios and -0.0 / +0.0 pairs to the exact replay (PrimalSimplex.cs:222-243)."""

@@ -9,7 +9,7 @@ from gpu_probe import time_batched
 from linear_programming_solver_lpr381_b200 import _ffi as F, api, workloads
 A, b, c = workloads.batch_c2(count=256, seed=3)
 ref = api.primal_solve_batched(A, b, c, kernel=F.KERNEL_CTA_REG, reg_variant=2)
-for rv in (1, 2, 3):
+for rv in (1, 2, 3, 4):
     got = api.primal_solve_batched(A, b, c, kernel=F.KERNEL_CTA_REG, reg_variant=rv)
     same = got["tableau"].tobytes() == ref["tableau"].tobytes() and np.array_equal(got["n_pivots"], ref["n_pivots"])
     print("reg_variant", rv, "bit-identical" if same else "MISMATCH", time_batched(F.KERNEL_CTA_REG, reg_variant=rv), flush=True)
