@@ -3,8 +3,9 @@
 //
 // GPU node pool: every LP relaxation (the ~100 % hot spot, Branch&Bound.cs:57,148) is a node
 // descriptor "base problem + unit rows"; all open nodes of all instances of a batch whose
-// relaxations are not known yet are solved in ONE launch of the per-CTA kernels (lpx_cta.cuh),
-// primal and dual nodes mixed.  A relaxation is a pure function of its node, so nodes are
+// relaxations are not known yet are solved in ONE launch of the per-CTA kernels (lpx_cta.cuh; batches
+// without a callback: the condensed-tableau kernel, lpx_cta_cond.cuh, a quarter of the instances per
+// launch so that four rounds are in flight), primal and dual nodes mixed.  A relaxation is a pure function of its node, so nodes are
 // evaluated speculatively (both children at once) and then COMMITTED ON THE HOST IN THE
 // REFERENCE'S ORDER (depth-first, ceil child first), which keeps incumbents, pruning decisions
 // and node numbering identical to the recursive C# code.
