@@ -18,6 +18,6 @@ def run(count, kind, n=2000, reps=2):
     ev = int(r["n_evals"].sum())
     print(f"{kind:13s} count={count:4d}: {ev:9d} evals (max {int(r['n_evals'].max())}) in {best*1e3:8.2f} ms = {ev/best/1e6:7.3f} M nodes/s", flush=True)
 
-for kind, counts in (("uncorrelated", (1, 16, 148, 592, 2368)), ("weak", (1, 16, 148, 592)), ("fractional", (1, 16, 148))):
+for kind, counts in (("uncorrelated", (1, 16, 148, 592, 2368)), ("weak", (1, 16, 148, 592)), ("fractional", (1, 16, 148, 592, 1184))):
     for c in counts:
         run(c, kind)
