@@ -321,6 +321,8 @@ extern "C" int lpx_bnb_pooled(int m, int n, int sense, const double* A, const in
     }
 
     std::vector<PNode*> sel;
+    long long rounds_big = 0, nodes_big = 0;
+    int deepest_rows = 0;
     double tr[3] = {0, 0, 0};  // LPX_POOLED_TRACE=1: seconds selecting + staging | launch .. results on the host | committing
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
@@ -375,6 +377,11 @@ extern "C" int lpx_bnb_pooled(int m, int n, int sense, const double* A, const in
             my_max_rows = std::max(my_max_rows, nd->rows);
             any_big = any_big || !cta_fits_smem(nd->rows, n + nd->rows);
         }
+        if (any_big) {
+            rounds_big++;
+            nodes_big += mine;
+        }
+        deepest_rows = std::max(deepest_rows, my_max_rows);
         const auto t1 = now();
         if (mine > 0) {
             LPX_CUDA(cudaMemcpyAsync(d_warm, h_warm, (size_t)mine * sizeof(WarmNode), cudaMemcpyHostToDevice, s));
@@ -412,7 +419,7 @@ extern "C" int lpx_bnb_pooled(int m, int n, int sense, const double* A, const in
     }
     if (getenv("LPX_POOLED_TRACE"))
         fprintf(stderr, "[pooled trace] rank %d of %d: %lld rounds, %lld nodes: select + stage %.3f s, launch .. results on the host "
-                        "%.3f s, commit %.3f s\n", rank, world, rounds, evaluated, tr[0], tr[1], tr[2]);
+                        "%.3f s, commit %.3f s; %lld rounds (%lld of this rank's nodes) on the global-memory kernel, deepest node %d rows\n", rank, world, rounds, evaluated, tr[0], tr[1], tr[2], rounds_big, nodes_big, deepest_rows);
     if (found) *found = have_best ? 1 : 0;
     if (best_z) *best_z = best;
     if (best_x && have_best)
