@@ -406,7 +406,7 @@ def run_ours(args):
                 "peak_source": "measured in this run: unfused DMUL+DADD issue rate (lpx_measure_fp64_rate); FMA is "
                                "excluded by the bit-exactness contract",
                 "flops_per_pivot": flops_per_pivot,
-                "kernel": "reg_simplex_kernel<11,6,2,2,3,cond>: one CTA per LP, three per SM, the CONDENSED tableau (n non-basic "
+                "kernel": "reg_simplex_kernel<8,8,2,2,3,cond>: one CTA per LP, three per SM, the CONDENSED tableau (n non-basic "
                           "columns + RHS) in registers / shared memory; the full tableau is put back together on the way out",
                 "note": "flops_per_pivot is SURVEY 8d's count for the reference's FULL (m+1) x (n+m+1) tableau; the condensed "
                         "kernel executes (n+1)/(n+m+1) of them — the m basic columns are unit vectors nobody has to update",
