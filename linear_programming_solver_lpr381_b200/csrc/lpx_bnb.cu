@@ -843,7 +843,7 @@ struct Driver {
         }
         const bool want_history = (flags & LPX_BNB_WANT_HISTORY) && on_node;
         use_condensed = opt.kernel == LPX_KERNEL_AUTO && !std::getenv("LPX_BNB_FULL_TABLEAU");
-        if (!on_node && count >= 32) return run_pipelined();
+        if (!on_node) return run_pipelined();  // no callback: nobody needs a node's tableaux
         while (true) {
             std::vector<Node*> todo;
             for (Instance& I : inst)
@@ -860,10 +860,9 @@ struct Driver {
             }
             int rc = evaluate(todo, want_history);
             if (rc != LPX_OK) return rc;
-            // SolveNode bodies of the evaluated nodes.  Instances are independent trees, so without a
-            // callback (whose records must arrive in order on the calling thread) they commit on a few
-            // host threads: IsFeasible alone is m x n multiplies per node.
-            auto commit_instance = [&](Instance& I) {
+            // SolveNode bodies of the evaluated nodes, on the calling thread: the callback's records must arrive in
+            // the reference's order (calls without a callback take run_pipelined)
+            for (Instance& I : inst) {
                 while (!I.finished && !I.stack.empty() && I.stack.back()->evaluated) {
                     std::unique_ptr<Node> nd = std::move(I.stack.back());
                     I.stack.pop_back();
@@ -871,23 +870,6 @@ struct Driver {
                     else commit_node(I, std::move(nd));
                 }
                 if (I.stack.empty()) I.finished = true;
-            };
-            const int nthreads = (on_node || count < 32) ? 1 : host_threads();
-            if (nthreads <= 1) {
-                for (Instance& I : inst) commit_instance(I);
-            } else {
-                std::atomic<int> next(0);
-                auto worker = [&]() {
-                    for (;;) {
-                        const int lo = next.fetch_add(8);
-                        if (lo >= count) break;
-                        for (int k = lo; k < std::min(count, lo + 8); k++) commit_instance(inst[k]);
-                    }
-                };
-                std::vector<std::thread> pool;
-                for (int t = 1; t < nthreads; t++) pool.emplace_back(worker);
-                worker();
-                for (std::thread& th : pool) th.join();
             }
         }
         return LPX_OK;
@@ -947,7 +929,7 @@ int lpx_bnb_simplex_batched(int count, int m, int n, int sense, const double* A,
     g_last_stats[0] = 0;
     g_last_stats[2] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_run).count();
     // pipelined batches keep the GPU busy for the whole search: its seconds are the call's
-    g_last_stats[1] = (!on_node && count >= 32) ? g_last_stats[2] : d.tr_time[0] + d.tr_time[1];
+    g_last_stats[1] = !on_node ? g_last_stats[2] : d.tr_time[0] + d.tr_time[1];
     g_last_stats[3] = (double)(d.tr_launch[0] + d.tr_launch[1]);
     for (int k = 0; k < count; k++) g_last_stats[0] += d.inst[k].lp_flops;
     for (int k = 0; k < count; k++) {

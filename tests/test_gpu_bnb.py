@@ -104,7 +104,7 @@ def _check_batch(got, wants, label):
 
 
 def test_bnb_batched_relations_and_sense(lpx, orc):
-    """Batches of >= 32 instances (the pipelined driver, condensed-tableau node kernel) whose root is NOT an
+    """Batches without a callback (the pipelined driver, condensed-tableau node kernel) whose root is NOT an
     all-'<=' Max problem: '>=' and '=' rows send the root LP through Dual Simplex — silent primal pivots, then
     the dual loop, equality rows expanded to two (DualSimplex.cs:117-158) — and Branch & Bound rejects its
     result (Branch&Bound.cs:60-70); a Min objective negates c (PrimalSimplex.cs:62-63)."""
