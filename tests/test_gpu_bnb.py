@@ -21,6 +21,45 @@ def test_bnb_kat(lpx, kat, name):
         assert_bits_equal(r["best_x"], unhex(case["best_x"]), "best_x")
 
 
+@pytest.mark.parametrize("name", ["ip_floor_path", "ip_integral_root", "ip_with_ge_root", "ip_three_vars"])
+def test_bnb_kat_without_callback(lpx, kat, name):
+    """The same known-answer cases as ONE tree without a callback: the pipelined driver and the condensed-tableau
+    node kernel, down to an integral root and a root that Dual Simplex has to take."""
+    case = kat["ip"][name]
+    A, b, c, rel = case_arrays(case)
+    traced = lpx.bnb_simplex(A, b, c, rel, case["sense"], trace=True)
+    r = lpx.bnb_simplex(A, b, c, rel, case["sense"])
+    assert r["found"] == case["found"]
+    assert r["n_nodes"] == len(case["node_outcomes"]) and r["lp_pivots"] == traced["lp_pivots"]
+    if case["found"]:
+        assert_bits_equal([r["best_z"]], [unhex(case["best_z"])], "best_z")
+        assert_bits_equal(r["best_x"], unhex(case["best_x"]), "best_x")
+
+
+def test_bnb_single_trees_without_callback(lpx, orc):
+    """One tree per call, no callback (1 .. 5 instances per call as well): unbounded, infeasible-by-rounding and
+    ordinary instances against the oracle."""
+    rng = np.random.default_rng(32)
+    for t in range(20):
+        m, n = int(rng.integers(2, 7)), int(rng.integers(2, 9))
+        A = rng.integers(-2, 12, size=(m, n)).astype(float)
+        b = rng.integers(5, 80, size=m).astype(float)
+        c = rng.integers(-3, 15, size=n).astype(float)
+        want = orc.bnb_simplex(A, b, c, node_cap=1 << 16)
+        got = lpx.bnb_simplex(A, b, c)
+        assert got["found"] == want["found"] and got["n_nodes"] == want["n_nodes"], t
+        assert got["lp_pivots"] == want["total_pivots"], t
+        if want["found"]:
+            assert_bits_equal([got["best_z"]], [want["best_z"]], f"best_z {t}")
+            assert_bits_equal(got["best_x"], want["best_x"], f"best_x {t}")
+    for count in (2, 3, 5):
+        A = rng.integers(1, 12, size=(count, 5, 7)).astype(float)
+        b = rng.integers(10, 80, size=(count, 5)).astype(float)
+        c = rng.integers(1, 15, size=(count, 7)).astype(float)
+        got = lpx.bnb_simplex_batched(A, b, c)
+        _check_batch(got, [orc.bnb_simplex(A[k], b[k], c[k], node_cap=1 << 16) for k in range(count)], f"count {count}")
+
+
 def compare_bnb(got, want, what):
     assert got["found"] == want["found"], what
     assert got["n_nodes"] == want["n_nodes"], what
